@@ -1,0 +1,183 @@
+/*
+ * fdsb200.h -- C ABI of the B200 finite-difference step engine (libfdsb200.so).
+ *
+ * This is the drop-in boundary for the time-stepping hot path of emtpb/pyfds. The reference has no
+ * FFI of its own: the seam is the template-method contract of `Field` (pyfds/fields.py:59-95) --
+ * `assemble_matrices()` builds scipy DIA operators, `sim_step()` applies them, `simulate()` loops.
+ * Each entry point below names the reference code it replaces. Plain pointers and sizes only; all
+ * host buffers are borrowed for the duration of the call; device memory belongs to the context.
+ *
+ * Every function returns 0 on success and a non-zero code on failure; the message is available from
+ * fds_last_error(). Nothing here falls back to the CPU: without a CUDA device fds_create() fails.
+ *
+ * Cell addressing: a context owns `rows` consecutive grid rows starting at global row `row0` of an
+ * nx-wide grid (a y-slab; the whole grid on one GPU). A *local cell index* is
+ * `x + (y - row0) * nx`; indices in [-halo_rows*nx, 0) and [rows*nx, (rows+halo_rows)*nx) address the
+ * neighbour slabs' rows kept as halo. 1-D models use ny = rows = 1.
+ */
+#ifndef FDSB200_H
+#define FDSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fds_ctx fds_ctx;
+
+/* Physical model = which `sim_step` is executed. */
+enum fds_model {
+    FDS_ACOUSTIC1D = 1,   /* pyfds/acoustics.py:40-52   */
+    FDS_ACOUSTIC2D = 2,   /* pyfds/acoustics.py:111-128 */
+    FDS_ACOUSTIC3DAXI = 3,/* pyfds/acoustics.py:205-225 */
+    FDS_THERMAL1D = 4,    /* pyfds/thermal.py:40-51     */
+    FDS_THERMAL2D = 5,    /* pyfds/thermal.py:92-107    */
+    FDS_THERMAL3DAXI = 6  /* pyfds/thermal.py:160-176   */
+};
+
+/* Field components in device order: the scalar quantity and the two staggered vector components. */
+enum fds_component {
+    FDS_COMP_S = 0,  /* pressure / temperature            */
+    FDS_COMP_X = 1,  /* velocity(_x) / heat_flux(_x)      */
+    FDS_COMP_Y = 2   /* velocity_y / heat_flux_y (2-D)    */
+};
+
+/* Per-material coefficient tables (index = material id, id 0 = "void": all zero, used for padding).
+ * They hold what `assemble_matrices` puts on the operator diagonals (pyfds/acoustics.py:27-38,
+ * 89-109,178-203; pyfds/thermal.py:30-38,75-90,139-158), evaluated on the host with the reference's
+ * NumPy expressions so that every coefficient has identical bits. */
+enum fds_table {
+    FDS_TAB_GX = 0,  /* a_vx_p factor  dt/dx/rho           | thermal: Kx = 1/dx*kx (a_qx_t)          */
+    FDS_TAB_GY = 1,  /* a_vy_p factor  dt/dy/rho           | thermal: Ky = 1/dy*ky (a_qy_t)          */
+    FDS_TAB_FX = 2,  /* a_p_vx factor  dt/dx*c^2*rho       | thermal: Ax = dt/dx/rho/cp (a_t_qx)     */
+    FDS_TAB_FY = 3,  /* a_p_vy factor  dt/dy*c^2*rho       | thermal: Ay = dt/dy/rho/cp (a_t_qy)     */
+    FDS_TAB_VM1 = 4, /* a_vx_vx diagonal at offset -1  (0 + dt/dx^2*mu/rho)                         */
+    FDS_TAB_VP1 = 5, /* a_vx_vx diagonal at offset +1                                                */
+    FDS_TAB_VMN = 6, /* a_vx_vx diagonal at offset -nx (0 + dt/dy^2*mu/rho)                         */
+    FDS_TAB_VPN = 7, /* a_vx_vx diagonal at offset +nx                                               */
+    FDS_TAB_V0 = 8,  /* a_vx_vx main diagonal (0 + -2*Hx) + -2*Hy                                    */
+    FDS_TAB_EB = 9,  /* axisymmetric: dt*mu/rho of the extra vx/r^2 term (pyfds/acoustics.py:213-215)*/
+    FDS_TAB_COUNT = 10
+};
+
+/* Per-(material, column) tables of the axisymmetric models, where 1/r enters the coefficient
+ * (pyfds/acoustics.py:181-201, pyfds/thermal.py:141-143). Layout [n_materials + 1][nx]. */
+enum fds_column_table {
+    FDS_CTAB_FX = 0,  /* a_p_vx / a_t_qx factor divided by r */
+    FDS_CTAB_VM1 = 1, /* a_vx_vx offset -1 diagonal incl. the central-difference 1/r term */
+    FDS_CTAB_VP1 = 2, /* a_vx_vx offset +1 diagonal incl. the central-difference 1/r term */
+    FDS_CTAB_COUNT = 3
+};
+
+/* Per-column vectors of the axisymmetric models (`_radii`, pyfds/acoustics.py:166-176). */
+enum fds_column_vector {
+    FDS_CVEC_R = 0,   /* r  = x + dx/2 */
+    FDS_CVEC_RR = 1,  /* r*r           */
+    FDS_CVEC_COUNT = 2
+};
+
+typedef struct fds_desc {
+    int32_t model;        /* enum fds_model */
+    int32_t device;       /* CUDA device ordinal */
+    int64_t nx;           /* samples along x = row length */
+    int64_t ny;           /* global number of rows (1 for 1-D models) */
+    int64_t row0;         /* first grid row owned by this context */
+    int64_t rows;         /* number of rows owned */
+    int32_t halo_rows;    /* rows of neighbour data kept on either side (0 on a single GPU) */
+    int32_t lossy;        /* non-zero if any material has absorption_coef != 0 (acoustic models) */
+    int32_t n_materials;  /* real materials, ids 1..n_materials (<= 63) */
+    int32_t kernel;       /* 0 = automatic, 1 = force the one-step reference kernel, 2 = force the
+                             streaming multi-step kernel (fails if the model/grid does not support it) */
+} fds_desc;
+
+/* --- life cycle ------------------------------------------------------------------------------ */
+
+/* Allocates all device state for one slab (zero-initialised). Replaces the implicit state held by
+ * `FieldComponent.values` (pyfds/fields.py:585) and the matrices of `assemble_matrices`. */
+int fds_create(const fds_desc *desc, fds_ctx **out);
+void fds_destroy(fds_ctx *ctx);
+/* Message of the last failure on this context (or of the last failed fds_create if ctx is NULL). */
+const char *fds_last_error(const fds_ctx *ctx);
+/* Number of CUDA devices visible (0 if the driver is missing); never fails. */
+int fds_device_count(void);
+
+/* --- setup: what `assemble_matrices()` produces (pyfds/acoustics.py:89-109 etc.) ------------- */
+
+/* Material id of every local cell, halo rows included: n = (rows + 2*halo_rows) * nx entries starting
+ * at local cell -halo_rows*nx. Replaces `Field.material_vector` painting (pyfds/fields.py:34-57). */
+int fds_upload_material_map(fds_ctx *ctx, const uint8_t *ids, int64_t n);
+/* One per-material table: n = n_materials + 1 doubles (entry 0 is the void material). */
+int fds_upload_table(fds_ctx *ctx, int32_t table, const double *values, int64_t n);
+/* One per-(material, column) table: n = (n_materials + 1) * nx doubles. */
+int fds_upload_column_table(fds_ctx *ctx, int32_t table, const double *values, int64_t n);
+/* One per-column vector: n = nx doubles. */
+int fds_upload_column_vector(fds_ctx *ctx, int32_t vec, const double *values, int64_t n);
+
+/* --- boundaries and sources: `FieldComponent.apply_bounds` + `Boundary.apply`
+ *     (pyfds/fields.py:591-600, pyfds/regions.py:125-145) -------------------------------------- */
+
+/* Boundary operations of one component in CSR form: `cells` are the n_cells distinct local cell
+ * indices (ascending) that carry at least one operation; the operations of cells[k] are
+ * offsets[k] .. offsets[k+1]-1, stored in the order of the component's `boundaries` list. Operation o
+ * computes  v = alpha[o] * v + (signal[o] < 0 ? value[o] : signals[signal[o]][step]).
+ * Cells in halo rows must be included (they are recomputed redundantly). */
+int fds_upload_boundaries(fds_ctx *ctx, int32_t component, const int64_t *cells,
+                          const int32_t *offsets, int64_t n_cells, const double *alpha,
+                          const double *value, const int32_t *signal, int64_t n_ops);
+/* Signal window: row-major [n_signals][n_steps] samples for absolute steps first_step ..
+ * first_step + n_steps - 1 (`value[step]`, pyfds/regions.py:141,144). */
+int fds_upload_signals(fds_ctx *ctx, const double *samples, int64_t n_signals, int64_t n_steps,
+                       int64_t first_step);
+
+/* --- probes: `FieldComponent.write_outputs` (pyfds/fields.py:602-611) ------------------------ */
+
+/* Probe points of one component: cells ascending (owned cells only; duplicates allowed), slots[k] is
+ * the column of the probe record that receives cells[k]. n_slots_total is the record width shared by
+ * all components (pass the same value for each component). */
+int fds_upload_probes(fds_ctx *ctx, int32_t component, const int64_t *cells, const int32_t *slots,
+                      int64_t n, int64_t n_slots_total);
+
+/* --- state: `FieldComponent.values` (pyfds/fields.py:585) ----------------------------------- */
+
+/* Copies n = rows * nx owned values of one component from / to host memory. */
+int fds_upload_state(fds_ctx *ctx, int32_t component, const double *values, int64_t n);
+int fds_download_state(fds_ctx *ctx, int32_t component, double *values, int64_t n);
+/* Zeroes all components on the device (`Field.reset`, pyfds/fields.py:121-127). */
+int fds_reset_state(fds_ctx *ctx);
+
+/* --- the hot path: `Field.simulate` loop body (pyfds/fields.py:87-93) = `sim_step` x n_steps -- */
+
+/* Advances the slab by n_steps steps starting at absolute step first_step. probes_out (may be NULL if
+ * there are no probes) receives row-major [n_steps][n_slots_total] samples; slots not owned by this
+ * slab are left untouched. The signal window uploaded before must cover the step range.
+ * Synchronous: returns after the state and all probe records are complete. */
+int fds_step(fds_ctx *ctx, int64_t first_step, int64_t n_steps, double *probes_out);
+/* Same, but only enqueues the work on the context's stream (no probe drain to the host, probes_out
+ * semantics do not apply); pair with fds_sync(). Used for device-resident timing. */
+int fds_step_async(fds_ctx *ctx, int64_t first_step, int64_t n_steps);
+int fds_sync(fds_ctx *ctx);
+
+/* --- multi-GPU: y-slab halo exchange over NCCL (no reference equivalent) ------- */
+
+/* Writes a 128-byte NCCL unique id (rank 0 calls this, the host side broadcasts it). */
+int fds_comm_unique_id(uint8_t id[128]);
+/* Joins the communicator; slab `rank` exchanges halo rows with rank-1 and rank+1. */
+int fds_comm_init(fds_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t world);
+
+/* --- measurement ------------------------------------------------------------------------------ */
+
+/* Device time in milliseconds of the step kernels launched by the last fds_step/fds_step_async call,
+ * measured with CUDA events on the launching stream; valid after fds_sync(). */
+int fds_last_step_ms(fds_ctx *ctx, double *ms);
+/* Number of step-kernel launches issued by the last fds_step/fds_step_async call and their name. */
+int fds_last_launch_info(fds_ctx *ctx, int64_t *launches, int64_t *steps_per_launch,
+                         const char **kernel_name);
+/* Bytes of device memory held by the context. */
+int64_t fds_device_bytes(const fds_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* FDSB200_H */

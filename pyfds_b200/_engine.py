@@ -1,0 +1,397 @@
+"""ctypes binding of ``libfdsb200.so`` (C ABI: ``include/fdsb200.h``) and the host driver that runs
+``Field.simulate`` / ``sim_step`` on it.
+
+The division of labour follows the reference seam (``pyfds/fields.py:59-95``): the model class says
+*what* to simulate (materials, boundaries, outputs, values), this module moves that description to the
+device once per call and lets the CUDA engine execute all requested steps back to back.
+
+There is deliberately no CPU path here: if the library or a GPU is missing, ``run`` raises.
+"""
+
+import ctypes as ct
+import os
+import weakref
+
+import numpy as np
+
+from . import _bake
+
+MODEL_IDS = {
+    'acoustic1d': 1, 'acoustic2d': 2, 'acoustic3daxi': 3,
+    'thermal1d': 4, 'thermal2d': 5, 'thermal3daxi': 6,
+}
+
+# enum fds_table / fds_column_table / fds_column_vector
+TAB = {'GX': 0, 'GY': 1, 'FX': 2, 'FY': 3, 'VM1': 4, 'VP1': 5, 'VMN': 6, 'VPN': 7, 'V0': 8, 'EB': 9}
+CTAB = {'FX': 0, 'VM1': 1, 'VP1': 2}
+CVEC = {'R': 0, 'RR': 1}
+
+#: upper bound for one probe drain buffer (steps per fds_step call are chunked to stay below it)
+MAX_PROBE_BYTES = 256 << 20
+
+
+class fds_desc(ct.Structure):
+    _fields_ = [
+        ('model', ct.c_int32), ('device', ct.c_int32),
+        ('nx', ct.c_int64), ('ny', ct.c_int64), ('row0', ct.c_int64), ('rows', ct.c_int64),
+        ('halo_rows', ct.c_int32), ('lossy', ct.c_int32), ('n_materials', ct.c_int32),
+        ('kernel', ct.c_int32),
+    ]
+
+
+_LIB = None
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libfdsb200.so')
+
+
+def load_library():
+    """Loads the CUDA engine. Raises ``RuntimeError`` if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            'libfdsb200.so is missing ({}). Build it with `python -m pyfds_b200._build`; this '
+            'package has no CPU implementation of the time-stepping path.'.format(path))
+    lib = ct.CDLL(path)
+    p = ct.c_void_p
+    i32, i64 = ct.c_int32, ct.c_int64
+    dptr = ct.POINTER(ct.c_double)
+    sigs = {
+        'fds_create': (ct.c_int, [ct.POINTER(fds_desc), ct.POINTER(p)]),
+        'fds_destroy': (None, [p]),
+        'fds_last_error': (ct.c_char_p, [p]),
+        'fds_device_count': (ct.c_int, []),
+        'fds_upload_material_map': (ct.c_int, [p, p, i64]),
+        'fds_upload_table': (ct.c_int, [p, i32, p, i64]),
+        'fds_upload_column_table': (ct.c_int, [p, i32, p, i64]),
+        'fds_upload_column_vector': (ct.c_int, [p, i32, p, i64]),
+        'fds_upload_boundaries': (ct.c_int, [p, i32, p, p, i64, p, p, p, i64]),
+        'fds_upload_signals': (ct.c_int, [p, p, i64, i64, i64]),
+        'fds_upload_probes': (ct.c_int, [p, i32, p, p, i64, i64]),
+        'fds_upload_state': (ct.c_int, [p, i32, p, i64]),
+        'fds_download_state': (ct.c_int, [p, i32, p, i64]),
+        'fds_reset_state': (ct.c_int, [p]),
+        'fds_step': (ct.c_int, [p, i64, i64, p]),
+        'fds_step_async': (ct.c_int, [p, i64, i64]),
+        'fds_sync': (ct.c_int, [p]),
+        'fds_comm_unique_id': (ct.c_int, [p]),
+        'fds_comm_init': (ct.c_int, [p, p, i32, i32]),
+        'fds_last_step_ms': (ct.c_int, [p, dptr]),
+        'fds_last_launch_info': (ct.c_int, [p, ct.POINTER(i64), ct.POINTER(i64),
+                                            ct.POINTER(ct.c_char_p)]),
+        'fds_device_bytes': (i64, [p]),
+    }
+    for name, (restype, argtypes) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _LIB = lib
+    return lib
+
+
+def _ptr(array):
+    return array.ctypes.data_as(ct.c_void_p)
+
+
+def _c(array, dtype):
+    return np.ascontiguousarray(array, dtype=dtype)
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class Engine:
+    """One device context = one y-slab of one field (the whole grid on a single GPU)."""
+
+    def __init__(self, model, nx, ny, n_materials, lossy, row0=0, rows=None, halo_rows=0,
+                 device=0, kernel=0):
+        self.lib = load_library()
+        rows = ny if rows is None else rows
+        self.desc = fds_desc(MODEL_IDS[model], device, nx, ny, row0, rows, halo_rows, int(lossy),
+                             n_materials, kernel)
+        self.model = model
+        self.nx, self.ny, self.row0, self.rows, self.halo_rows = nx, ny, row0, rows, halo_rows
+        self.n_materials = n_materials
+        self.lossy = bool(lossy)
+        self.owned = rows * nx
+        self.ncomp = 2 if model.endswith('1d') else 3
+        handle = ct.c_void_p()
+        if self.lib.fds_create(ct.byref(self.desc), ct.byref(handle)) != 0:
+            raise EngineError(self.lib.fds_last_error(None).decode())
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, self.lib.fds_destroy, handle)
+
+    def close(self):
+        self._finalizer()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(self.lib.fds_last_error(self.handle).decode())
+
+    # window of global cells held by this context, halo rows included
+    @property
+    def cell_lo(self):
+        return (self.row0 - self.halo_rows) * self.nx
+
+    @property
+    def cell_hi(self):
+        return (self.row0 + self.rows + self.halo_rows) * self.nx
+
+    def upload_material_map(self, ids):
+        ids = _c(ids, np.uint8)
+        self._check(self.lib.fds_upload_material_map(self.handle, _ptr(ids), ids.size))
+
+    def upload_table(self, which, values):
+        values = _c(values, np.float64)
+        self._check(self.lib.fds_upload_table(self.handle, which, _ptr(values), values.size))
+
+    def upload_column_table(self, which, values):
+        values = _c(values, np.float64)
+        self._check(self.lib.fds_upload_column_table(self.handle, which, _ptr(values), values.size))
+
+    def upload_column_vector(self, which, values):
+        values = _c(values, np.float64)
+        self._check(self.lib.fds_upload_column_vector(self.handle, which, _ptr(values),
+                                                      values.size))
+
+    def upload_boundaries(self, component, table):
+        cells, offsets = _c(table.cells, np.int64), _c(table.offsets, np.int32)
+        alpha, value = _c(table.alpha, np.float64), _c(table.value, np.float64)
+        signal = _c(table.signal, np.int32)
+        self._check(self.lib.fds_upload_boundaries(
+            self.handle, component, _ptr(cells), _ptr(offsets), cells.size, _ptr(alpha),
+            _ptr(value), _ptr(signal), alpha.size))
+
+    def upload_signals(self, samples, first_step):
+        samples = _c(samples, np.float64)
+        n_signals, n_steps = samples.shape if samples.ndim == 2 else (0, 0)
+        self._check(self.lib.fds_upload_signals(self.handle, _ptr(samples), n_signals, n_steps,
+                                                first_step))
+
+    def upload_probes(self, component, cells, slots, n_slots_total):
+        cells, slots = _c(cells, np.int64), _c(slots, np.int32)
+        self._check(self.lib.fds_upload_probes(self.handle, component, _ptr(cells), _ptr(slots),
+                                               cells.size, n_slots_total))
+
+    def upload_state(self, component, values):
+        values = _c(values, np.float64)
+        self._check(self.lib.fds_upload_state(self.handle, component, _ptr(values), values.size))
+
+    def download_state(self, component, out=None):
+        if out is None:
+            out = np.empty(self.owned, dtype=np.float64)
+        self._check(self.lib.fds_download_state(self.handle, component, _ptr(out), out.size))
+        return out
+
+    def reset_state(self):
+        self._check(self.lib.fds_reset_state(self.handle))
+
+    def step(self, first_step, n_steps, n_slots):
+        """Runs n_steps steps synchronously; returns the probe records [n_steps][n_slots]."""
+        probes = np.zeros((n_steps, n_slots), dtype=np.float64)
+        self._check(self.lib.fds_step(self.handle, first_step, n_steps,
+                                      _ptr(probes) if n_slots else None))
+        return probes
+
+    def step_async(self, first_step, n_steps):
+        self._check(self.lib.fds_step_async(self.handle, first_step, n_steps))
+
+    def sync(self):
+        self._check(self.lib.fds_sync(self.handle))
+
+    def last_step_ms(self):
+        ms = ct.c_double()
+        self._check(self.lib.fds_last_step_ms(self.handle, ct.byref(ms)))
+        return ms.value
+
+    def last_launch_info(self):
+        launches, spl, name = ct.c_int64(), ct.c_int64(), ct.c_char_p()
+        self._check(self.lib.fds_last_launch_info(self.handle, ct.byref(launches), ct.byref(spl),
+                                                  ct.byref(name)))
+        return launches.value, spl.value, (name.value or b'').decode()
+
+    def device_bytes(self):
+        return self.lib.fds_device_bytes(self.handle)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (ct.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self.lib.fds_comm_init(self.handle, buf, rank, world))
+
+
+def comm_unique_id():
+    lib = load_library()
+    buf = (ct.c_uint8 * 128)()
+    if lib.fds_comm_unique_id(buf) != 0:
+        raise EngineError(lib.fds_last_error(None).decode())
+    return bytes(buf)
+
+
+# ---------------------------------------------------------------------------------------------
+# host driver
+# ---------------------------------------------------------------------------------------------
+
+class _State:
+    """Per-field device state; lives in ``field.__dict__['_engine_state']`` and is never pickled."""
+
+    def __init__(self):
+        self.engine = None
+        self.epoch = -1
+        self.key = None
+
+
+def _components(field):
+    return [getattr(field, name) for name in field._device_components]
+
+
+def _grid(field):
+    nx = field.x.samples
+    ny = field.y.samples if hasattr(field, 'y') else 1
+    return nx, ny
+
+
+def halo_rows_for(field, world):
+    """Rows a slab needs from each neighbour for one step: 1 (lossless) or 2 (viscous operator)."""
+    if world <= 1 or not hasattr(field, 'y'):
+        return 0
+    return 2 if field._baked['lossy'] else 1
+
+
+def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=0):
+    """Creates (or reuses) the device context of ``field`` and uploads what ``assemble_matrices``
+    froze: the material map and the coefficient tables. Returns the ``Engine``."""
+    state = field.__dict__.get('_engine_state')
+    if state is None:
+        state = field.__dict__['_engine_state'] = _State()
+    baked = field._baked
+    nx, ny = _grid(field)
+    rows = ny if rows is None else rows
+    key = (field._device_model, nx, ny, row0, rows, halo_rows, device, kernel)
+    if state.engine is not None and state.epoch == baked['epoch'] and state.key == key:
+        return state.engine
+
+    snapshot = baked['snapshot']
+    lo, hi = (row0 - halo_rows) * nx, (row0 + rows + halo_rows) * nx
+    ids, values = _bake.material_ids(snapshot, field.num_points, nx, lo, hi)
+    tables = field._coefficient_tables(values)
+    n_materials = len(next(iter(values.values()))) - 1
+    lossy = bool(tables.get('lossy', False))
+    baked['lossy'] = lossy
+
+    engine = state.engine
+    if engine is None or state.key != key or engine.n_materials != n_materials or \
+            engine.lossy != lossy:
+        if engine is not None:
+            engine.close()
+        engine = Engine(field._device_model, nx, ny, n_materials, lossy, row0=row0, rows=rows,
+                        halo_rows=halo_rows, device=device, kernel=kernel)
+    engine.upload_material_map(ids)
+    for name, column in tables['tables'].items():
+        engine.upload_table(TAB[name], np.concatenate(([0.0], column)))
+    for name, matrix in tables.get('column_tables', {}).items():
+        engine.upload_column_table(CTAB[name], np.vstack((np.zeros((1, nx)), matrix)))
+    for name, vector in tables.get('column_vectors', {}).items():
+        engine.upload_column_vector(CVEC[name], vector)
+    state.engine, state.epoch, state.key = engine, baked['epoch'], key
+    return engine
+
+
+def upload_run_tables(field, engine, first_step, n_steps):
+    """Bakes and uploads what may change between two ``simulate`` calls: boundary operations, the
+    signal window for the step range, and the probe points. Returns ``(n_slots, layout)`` where layout
+    lists ``(output, first_slot, n_points)``."""
+    nx = engine.nx
+    signals = []
+    for c, component in enumerate(_components(field)):
+        table = _bake.boundary_table(component.boundaries, first_step, n_steps, engine.cell_lo,
+                                     engine.cell_hi, signals)
+        # the device addresses cells relative to the first *owned* cell
+        table.cells = table.cells - engine.halo_rows * nx
+        engine.upload_boundaries(c, table)
+    engine.upload_signals(np.array(signals, dtype=np.float64).reshape(len(signals), n_steps)
+                          if signals else np.zeros((0, 0)), first_step)
+
+    layout = []
+    tables = []
+    slot = 0
+    own_lo, own_hi = engine.row0 * nx, (engine.row0 + engine.rows) * nx
+    for c, component in enumerate(_components(field)):
+        base = slot
+        for output in component.outputs:
+            count = np.asarray(output.region.indices).reshape(-1).shape[0]
+            layout.append((output, slot, count))
+            slot += count
+        cells, slots, _ = _bake.probe_table(component.outputs, base, own_lo, own_hi)
+        tables.append((c, cells, slots))
+    for c, cells, slots in tables:
+        engine.upload_probes(c, cells, slots, slot)
+    return slot, layout
+
+
+def _append_signals(layout, records):
+    """``Output.signals[k]`` grows by one sample per step (``pyfds/fields.py:606-611``)."""
+    for output, first, count in layout:
+        block = records[:, first:first + count]
+        if not output.signals:
+            output.signals = block.T.tolist()
+        else:
+            for k, signal in enumerate(output.signals[:count]):
+                signal.extend(block[:, k].tolist())
+
+
+def _host_values(component, num_points):
+    values = np.asarray(component.values, dtype=np.float64).reshape(-1)
+    if values.shape[0] != num_points:
+        raise ValueError('Field component has {} values, the field has {} points.'.format(
+            values.shape[0], num_points))
+    return values
+
+
+def run(field, n_steps, progress_logger=None, advance=True):
+    """``n_steps`` x ``sim_step`` on the device: upload values, step, download values and probes."""
+    engine = prepare(field)
+    first_step = field.step
+    n_slots, layout = upload_run_tables(field, engine, first_step, n_steps)
+
+    components = _components(field)
+    for c, component in enumerate(components):
+        engine.upload_state(c, _host_values(component, field.num_points))
+
+    chunk = n_steps
+    if n_slots:
+        chunk = max(1, min(chunk, MAX_PROBE_BYTES // (8 * n_slots)))
+    if progress_logger is not None:
+        chunk = max(1, min(chunk, -(-n_steps // 20)))
+    done = 0
+    while done < n_steps:
+        count = min(chunk, n_steps - done)
+        records = engine.step(first_step + done, count, n_slots)
+        if n_slots:
+            _append_signals(layout, records)
+        if progress_logger is not None:
+            for s in range(first_step + done, first_step + done + count):
+                progress_logger.log(s)
+        done += count
+
+    for c, component in enumerate(components):
+        target = component.values
+        if isinstance(target, np.ndarray) and target.dtype == np.float64 and \
+                target.flags.c_contiguous and target.flags.writeable and \
+                target.shape == (field.num_points,):
+            engine.download_state(c, out=target)
+        else:
+            component.values = engine.download_state(c)
+    if advance:
+        field.step += n_steps
+
+
+def reset(field):
+    """Drops nothing, but makes sure stale device values can never leak into a reset field: the next
+    ``run`` uploads the (zeroed) host values anyway."""
+    state = field.__dict__.get('_engine_state')
+    if state is not None and state.engine is not None:
+        state.engine.reset_state()

@@ -1,0 +1,936 @@
+// C ABI of the B200 finite-difference step engine (see include/fdsb200.h for the contract and the
+// reference code every entry point replaces).
+//
+// HBM layout of one context (one y-slab):
+//   * every field component lives in TWO buffers (steps are out of place and ping-pong between them);
+//     each buffer is  [ pad | halo rows | owned rows | halo rows | pad ]  doubles, zero-initialised.
+//     The pad (>= 9 rows + 4096 cells) is never written: cells outside the global grid read as 0.0 with
+//     the void material, which makes every skipped DIA term an exact "+ 0.0" and removes all edge
+//     special-casing from the kernels (and gives the row-wrap of the x operators for free, because
+//     cells are addressed by flat index).
+//   * one byte per cell: material id (6 bits) | boundary flag | probe flag, same padding.
+//   * coefficient tables: [FDS_TAB_COUNT][64] doubles (+ per-column tables for axisymmetric models).
+//   * boundary operations / probe points as small sorted tables, signals as a [n_signals][n_steps]
+//     window, probe records in a two-half device ring drained to pinned host memory on a second
+//     stream while the next half is being computed.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "fds_common.cuh"
+#include "fds_step1d.cuh"
+#include "fds_step2d.cuh"
+#include "fds_stream2d.cuh"
+
+using namespace fds;
+
+namespace {
+
+std::mutex g_err_mutex;
+std::string g_create_error = "";
+
+struct DevArray {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+};
+
+// ---- NCCL, resolved lazily so that single-GPU use has no dependency on it ----------------------
+struct ncclComm;
+typedef struct { char internal[128]; } nccl_unique_id;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(nccl_unique_id *) = nullptr;
+    int (*CommInitRank)(ncclComm **, int, nccl_unique_id, int) = nullptr;
+    int (*CommDestroy)(ncclComm *) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8;  // ncclDouble
+
+const char *load_nccl() {
+    if (g_nccl.lib) return nullptr;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+        g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return "libnccl.so.2 not found";
+#define FDS_NCCL_SYM(field, name)                                                        \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name);                                 \
+    if (!g_nccl.field) { g_nccl.lib = nullptr; return "NCCL symbol " name " missing"; }
+    FDS_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    FDS_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    FDS_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    FDS_NCCL_SYM(Send, "ncclSend")
+    FDS_NCCL_SYM(Recv, "ncclRecv")
+    FDS_NCCL_SYM(GroupStart, "ncclGroupStart")
+    FDS_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    FDS_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef FDS_NCCL_SYM
+    return nullptr;
+}
+
+}  // namespace
+
+struct fds_ctx {
+    fds_desc d{};
+    int dims = 2;
+    int ncomp = 3;
+    bool thermal = false;
+    bool axi = false;
+    long long owned = 0;      // owned cells
+    long long halo = 0;       // halo cells per side
+    long long pad = 0;        // pad cells per side (beyond the halo)
+    long long alloc = 0;      // cells per buffer
+    double *buf[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    uint8_t *map = nullptr;
+    bool map_uploaded = false;
+    double *tab = nullptr;
+    double *ctab = nullptr;
+    double *cvec = nullptr;
+    int cur = 0;
+
+    DevArray bcells[3], boffsets[3], balpha[3], bvalue[3], bsignal[3];
+    long long n_bcells[3] = {0, 0, 0};
+    DevArray pcells[3], pslots[3];
+    long long n_probes[3] = {0, 0, 0};
+    DevArray flagged;         // cells whose flag bits are currently set
+    long long n_flagged = 0;
+    bool flags_dirty = false;
+    DevArray signals;
+    long long sig_steps = 0, sig_first = 0, n_signals = 0;
+
+    long long n_slots = 0;
+    DevArray ring;
+    long long ring_half = 0;  // steps per ring half
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+
+    cudaStream_t stream = nullptr, drain = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_half[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_edge = nullptr, ev_comm = nullptr;
+    bool timed = false;
+
+    long long last_launches = 0, last_steps_per_launch = 0;
+    const char *last_kernel = "none";
+    long long device_bytes = 0;
+
+    ncclComm *comm = nullptr;
+    int rank = 0, world = 1;
+
+    std::string err;
+};
+
+namespace {
+
+int fail(fds_ctx *ctx, const std::string &msg) {
+    if (ctx) ctx->err = msg;
+    else {
+        std::lock_guard<std::mutex> lock(g_err_mutex);
+        g_create_error = msg;
+    }
+    return 1;
+}
+
+#define FDS_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+#define FDS_NCCL(ctx, call)                                                              \
+    do {                                                                                 \
+        int e_ = (call);                                                                 \
+        if (e_ != 0)                                                                     \
+            return fail(ctx, std::string(#call) + ": " + g_nccl.GetErrorString(e_));     \
+    } while (0)
+
+int dev_alloc(fds_ctx *ctx, void **p, size_t bytes, bool zero) {
+    FDS_CUDA(ctx, cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    if (zero) FDS_CUDA(ctx, cudaMemsetAsync(*p, 0, std::max<size_t>(bytes, 16), ctx->stream));
+    ctx->device_bytes += (long long)bytes;
+    return 0;
+}
+
+int dev_upload(fds_ctx *ctx, DevArray &a, const void *host, size_t bytes) {
+    if (a.bytes < bytes || !a.ptr) {
+        if (a.ptr) {
+            FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(a.ptr);
+            ctx->device_bytes -= (long long)a.bytes;
+        }
+        a.ptr = nullptr;
+        a.bytes = 0;
+        void *p = nullptr;
+        if (dev_alloc(ctx, &p, bytes, false)) return 1;
+        a.ptr = p;
+        a.bytes = bytes;
+    }
+    if (bytes)
+        FDS_CUDA(ctx, cudaMemcpyAsync(a.ptr, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    // the host buffer is borrowed only for the duration of the call
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+__global__ void flag_kernel(uint8_t *map, const long long *cells, long long n, uint8_t set_mask,
+                            uint8_t clear_mask) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    // several table entries may name the same cell: make the read-modify-write atomic on the word
+    const long long c = cells[k];
+    unsigned int *word = reinterpret_cast<unsigned int *>(
+        reinterpret_cast<uintptr_t>(map + c) & ~uintptr_t(3));
+    const int shift = 8 * (int)(reinterpret_cast<uintptr_t>(map + c) & 3);
+    if (clear_mask) atomicAnd(word, ~((unsigned int)clear_mask << shift));
+    if (set_mask) atomicOr(word, (unsigned int)set_mask << shift);
+}
+
+int launch_flags(fds_ctx *ctx, const long long *cells, long long n, uint8_t set_mask,
+                 uint8_t clear_mask) {
+    if (n <= 0) return 0;
+    const int threads = 256;
+    const long long blocks = (n + threads - 1) / threads;
+    flag_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->map + ctx->pad + ctx->halo,
+                                                               cells, n, set_mask, clear_mask);
+    FDS_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+// Rebuilds the per-cell flag bits from the boundary and probe tables.
+int refresh_flags(fds_ctx *ctx) {
+    if (!ctx->flags_dirty) return 0;
+    if (ctx->n_flagged)
+        if (launch_flags(ctx, (const long long *)ctx->flagged.ptr, ctx->n_flagged, 0,
+                         kFlagBound | kFlagProbe))
+            return 1;
+    long long total = 0;
+    for (int c = 0; c < 3; ++c) total += ctx->n_bcells[c] + ctx->n_probes[c];
+    if (ctx->flagged.bytes < (size_t)total * 8) {
+        if (ctx->flagged.ptr) {
+            FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->flagged.ptr);
+            ctx->device_bytes -= (long long)ctx->flagged.bytes;
+            ctx->flagged = DevArray();
+        }
+        void *p = nullptr;
+        if (dev_alloc(ctx, &p, (size_t)total * 8, false)) return 1;
+        ctx->flagged.ptr = p;
+        ctx->flagged.bytes = (size_t)total * 8;
+    }
+    long long at = 0;
+    for (int c = 0; c < 3; ++c) {
+        const long long nb = ctx->n_bcells[c], np = ctx->n_probes[c];
+        long long *dst = (long long *)ctx->flagged.ptr;
+        if (nb) {
+            FDS_CUDA(ctx, cudaMemcpyAsync(dst + at, ctx->bcells[c].ptr, nb * 8,
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+            if (launch_flags(ctx, dst + at, nb, kFlagBound, 0)) return 1;
+            at += nb;
+        }
+        if (np) {
+            FDS_CUDA(ctx, cudaMemcpyAsync(dst + at, ctx->pcells[c].ptr, np * 8,
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+            if (launch_flags(ctx, dst + at, np, kFlagProbe, 0)) return 1;
+            at += np;
+        }
+    }
+    ctx->n_flagged = total;
+    ctx->flags_dirty = false;
+    return 0;
+}
+
+double *origin(fds_ctx *ctx, int which, int comp) {
+    return ctx->buf[which][comp] + ctx->pad + ctx->halo;
+}
+
+StepTables make_tables(fds_ctx *ctx) {
+    StepTables t{};
+    t.map = ctx->map + ctx->pad + ctx->halo;
+    t.tab = ctx->tab;
+    t.ctab = ctx->ctab;
+    t.cvec = ctx->cvec;
+    for (int c = 0; c < 3; ++c) {
+        t.bound[c].cells = (const long long *)ctx->bcells[c].ptr;
+        t.bound[c].offsets = (const int *)ctx->boffsets[c].ptr;
+        t.bound[c].alpha = (const double *)ctx->balpha[c].ptr;
+        t.bound[c].value = (const double *)ctx->bvalue[c].ptr;
+        t.bound[c].signal = (const int *)ctx->bsignal[c].ptr;
+        t.bound[c].n_cells = (int)ctx->n_bcells[c];
+        t.probe[c].cells = (const long long *)ctx->pcells[c].ptr;
+        t.probe[c].slots = (const int *)ctx->pslots[c].ptr;
+        t.probe[c].n = (int)ctx->n_probes[c];
+    }
+    t.signals = (const double *)ctx->signals.ptr;
+    t.sig_steps = ctx->sig_steps;
+    t.sig_first_step = ctx->sig_first;
+    t.ring = (double *)ctx->ring.ptr;
+    t.n_slots = (int)ctx->n_slots;
+    return t;
+}
+
+// ---- kernel dispatch ----------------------------------------------------------------------------
+
+template <int MODEL, bool LOSSY>
+int launch_step2d(fds_ctx *ctx, const Step2DArgs &a, const StepTables &t) {
+    const long long rows = a.row_end - a.row_begin;
+    if (rows <= 0) return 0;
+    dim3 grid((unsigned)rows, (unsigned)((a.nx + 255) / 256));
+    step2d_kernel<MODEL, LOSSY><<<grid, 256, 0, ctx->stream>>>(a, t, ctx->d.n_materials + 1);
+    FDS_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+int dispatch_step2d(fds_ctx *ctx, const Step2DArgs &a, const StepTables &t) {
+    const bool lossy = ctx->d.lossy != 0;
+    switch (ctx->d.model) {
+        case FDS_ACOUSTIC2D:
+            return lossy ? launch_step2d<FDS_ACOUSTIC2D, true>(ctx, a, t)
+                         : launch_step2d<FDS_ACOUSTIC2D, false>(ctx, a, t);
+        case FDS_ACOUSTIC3DAXI:
+            return lossy ? launch_step2d<FDS_ACOUSTIC3DAXI, true>(ctx, a, t)
+                         : launch_step2d<FDS_ACOUSTIC3DAXI, false>(ctx, a, t);
+        case FDS_THERMAL2D:
+            return launch_step2d<FDS_THERMAL2D, false>(ctx, a, t);
+        case FDS_THERMAL3DAXI:
+            return launch_step2d<FDS_THERMAL3DAXI, false>(ctx, a, t);
+    }
+    return fail(ctx, "model has no 2-D kernel");
+}
+
+const char *step2d_name(const fds_ctx *ctx) {
+    switch (ctx->d.model) {
+        case FDS_ACOUSTIC2D: return ctx->d.lossy ? "step2d_kernel<acoustic2d,lossy>"
+                                                 : "step2d_kernel<acoustic2d,lossless>";
+        case FDS_ACOUSTIC3DAXI: return ctx->d.lossy ? "step2d_kernel<acoustic3daxi,lossy>"
+                                                    : "step2d_kernel<acoustic3daxi,lossless>";
+        case FDS_THERMAL2D: return "step2d_kernel<thermal2d>";
+        case FDS_THERMAL3DAXI: return "step2d_kernel<thermal3daxi>";
+    }
+    return "none";
+}
+
+// 1-D tiling: owned cells per CTA, halo and steps per launch.
+struct Plan1D {
+    int tile, halo, steps;
+    long long ctas;
+    size_t smem;
+};
+
+Plan1D plan_1d(const fds_ctx *ctx, long long steps_left) {
+    Plan1D p{};
+    const long long n = ctx->d.nx;
+    const int max_width = 13000;
+    if (n + 4 <= max_width) {  // the whole line in one CTA: no neighbours, any number of steps
+        p.tile = (int)n;
+        p.halo = 2;
+        p.ctas = 1;
+        p.steps = (int)std::min<long long>(steps_left, 1 << 20);
+    } else {
+        p.halo = 64;
+        p.tile = 4096 - 2 * p.halo;
+        p.ctas = (n + p.tile - 1) / p.tile;
+        p.steps = (int)std::min<long long>(steps_left, p.halo / 2);
+    }
+    p.smem = (size_t)(p.tile + 2 * p.halo) * 17 + 16;
+    return p;
+}
+
+template <bool THERMAL, bool LOSSY>
+int launch_step1d(fds_ctx *ctx, const Step1DArgs &a, const StepTables &t, const Plan1D &p) {
+    auto kernel = step1d_kernel<THERMAL, LOSSY>;
+    FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)p.smem));
+    kernel<<<(unsigned)p.ctas, k1DThreads, p.smem, ctx->stream>>>(a, t);
+    FDS_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+int ensure_ring(fds_ctx *ctx, long long n_steps) {
+    // two halves, each holding `ring_half` step records
+    long long half = 1;
+    if (ctx->n_slots > 0) {
+        const long long budget = (32ll << 20) / (ctx->n_slots * 8);
+        half = std::max<long long>(1, std::min<long long>(n_steps, std::max<long long>(budget, 64)));
+    }
+    const size_t bytes = (size_t)(2 * half * std::max<long long>(ctx->n_slots, 1)) * 8;
+    if (ctx->ring.bytes < bytes || ctx->ring_half < half) {
+        if (ctx->ring.ptr) {
+            FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->ring.ptr);
+            ctx->device_bytes -= (long long)ctx->ring.bytes;
+            ctx->ring = DevArray();
+        }
+        void *p = nullptr;
+        if (dev_alloc(ctx, &p, bytes, true)) return 1;
+        ctx->ring.ptr = p;
+        ctx->ring.bytes = bytes;
+    }
+    ctx->ring_half = half;
+    return 0;
+}
+
+int exchange_halos(fds_ctx *ctx, int which);
+
+// The time loop. `drain` = copy probe records to pinned host memory behind the computation.
+int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain) {
+    if (n_steps <= 0) return 0;
+    if (!ctx->map_uploaded) return fail(ctx, "fds_step: material map not uploaded");
+    if (ctx->n_signals > 0 &&
+        (first_step < ctx->sig_first || first_step + n_steps > ctx->sig_first + ctx->sig_steps))
+        return fail(ctx, "fds_step: step range outside the uploaded signal window");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    if (refresh_flags(ctx)) return 1;
+    if (ensure_ring(ctx, n_steps)) return 1;
+    if (drain && ctx->n_slots > 0) {
+        const size_t need = (size_t)n_steps * ctx->n_slots * 8;
+        if (ctx->pinned_bytes < need) {
+            if (ctx->pinned) cudaFreeHost(ctx->pinned);
+            ctx->pinned = nullptr;
+            ctx->pinned_bytes = 0;
+            FDS_CUDA(ctx, cudaMallocHost(&ctx->pinned, need));
+            ctx->pinned_bytes = need;
+        }
+    }
+
+    StepTables t = make_tables(ctx);
+    const long long half = ctx->ring_half;
+    const long long sig0 = first_step - ctx->sig_first;
+    ctx->last_launches = 0;
+    ctx->last_steps_per_launch = 1;
+
+    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    long long done = 0;
+    long long chunk = 0;
+    while (done < n_steps) {
+        const long long chunk_steps = std::min(half, n_steps - done);
+        const int h = (int)(chunk & 1);
+        if (drain && ctx->n_slots > 0 && chunk >= 2)  // the half must have been drained
+            FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_drained[h], 0));
+        long long in_chunk = 0;
+        while (in_chunk < chunk_steps) {
+            const long long s = done + in_chunk;
+            const long long ring_row = h * half + in_chunk;
+            long long advanced = 1;
+            if (ctx->dims == 1) {
+                Plan1D p = plan_1d(ctx, chunk_steps - in_chunk);
+                Step1DArgs a{};
+                a.in[0] = origin(ctx, ctx->cur, 0);
+                a.in[1] = origin(ctx, ctx->cur, 1);
+                a.out[0] = origin(ctx, ctx->cur ^ 1, 0);
+                a.out[1] = origin(ctx, ctx->cur ^ 1, 1);
+                a.n = ctx->d.nx;
+                a.tile = p.tile;
+                a.halo = p.halo;
+                a.n_steps = p.steps;
+                a.sig_index = sig0 + s;
+                a.ring_row = ring_row;
+                int rc;
+                if (ctx->thermal) rc = launch_step1d<true, false>(ctx, a, t, p);
+                else if (ctx->d.lossy) rc = launch_step1d<false, true>(ctx, a, t, p);
+                else rc = launch_step1d<false, false>(ctx, a, t, p);
+                if (rc) return 1;
+                advanced = p.steps;
+                ctx->last_kernel = ctx->thermal ? "step1d_kernel<thermal>"
+                                   : ctx->d.lossy ? "step1d_kernel<acoustic,lossy>"
+                                                  : "step1d_kernel<acoustic,lossless>";
+                ctx->last_steps_per_launch = p.steps;
+                ctx->last_launches += 1;
+            } else {
+                Step2DArgs a{};
+                for (int c = 0; c < 3; ++c) {
+                    a.in[c] = origin(ctx, ctx->cur, c);
+                    a.out[c] = origin(ctx, ctx->cur ^ 1, c);
+                }
+                a.nx = ctx->d.nx;
+                a.sig_index = sig0 + s;
+                a.ring_row = ring_row;
+                // thermal fluxes are derived data: store them only with the last step of the call
+                a.write_vector = (s == n_steps - 1);
+                const long long rows = ctx->d.rows;
+                if (ctx->comm && ctx->world > 1) {
+                    // edge bands first, so that their rows can travel while the interior computes
+                    const long long band = std::min<long long>(ctx->d.halo_rows, rows);
+                    a.row_begin = 0; a.row_end = band;
+                    if (dispatch_step2d(ctx, a, t)) return 1;
+                    a.row_begin = std::max(band, rows - band); a.row_end = rows;
+                    if (dispatch_step2d(ctx, a, t)) return 1;
+                    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
+                    FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
+                    if (exchange_halos(ctx, ctx->cur ^ 1)) return 1;
+                    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+                    a.row_begin = band; a.row_end = std::max(band, rows - band);
+                    if (dispatch_step2d(ctx, a, t)) return 1;
+                    FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+                    ctx->last_launches += 3;
+                } else {
+                    a.row_begin = 0; a.row_end = rows;
+                    if (dispatch_step2d(ctx, a, t)) return 1;
+                    ctx->last_launches += 1;
+                }
+                ctx->last_kernel = step2d_name(ctx);
+            }
+            ctx->cur ^= 1;
+            in_chunk += advanced;
+        }
+        if (drain && ctx->n_slots > 0) {
+            FDS_CUDA(ctx, cudaEventRecord(ctx->ev_half[h], ctx->stream));
+            FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->drain, ctx->ev_half[h], 0));
+            FDS_CUDA(ctx, cudaMemcpyAsync((double *)ctx->pinned + done * ctx->n_slots,
+                                          (double *)ctx->ring.ptr + h * half * ctx->n_slots,
+                                          (size_t)chunk_steps * ctx->n_slots * 8,
+                                          cudaMemcpyDeviceToHost, ctx->drain));
+            FDS_CUDA(ctx, cudaEventRecord(ctx->ev_drained[h], ctx->drain));
+        }
+        done += chunk_steps;
+        ++chunk;
+    }
+    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+    ctx->timed = true;
+    return 0;
+}
+
+// Sends the outermost owned rows of buffer `which` to the neighbour slabs and receives their rows
+// into the halo rows of the same buffer.
+int exchange_halos(fds_ctx *ctx, int which) {
+    const long long nx = ctx->d.nx, h = ctx->d.halo_rows, rows = ctx->d.rows;
+    const size_t count = (size_t)(h * nx);
+    const int ncomp = ctx->thermal ? 1 : 3;  // thermal fluxes are recomputed from T
+    FDS_NCCL(ctx, g_nccl.GroupStart());
+    for (int c = 0; c < ncomp; ++c) {
+        double *o = origin(ctx, which, c);
+        if (ctx->rank > 0) {
+            FDS_NCCL(ctx, g_nccl.Send(o, count, kNcclFloat64, ctx->rank - 1, ctx->comm,
+                                      ctx->comm_stream));
+            FDS_NCCL(ctx, g_nccl.Recv(o - h * nx, count, kNcclFloat64, ctx->rank - 1, ctx->comm,
+                                      ctx->comm_stream));
+        }
+        if (ctx->rank < ctx->world - 1) {
+            FDS_NCCL(ctx, g_nccl.Send(o + (rows - h) * nx, count, kNcclFloat64, ctx->rank + 1,
+                                      ctx->comm, ctx->comm_stream));
+            FDS_NCCL(ctx, g_nccl.Recv(o + rows * nx, count, kNcclFloat64, ctx->rank + 1, ctx->comm,
+                                      ctx->comm_stream));
+        }
+    }
+    FDS_NCCL(ctx, g_nccl.GroupEnd());
+    return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+// exported entry points
+// =================================================================================================
+
+extern "C" {
+
+int fds_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *fds_last_error(const fds_ctx *ctx) {
+    if (ctx) return ctx->err.c_str();
+    return g_create_error.c_str();
+}
+
+int fds_create(const fds_desc *desc, fds_ctx **out) {
+    if (!desc || !out) return fail(nullptr, "fds_create: null argument");
+    *out = nullptr;
+    const fds_desc &d = *desc;
+    if (d.model < FDS_ACOUSTIC1D || d.model > FDS_THERMAL3DAXI)
+        return fail(nullptr, "fds_create: unknown model");
+    const bool one_d = (d.model == FDS_ACOUSTIC1D || d.model == FDS_THERMAL1D);
+    if (d.nx < 1 || d.ny < 1 || d.rows < 1 || d.row0 < 0 || d.row0 + d.rows > d.ny)
+        return fail(nullptr, "fds_create: bad grid or slab extents");
+    if (one_d && (d.ny != 1 || d.halo_rows != 0))
+        return fail(nullptr, "fds_create: 1-D models are single rows without halo");
+    if (!one_d && d.nx < 2)
+        return fail(nullptr, "fds_create: 2-D models need at least two samples along x");
+    if (d.n_materials < 1 || d.n_materials >= kMaxMaterials)
+        return fail(nullptr, "fds_create: 1..63 distinct materials supported");
+    if (d.halo_rows < 0 || d.halo_rows > 64)
+        return fail(nullptr, "fds_create: halo_rows out of range");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, std::string("fds_create: no CUDA device (") +
+                                 (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") +
+                                 "); this engine has no CPU path");
+    }
+    if (d.device < 0 || d.device >= n_dev) return fail(nullptr, "fds_create: bad device ordinal");
+
+    fds_ctx *ctx = new fds_ctx();
+    ctx->d = d;
+    ctx->dims = one_d ? 1 : 2;
+    ctx->ncomp = one_d ? 2 : 3;
+    ctx->thermal = (d.model == FDS_THERMAL1D || d.model == FDS_THERMAL2D ||
+                    d.model == FDS_THERMAL3DAXI);
+    ctx->axi = (d.model == FDS_ACOUSTIC3DAXI || d.model == FDS_THERMAL3DAXI);
+    ctx->owned = d.rows * d.nx;
+    ctx->halo = (long long)d.halo_rows * d.nx;
+    // >= 9 rows + 4096 cells of padding, rounded so that the origin stays 512-byte aligned
+    long long pad = (one_d ? 0 : 9 * d.nx) + 4096;
+    pad = (pad + ctx->halo + 63) / 64 * 64 - ctx->halo;
+    while ((pad + ctx->halo) % 64) ++pad;
+    ctx->pad = pad;
+    ctx->alloc = ctx->owned + 2 * (ctx->halo + ctx->pad);
+
+    auto bail = [&](int) {
+        std::string msg = ctx->err;
+        fds_destroy(ctx);
+        return fail(nullptr, "fds_create: " + msg);
+    };
+#define FDS_TRY(expr) if (expr) return bail(0)
+    if (cudaSetDevice(d.device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return bail(0); }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->drain, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        ctx->err = "cudaStreamCreate failed";
+        return bail(0);
+    }
+    cudaEvent_t *plain[] = {&ctx->ev_half[0], &ctx->ev_half[1], &ctx->ev_drained[0],
+                            &ctx->ev_drained[1], &ctx->ev_edge, &ctx->ev_comm};
+    for (cudaEvent_t *ev : plain)
+        if (cudaEventCreateWithFlags(ev, cudaEventDisableTiming) != cudaSuccess) {
+            ctx->err = "cudaEventCreate failed";
+            return bail(0);
+        }
+    if (cudaEventCreate(&ctx->ev_t0) != cudaSuccess || cudaEventCreate(&ctx->ev_t1) != cudaSuccess) {
+        ctx->err = "cudaEventCreate failed";
+        return bail(0);
+    }
+    for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < ctx->ncomp; ++c)
+            FDS_TRY(dev_alloc(ctx, (void **)&ctx->buf[b][c], (size_t)ctx->alloc * 8, true));
+    FDS_TRY(dev_alloc(ctx, (void **)&ctx->map, (size_t)ctx->alloc, true));
+    FDS_TRY(dev_alloc(ctx, (void **)&ctx->tab, sizeof(double) * FDS_TAB_COUNT * kMaxMaterials, true));
+    if (ctx->axi) {
+        FDS_TRY(dev_alloc(ctx, (void **)&ctx->ctab,
+                          sizeof(double) * FDS_CTAB_COUNT * (d.n_materials + 1) * d.nx, true));
+        FDS_TRY(dev_alloc(ctx, (void **)&ctx->cvec, sizeof(double) * FDS_CVEC_COUNT * d.nx, true));
+    }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        ctx->err = "device initialisation failed";
+        return bail(0);
+    }
+#undef FDS_TRY
+    *out = ctx;
+    return 0;
+}
+
+void fds_destroy(fds_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->d.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->drain) cudaStreamSynchronize(ctx->drain);
+    if (ctx->comm_stream) cudaStreamSynchronize(ctx->comm_stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 3; ++c)
+            if (ctx->buf[b][c]) cudaFree(ctx->buf[b][c]);
+    if (ctx->map) cudaFree(ctx->map);
+    if (ctx->tab) cudaFree(ctx->tab);
+    if (ctx->ctab) cudaFree(ctx->ctab);
+    if (ctx->cvec) cudaFree(ctx->cvec);
+    for (int c = 0; c < 3; ++c) {
+        DevArray *arrays[] = {&ctx->bcells[c], &ctx->boffsets[c], &ctx->balpha[c], &ctx->bvalue[c],
+                              &ctx->bsignal[c], &ctx->pcells[c], &ctx->pslots[c]};
+        for (DevArray *a : arrays)
+            if (a->ptr) cudaFree(a->ptr);
+    }
+    if (ctx->flagged.ptr) cudaFree(ctx->flagged.ptr);
+    if (ctx->signals.ptr) cudaFree(ctx->signals.ptr);
+    if (ctx->ring.ptr) cudaFree(ctx->ring.ptr);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaEvent_t events[] = {ctx->ev_half[0], ctx->ev_half[1], ctx->ev_drained[0], ctx->ev_drained[1],
+                            ctx->ev_t0, ctx->ev_t1, ctx->ev_edge, ctx->ev_comm};
+    for (cudaEvent_t ev : events)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->drain) cudaStreamDestroy(ctx->drain);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+    delete ctx;
+}
+
+int fds_upload_material_map(fds_ctx *ctx, const uint8_t *ids, int64_t n) {
+    if (!ctx || !ids) return fail(ctx, "fds_upload_material_map: null argument");
+    if (n != ctx->owned + 2 * ctx->halo)
+        return fail(ctx, "fds_upload_material_map: expected (rows + 2*halo_rows) * nx ids");
+    for (int64_t k = 0; k < n; ++k)
+        if (ids[k] > ctx->d.n_materials)
+            return fail(ctx, "fds_upload_material_map: id exceeds n_materials");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    FDS_CUDA(ctx, cudaMemcpyAsync(ctx->map + ctx->pad, ids, (size_t)n, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->map_uploaded = true;
+    ctx->n_flagged = 0;      // the upload overwrote all flag bits
+    ctx->flags_dirty = true;
+    return 0;
+}
+
+int fds_upload_table(fds_ctx *ctx, int32_t table, const double *values, int64_t n) {
+    if (!ctx || !values) return fail(ctx, "fds_upload_table: null argument");
+    if (table < 0 || table >= FDS_TAB_COUNT) return fail(ctx, "fds_upload_table: bad table id");
+    if (n != ctx->d.n_materials + 1)
+        return fail(ctx, "fds_upload_table: expected n_materials + 1 values");
+    if (values[0] != 0.0) return fail(ctx, "fds_upload_table: entry 0 (void material) must be 0");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    FDS_CUDA(ctx, cudaMemcpyAsync(ctx->tab + (size_t)table * kMaxMaterials, values, (size_t)n * 8,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int fds_upload_column_table(fds_ctx *ctx, int32_t table, const double *values, int64_t n) {
+    if (!ctx || !values) return fail(ctx, "fds_upload_column_table: null argument");
+    if (!ctx->axi) return fail(ctx, "fds_upload_column_table: model is not axisymmetric");
+    if (table < 0 || table >= FDS_CTAB_COUNT)
+        return fail(ctx, "fds_upload_column_table: bad table id");
+    const int64_t expect = (int64_t)(ctx->d.n_materials + 1) * ctx->d.nx;
+    if (n != expect) return fail(ctx, "fds_upload_column_table: expected (n_materials+1)*nx values");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    FDS_CUDA(ctx, cudaMemcpyAsync(ctx->ctab + (size_t)table * expect, values, (size_t)n * 8,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int fds_upload_column_vector(fds_ctx *ctx, int32_t vec, const double *values, int64_t n) {
+    if (!ctx || !values) return fail(ctx, "fds_upload_column_vector: null argument");
+    if (!ctx->axi) return fail(ctx, "fds_upload_column_vector: model is not axisymmetric");
+    if (vec < 0 || vec >= FDS_CVEC_COUNT) return fail(ctx, "fds_upload_column_vector: bad id");
+    if (n != ctx->d.nx) return fail(ctx, "fds_upload_column_vector: expected nx values");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    FDS_CUDA(ctx, cudaMemcpyAsync(ctx->cvec + (size_t)vec * ctx->d.nx, values, (size_t)n * 8,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int fds_upload_boundaries(fds_ctx *ctx, int32_t component, const int64_t *cells,
+                          const int32_t *offsets, int64_t n_cells, const double *alpha,
+                          const double *value, const int32_t *signal, int64_t n_ops) {
+    if (!ctx) return fail(ctx, "fds_upload_boundaries: null context");
+    if (component < 0 || component >= ctx->ncomp)
+        return fail(ctx, "fds_upload_boundaries: bad component");
+    if (n_cells < 0 || n_ops < n_cells || n_cells > 0x7fffffff || n_ops > 0x7fffffff)
+        return fail(ctx, "fds_upload_boundaries: bad sizes");
+    if (n_cells > 0) {
+        if (!cells || !offsets || !alpha || !value || !signal)
+            return fail(ctx, "fds_upload_boundaries: null table");
+        const long long lo = -ctx->halo, hi = ctx->owned + ctx->halo;
+        for (int64_t k = 0; k < n_cells; ++k) {
+            if (cells[k] < lo || cells[k] >= hi)
+                return fail(ctx, "fds_upload_boundaries: cell outside the slab");
+            if (k && cells[k] <= cells[k - 1])
+                return fail(ctx, "fds_upload_boundaries: cells must be strictly ascending");
+            if (offsets[k + 1] <= offsets[k])
+                return fail(ctx, "fds_upload_boundaries: offsets must be strictly ascending");
+        }
+        if (offsets[0] != 0 || offsets[n_cells] != n_ops)
+            return fail(ctx, "fds_upload_boundaries: offsets do not cover the operations");
+    }
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    const int c = component;
+    if (dev_upload(ctx, ctx->bcells[c], cells, (size_t)n_cells * 8)) return 1;
+    if (dev_upload(ctx, ctx->boffsets[c], offsets, (size_t)(n_cells ? n_cells + 1 : 0) * 4)) return 1;
+    if (dev_upload(ctx, ctx->balpha[c], alpha, (size_t)n_ops * 8)) return 1;
+    if (dev_upload(ctx, ctx->bvalue[c], value, (size_t)n_ops * 8)) return 1;
+    if (dev_upload(ctx, ctx->bsignal[c], signal, (size_t)n_ops * 4)) return 1;
+    ctx->n_bcells[c] = n_cells;
+    ctx->flags_dirty = true;
+    return 0;
+}
+
+int fds_upload_signals(fds_ctx *ctx, const double *samples, int64_t n_signals, int64_t n_steps,
+                       int64_t first_step) {
+    if (!ctx) return fail(ctx, "fds_upload_signals: null context");
+    if (n_signals < 0 || n_steps < 0) return fail(ctx, "fds_upload_signals: bad sizes");
+    if (n_signals > 0 && n_steps > 0 && !samples)
+        return fail(ctx, "fds_upload_signals: null samples");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    if (dev_upload(ctx, ctx->signals, samples, (size_t)(n_signals * n_steps) * 8)) return 1;
+    ctx->n_signals = n_signals;
+    ctx->sig_steps = n_steps;
+    ctx->sig_first = first_step;
+    return 0;
+}
+
+int fds_upload_probes(fds_ctx *ctx, int32_t component, const int64_t *cells, const int32_t *slots,
+                      int64_t n, int64_t n_slots_total) {
+    if (!ctx) return fail(ctx, "fds_upload_probes: null context");
+    if (component < 0 || component >= ctx->ncomp) return fail(ctx, "fds_upload_probes: bad component");
+    if (n < 0 || n > 0x7fffffff || n_slots_total < 0 || n_slots_total > 0x7fffffff)
+        return fail(ctx, "fds_upload_probes: bad sizes");
+    for (int64_t k = 0; k < n; ++k) {
+        if (cells[k] < 0 || cells[k] >= ctx->owned)
+            return fail(ctx, "fds_upload_probes: cell not owned by the slab");
+        if (k && cells[k] < cells[k - 1])
+            return fail(ctx, "fds_upload_probes: cells must be ascending");
+        if (slots[k] < 0 || slots[k] >= n_slots_total)
+            return fail(ctx, "fds_upload_probes: slot out of range");
+    }
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    if (dev_upload(ctx, ctx->pcells[component], cells, (size_t)n * 8)) return 1;
+    if (dev_upload(ctx, ctx->pslots[component], slots, (size_t)n * 4)) return 1;
+    ctx->n_probes[component] = n;
+    ctx->n_slots = n_slots_total;
+    ctx->flags_dirty = true;
+    return 0;
+}
+
+int fds_upload_state(fds_ctx *ctx, int32_t component, const double *values, int64_t n) {
+    if (!ctx || !values) return fail(ctx, "fds_upload_state: null argument");
+    if (component < 0 || component >= ctx->ncomp) return fail(ctx, "fds_upload_state: bad component");
+    if (n != ctx->owned) return fail(ctx, "fds_upload_state: expected rows * nx values");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    FDS_CUDA(ctx, cudaMemcpyAsync(origin(ctx, ctx->cur, component), values, (size_t)n * 8,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int fds_download_state(fds_ctx *ctx, int32_t component, double *values, int64_t n) {
+    if (!ctx || !values) return fail(ctx, "fds_download_state: null argument");
+    if (component < 0 || component >= ctx->ncomp)
+        return fail(ctx, "fds_download_state: bad component");
+    if (n != ctx->owned) return fail(ctx, "fds_download_state: expected rows * nx values");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    FDS_CUDA(ctx, cudaMemcpyAsync(values, origin(ctx, ctx->cur, component), (size_t)n * 8,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int fds_reset_state(fds_ctx *ctx) {
+    if (!ctx) return fail(ctx, "fds_reset_state: null context");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < ctx->ncomp; ++c)
+            FDS_CUDA(ctx, cudaMemsetAsync(ctx->buf[b][c], 0, (size_t)ctx->alloc * 8, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int fds_step(fds_ctx *ctx, int64_t first_step, int64_t n_steps, double *probes_out) {
+    if (!ctx) return fail(ctx, "fds_step: null context");
+    if (n_steps < 0) return fail(ctx, "fds_step: negative step count");
+    if (ctx->n_slots > 0 && n_steps > 0 && !probes_out)
+        return fail(ctx, "fds_step: probes are configured but probes_out is NULL");
+    if (ctx->comm && ctx->world > 1 && ctx->dims == 2) {
+        // neighbours need our current rows before the first step
+        FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+        FDS_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
+        FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
+        if (exchange_halos(ctx, ctx->cur)) return 1;
+        FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+        FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+    }
+    if (run_steps(ctx, first_step, n_steps, true)) return 1;
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->drain));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    if (ctx->n_slots > 0 && n_steps > 0) {
+        // copy only the slots this slab owns; the others belong to other ranks
+        std::vector<char> mine((size_t)ctx->n_slots, 0);
+        bool all = true;
+        {
+            std::vector<int> slots;
+            for (int c = 0; c < ctx->ncomp; ++c) {
+                if (!ctx->n_probes[c]) continue;
+                slots.resize((size_t)ctx->n_probes[c]);
+                FDS_CUDA(ctx, cudaMemcpy(slots.data(), ctx->pslots[c].ptr,
+                                         (size_t)ctx->n_probes[c] * 4, cudaMemcpyDeviceToHost));
+                for (int s : slots) mine[(size_t)s] = 1;
+            }
+            for (char m : mine) all = all && m;
+        }
+        const double *src = (const double *)ctx->pinned;
+        if (all) {
+            memcpy(probes_out, src, (size_t)n_steps * ctx->n_slots * 8);
+        } else {
+            for (int64_t s = 0; s < n_steps; ++s)
+                for (int64_t k = 0; k < ctx->n_slots; ++k)
+                    if (mine[(size_t)k]) probes_out[s * ctx->n_slots + k] = src[s * ctx->n_slots + k];
+        }
+    }
+    return 0;
+}
+
+int fds_step_async(fds_ctx *ctx, int64_t first_step, int64_t n_steps) {
+    if (!ctx) return fail(ctx, "fds_step_async: null context");
+    if (n_steps < 0) return fail(ctx, "fds_step_async: negative step count");
+    return run_steps(ctx, first_step, n_steps, false);
+}
+
+int fds_sync(fds_ctx *ctx) {
+    if (!ctx) return fail(ctx, "fds_sync: null context");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->drain));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    return 0;
+}
+
+int fds_comm_unique_id(uint8_t id[128]) {
+    if (const char *e = load_nccl()) return fail(nullptr, std::string("fds_comm_unique_id: ") + e);
+    nccl_unique_id uid;
+    int rc = g_nccl.GetUniqueId(&uid);
+    if (rc) return fail(nullptr, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+    memcpy(id, uid.internal, 128);
+    return 0;
+}
+
+int fds_comm_init(fds_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t world) {
+    if (!ctx || !id) return fail(ctx, "fds_comm_init: null argument");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, "fds_comm_init: bad rank/world");
+    if (world > 1 && ctx->d.halo_rows < 1)
+        return fail(ctx, "fds_comm_init: a multi-slab run needs halo_rows >= 1");
+    if (const char *e = load_nccl()) return fail(ctx, std::string("fds_comm_init: ") + e);
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    nccl_unique_id uid;
+    memcpy(uid.internal, id, 128);
+    FDS_NCCL(ctx, g_nccl.CommInitRank(&ctx->comm, world, uid, rank));
+    ctx->rank = rank;
+    ctx->world = world;
+    return 0;
+}
+
+int fds_last_step_ms(fds_ctx *ctx, double *ms) {
+    if (!ctx || !ms) return fail(ctx, "fds_last_step_ms: null argument");
+    if (!ctx->timed) return fail(ctx, "fds_last_step_ms: no step call recorded yet");
+    float f = 0.f;
+    FDS_CUDA(ctx, cudaEventElapsedTime(&f, ctx->ev_t0, ctx->ev_t1));
+    *ms = (double)f;
+    return 0;
+}
+
+int fds_last_launch_info(fds_ctx *ctx, int64_t *launches, int64_t *steps_per_launch,
+                         const char **kernel_name) {
+    if (!ctx) return fail(ctx, "fds_last_launch_info: null context");
+    if (launches) *launches = ctx->last_launches;
+    if (steps_per_launch) *steps_per_launch = ctx->last_steps_per_launch;
+    if (kernel_name) *kernel_name = ctx->last_kernel;
+    return 0;
+}
+
+int64_t fds_device_bytes(const fds_ctx *ctx) { return ctx ? ctx->device_bytes : 0; }
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// 1-D kernels (Acoustic1D pyfds/acoustics.py:40-52, Thermal1D pyfds/thermal.py:40-51).
+//
+// A 1-D problem is a few thousand cells stepped tens of thousands of times: the state fits on chip and
+// the cost is synchronisation, not bandwidth. Each CTA therefore loads a tile of the line plus a halo
+// of `halo` cells per side into shared memory, advances it `n_steps` time steps there (boundaries,
+// sources and probes included) and stores the owned cells. Per step the region of valid values
+// shrinks by two cells per side (the lossy operator has reach 2), so n_steps <= halo / 2 when the line
+// is split over several CTAs; a line that fits one CTA has no neighbours and can take any number of
+// steps in a single launch. Cells outside the line are the zero padding with the void material.
+#pragma once
+
+#include "fds_common.cuh"
+
+namespace fds {
+
+struct Step1DArgs {
+    const double *in[2];   // origin at cell 0
+    double *out[2];
+    long long n;           // cells of the line
+    int tile;              // owned cells per CTA
+    int halo;              // extra cells loaded on either side (>= 2)
+    int n_steps;           // steps advanced by this launch
+    long long sig_index;   // first step - sig_first_step
+    long long ring_row;    // probe record of the first step
+};
+
+constexpr int k1DThreads = 1024;
+constexpr int k1DMaxPerThread = 14;   // (tile + 2*halo) <= 14 * 1024 cells = 238 KB of state + ids
+
+template <bool THERMAL, bool LOSSY>
+__global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, StepTables t) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int width = a.tile + 2 * a.halo;
+    double *s = reinterpret_cast<double *>(smem_raw);     // scalar component
+    double *u = s + width;                                // vector component
+    uint8_t *id = reinterpret_cast<uint8_t *>(u + width); // material id + flags
+    __shared__ double tabs[FDS_TAB_COUNT][kMaxMaterials];
+
+    const int tid = threadIdx.x;
+    const long long origin = (long long)blockIdx.x * a.tile - a.halo;  // global cell of local 0
+
+    for (int k = tid; k < FDS_TAB_COUNT * kMaxMaterials; k += k1DThreads)
+        (&tabs[0][0])[k] = t.tab[k];
+    for (int l = tid; l < width; l += k1DThreads) {
+        const long long g = origin + l;
+        s[l] = a.in[0][g];
+        u[l] = THERMAL ? 0.0 : a.in[1][g];
+        id[l] = t.map[g];
+    }
+    __syncthreads();
+
+    double unew[k1DMaxPerThread];
+    for (int q = 0; q < a.n_steps; ++q) {
+        const long long sig = a.sig_index + q;
+        double *__restrict__ record = t.ring + (a.ring_row + q) * t.n_slots;
+
+        // 1. boundaries and probes of the scalar component
+        for (int l = tid; l < width; l += k1DThreads) {
+            const uint8_t f = id[l];
+            if (f & (kFlagBound | kFlagProbe)) {
+                const long long g = origin + l;
+                double v = s[l];
+                if (f & kFlagBound) {
+                    v = apply_bounds(t.bound[0], t.signals, t.sig_steps, sig, g, v);
+                    s[l] = v;
+                }
+                if ((f & kFlagProbe) && l >= a.halo && l < a.halo + a.tile)
+                    write_probes(t.probe[0], record, g, v);
+            }
+        }
+        __syncthreads();
+
+        // 2. vector component: backward difference of the scalar (+ viscous second difference)
+#pragma unroll
+        for (int r = 0; r < k1DMaxPerThread; ++r) {
+            const int l = tid + r * k1DThreads;
+            if (l >= 2 && l < width - 2 && (id[l] & kIdMask)) {
+                const int m = id[l] & kIdMask, mm = id[l - 1] & kIdMask;
+                const double d = diff2(tabs[FDS_TAB_GX][mm], s[l - 1], tabs[FDS_TAB_GX][m], s[l]);
+                if (THERMAL) {
+                    unew[r] = -d;
+                } else if (LOSSY) {
+                    const int mp = id[l + 1] & kIdMask;
+                    double vis = acc0(mul(tabs[FDS_TAB_VM1][mm], u[l - 1]));
+                    vis = add(vis, mul(tabs[FDS_TAB_V0][m], u[l]));
+                    vis = add(vis, mul(tabs[FDS_TAB_VP1][mp], u[l + 1]));
+                    unew[r] = sub(u[l], sub(d, vis));
+                } else {
+                    unew[r] = sub(u[l], d);
+                }
+            }
+        }
+        if (LOSSY) __syncthreads();
+
+        // 3. boundaries and probes of the vector component
+#pragma unroll
+        for (int r = 0; r < k1DMaxPerThread; ++r) {
+            const int l = tid + r * k1DThreads;
+            if (l >= 2 && l < width - 2 && (id[l] & kIdMask)) {
+                const uint8_t f = id[l];
+                double v = unew[r];
+                if (f & (kFlagBound | kFlagProbe)) {
+                    const long long g = origin + l;
+                    if (f & kFlagBound)
+                        v = apply_bounds(t.bound[1], t.signals, t.sig_steps, sig, g, v);
+                    if ((f & kFlagProbe) && l >= a.halo && l < a.halo + a.tile)
+                        write_probes(t.probe[1], record, g, v);
+                }
+                u[l] = v;
+            }
+        }
+        __syncthreads();
+
+        // 4. scalar component: forward difference of the vector component
+#pragma unroll
+        for (int r = 0; r < k1DMaxPerThread; ++r) {
+            const int l = tid + r * k1DThreads;
+            if (l >= 2 && l < width - 2 && (id[l] & kIdMask)) {
+                const int m = id[l] & kIdMask, mp = id[l + 1] & kIdMask;
+                s[l] = sub(s[l], diff2(tabs[FDS_TAB_FX][m], u[l], tabs[FDS_TAB_FX][mp], u[l + 1]));
+            }
+        }
+        // no barrier: phase 1 of the next step only touches a thread's own cells
+    }
+    __syncthreads();
+
+    for (int l = a.halo + tid; l < a.halo + a.tile; l += k1DThreads) {
+        const long long g = origin + l;
+        if (g < a.n) {
+            a.out[0][g] = s[l];
+            a.out[1][g] = u[l];
+        }
+    }
+}
+
+}  // namespace fds

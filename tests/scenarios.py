@@ -1,0 +1,281 @@
+"""Simulation scenarios written against the *pyfds public API only*, so that the very same builder
+runs on the real reference (``oracle/gen_golden.py``, in the build container), on ``pyfds_b200`` (the
+GPU parity tests) and feeds the CPU restatement in ``oracle/restate.py``.
+
+Every builder takes the package module (``pyfds`` or ``pyfds_b200``) and returns
+``(field, n_steps)``; nothing here is random except through the fixed seeds below.
+"""
+
+import numpy as np
+
+
+def _pulse(t_samples, centre, width, omega=0.1):
+    k = np.arange(t_samples)
+    return np.sin(omega * k) * np.exp(-((k - centre) / width) ** 2)
+
+
+def _randomise(field, names, seed, scale=1e-3):
+    rng = np.random.default_rng(seed)
+    for name in names:
+        component = getattr(field, name)
+        component.values = scale * rng.standard_normal(component.values.shape[0])
+
+
+def acoustic1d_lossy(fds):
+    """Config 1 of BASELINE.json scaled down (doc/ex_acoustics.rst:14-37): viscous fluid, rigid and
+    pressure-release ends, additive pulse, one probe; plus a second material in the middle."""
+    fld = fds.Acoustic1D(t_delta=1e-7, t_samples=400, x_delta=1e-3, x_samples=300,
+                         material=fds.AcousticMaterial(700, 0.01, shear_viscosity=1e-3))
+    fld.add_material_region(fld.get_line_region((120e-3, 170e-3)),
+                            fds.AcousticMaterial(650, 0.012, bulk_viscosity=2e-3))
+    fld.velocity.add_boundary(fld.get_point_region(0))
+    fld.pressure.add_boundary(fld.get_point_region(299 * 1e-3))
+    fld.pressure.add_boundary(fld.get_point_region(100 * 1e-3), value=_pulse(400, 60, 20),
+                              additive=True)
+    fld.pressure.add_output(fld.get_point_region(200 * 1e-3))
+    fld.velocity.add_output(fld.get_line_region((10 * 1e-3, 14 * 1e-3)))
+    return fld, 400
+
+
+def acoustic1d_lossless(fds):
+    """Lossless 1-D line with a random initial state: every cell and both global ends active."""
+    fld = fds.Acoustic1D(t_delta=1e-7, t_samples=250, x_delta=1e-3, x_samples=257,
+                         material=fds.AcousticMaterial(700, 0.01))
+    _randomise(fld, ('pressure', 'velocity'), seed=1)
+    fld.pressure.add_output(fld.get_point_region(0))
+    fld.pressure.add_output(fld.get_point_region(256 * 1e-3))
+    return fld, 250
+
+
+def acoustic1d_long(fds):
+    """Longer than one CTA tile can hold: exercises the multi-tile 1-D path with its halos."""
+    fld = fds.Acoustic1D(t_delta=1e-7, t_samples=150, x_delta=1e-3, x_samples=20000,
+                         material=fds.AcousticMaterial(700, 0.01, shear_viscosity=1e-3))
+    fld.add_material_region(fld.get_line_region((3.9, 4.3)), fds.AcousticMaterial(600, 0.02))
+    _randomise(fld, ('pressure', 'velocity'), seed=2)
+    fld.velocity.add_boundary(fld.get_point_region(0))
+    fld.pressure.add_boundary(fld.get_point_region(3968 * 1e-3), value=_pulse(150, 40, 15),
+                              additive=True)
+    fld.pressure.add_output(fld.get_point_region(3967 * 1e-3))
+    fld.pressure.add_output(fld.get_point_region(3969 * 1e-3))
+    fld.velocity.add_output(fld.get_point_region(19999 * 1e-3))
+    return fld, 150
+
+
+def _acoustic2d(fds, lossy, nx=48, ny=40, steps=120, seed=3, klass='Acoustic2D'):
+    """Config 2 of BASELINE.json scaled down: two materials, additive point source, rigid line at
+    x=0 (doc/ex_acoustics.rst:73-74), four pressure probes; random initial state."""
+    main = fds.AcousticMaterial(1500, 1000, shear_viscosity=1e-3 if lossy else 0)
+    fld = getattr(fds, klass)(t_delta=1e-7, t_samples=steps, x_delta=1e-3, x_samples=nx,
+                              y_delta=1e-3, y_samples=ny, material=main)
+    qx, qy = nx // 4, ny // 4
+    second = fds.AcousticMaterial(1200, 900, absorption_coef=7.7 if lossy else None)
+    fld.add_material_region(fld.get_rect_region((qx * 1e-3, qy * 1e-3, qx * 1e-3, qy * 1e-3)),
+                            second)
+    _randomise(fld, ('pressure', 'velocity_x', 'velocity_y'), seed=seed)
+    fld.pressure.add_boundary(fld.get_point_region(((nx // 2) * 1e-3, (ny // 2) * 1e-3)),
+                              value=_pulse(steps, 40, 15), additive=True)
+    fld.velocity_x.add_boundary(fld.get_line_region((0, 0, 0, (ny - 1) * 1e-3)))
+    for m in range(1, 5):
+        fld.pressure.add_output(fld.get_point_region(((m * nx // 5) * 1e-3, (m * ny // 5) * 1e-3)))
+    return fld, steps
+
+
+def acoustic2d_lossless(fds):
+    return _acoustic2d(fds, lossy=False)
+
+
+def acoustic2d_lossy(fds):
+    return _acoustic2d(fds, lossy=True)
+
+
+def acoustic2d_wide(fds):
+    """Wide enough (nx = 400) for the streaming kernel to run several strips side by side, odd ny."""
+    return _acoustic2d(fds, lossy=False, nx=400, ny=75, steps=60, seed=4)
+
+
+def acoustic2d_boundaries(fds):
+    """Every boundary flavour at once (pyfds/regions.py:136-145), overlapping and in list order, on
+    the first and last cell of the grid, with probes on the very same cells."""
+    nx, ny, steps = 37, 29, 80
+    fld = fds.Acoustic2D(t_delta=1e-7, t_samples=steps, x_delta=1e-3, x_samples=nx,
+                         y_delta=1e-3, y_samples=ny, material=fds.AcousticMaterial(1500, 1000))
+    _randomise(fld, ('pressure', 'velocity_x', 'velocity_y'), seed=5)
+    top = fld.get_line_region((0, (ny - 1) * 1e-3, (nx - 1) * 1e-3, (ny - 1) * 1e-3))
+    left = fld.get_line_region((0, 0, 0, (ny - 1) * 1e-3))
+    diag = fld.get_line_region((3e-3, 2e-3, 30e-3, 20e-3))
+    first, last = fld.get_point_region((0, 0)), fld.get_point_region(((nx - 1) * 1e-3,
+                                                                       (ny - 1) * 1e-3))
+    # pressure: fixed value, then an additive scalar on an overlapping line, then a signal
+    fld.pressure.add_boundary(top, value=0)
+    fld.pressure.add_boundary(left, value=2.5e-4, additive=True)
+    fld.pressure.add_boundary(diag, value=_pulse(steps, 30, 12), additive=True)
+    fld.pressure.add_boundary(last, value=1e-3)
+    fld.pressure.add_boundary(first, value=_pulse(steps, 20, 9, omega=0.3))
+    # velocity_y: one signal per point, additive; region with a duplicated index (last write wins)
+    region = fds.regions.LineRegion([5 + 4 * nx, 6 + 4 * nx, 7 + 4 * nx, 6 + 4 * nx],
+                                    (0, 0, 0, 0), 'explicit')
+    signals = [_pulse(steps, 25, 10, omega=0.1 * (k + 1)) for k in range(4)]
+    fld.velocity_y.add_boundary(region, value=signals, additive=True)
+    fld.velocity_x.add_boundary(left)
+    fld.velocity_x.add_boundary(top, value=-1e-5, additive=True)
+    for component in (fld.pressure, fld.velocity_x, fld.velocity_y):
+        component.add_output(first)
+        component.add_output(last)
+        component.add_output(diag)
+    fld.velocity_y.add_output(region)
+    return fld, steps
+
+
+def acoustic3daxi_lossy(fds):
+    """Config 3 of BASELINE.json scaled down: viscous medium, lossy sponge regions along three edges
+    (the reference has no absorbing boundary), Dirichlet lines, additive line source, line probe."""
+    nx, ny, steps = 40, 36, 100
+    main = fds.AcousticMaterial(1500, 1000, shear_viscosity=1e-3)
+    sponge = fds.AcousticMaterial(1500, 1000, absorption_coef=500)
+    fld = fds.Acoustic3DAxi(t_delta=1e-7, t_samples=steps, x_delta=1e-3, x_samples=nx,
+                            y_delta=1e-3, y_samples=ny, material=main)
+    w = 6
+    X, Y = (nx - 1) * 1e-3, (ny - 1) * 1e-3
+    fld.add_material_region(fld.get_rect_region(((nx - w) * 1e-3, 0, (w - 1) * 1e-3, Y)), sponge)
+    fld.add_material_region(fld.get_rect_region((0, 0, X, (w - 1) * 1e-3)), sponge)
+    fld.add_material_region(fld.get_rect_region((0, (ny - w) * 1e-3, X, (w - 1) * 1e-3)), sponge)
+    _randomise(fld, ('pressure', 'velocity_x', 'velocity_y'), seed=6)
+    for line in ((X, 0, X, Y), (0, 0, X, 0), (0, Y, X, Y)):
+        fld.pressure.add_boundary(fld.get_line_region(line))
+    fld.velocity_x.add_boundary(fld.get_line_region((0, 0, 0, Y)))
+    fld.pressure.add_boundary(fld.get_line_region((0, 18e-3, 8e-3, 18e-3)),
+                              value=_pulse(steps, 35, 14), additive=True)
+    fld.pressure.add_output(fld.get_line_region((0, 25e-3, 12e-3, 25e-3)))
+    fld.velocity_x.add_output(fld.get_point_region((5e-3, 5e-3)))
+    return fld, steps
+
+
+def acoustic3daxi_lossless(fds):
+    fld, steps = _acoustic2d(fds, lossy=False, nx=33, ny=41, steps=90, seed=7,
+                             klass='Acoustic3DAxi')
+    return fld, steps
+
+
+def _thermal2d(fds, klass, nx, ny, steps, seed):
+    """Config 4 of BASELINE.json scaled down: two materials (one anisotropic), Dirichlet temperature
+    on x=0 / x=max, adiabatic (zero flux) y=0 / y=max, probes on temperature and flux."""
+    fld = getattr(fds, klass)(t_delta=1e-3, t_samples=steps, x_delta=1e-3, x_samples=nx,
+                              y_delta=1e-3, y_samples=ny,
+                              material=fds.ThermalMaterial(900, 2700, 200))
+    fld.add_material_region(
+        fld.get_rect_region(((nx // 3) * 1e-3, (ny // 3) * 1e-3, (nx // 4) * 1e-3,
+                             (ny // 4) * 1e-3)), fds.ThermalMaterial(450, 7800, (50, 30)))
+    rng = np.random.default_rng(seed)
+    fld.temperature.values = 20 + rng.standard_normal(nx * ny)
+    X, Y = (nx - 1) * 1e-3, (ny - 1) * 1e-3
+    fld.temperature.add_boundary(fld.get_line_region((0, 0, 0, Y)), value=100)
+    fld.temperature.add_boundary(fld.get_line_region((X, 0, X, Y)), value=0)
+    fld.heat_flux_y.add_boundary(fld.get_line_region((0, 0, X, 0)), value=0)
+    fld.heat_flux_y.add_boundary(fld.get_line_region((0, Y, X, Y)), value=0)
+    fld.heat_flux_x.add_boundary(fld.get_point_region((5e-3, 5e-3)), value=1e-2, additive=True)
+    for m in range(1, 5):
+        fld.temperature.add_output(
+            fld.get_point_region(((m * nx // 5) * 1e-3, (m * ny // 5) * 1e-3)))
+    fld.heat_flux_x.add_output(fld.get_line_region((1e-3, 3e-3, 6e-3, 3e-3)))
+    fld.heat_flux_y.add_output(fld.get_point_region((0, 0)))
+    return fld, steps
+
+
+def thermal2d(fds):
+    return _thermal2d(fds, 'Thermal2D', 44, 32, 150, seed=8)
+
+
+def thermal3daxi(fds):
+    return _thermal2d(fds, 'Thermal3DAxi', 30, 35, 120, seed=9)
+
+
+def thermal1d(fds):
+    fld = fds.Thermal1D(t_delta=1e-3, t_samples=300, x_delta=1e-3, x_samples=181,
+                        material=fds.ThermalMaterial(900, 2700, 200))
+    fld.add_material_region(fld.get_line_region((60e-3, 99e-3)), fds.ThermalMaterial(450, 7800, 50))
+    rng = np.random.default_rng(10)
+    fld.temperature.values = 20 + rng.standard_normal(181)
+    fld.temperature.add_boundary(fld.get_point_region(0), value=100)
+    fld.heat_flux.add_boundary(fld.get_point_region(180e-3), value=0)
+    fld.temperature.add_output(fld.get_line_region((50e-3, 53e-3)))
+    fld.heat_flux.add_output(fld.get_point_region(90e-3))
+    return fld, 300
+
+
+SCENARIOS = {
+    'acoustic1d_lossy': acoustic1d_lossy,
+    'acoustic1d_lossless': acoustic1d_lossless,
+    'acoustic1d_long': acoustic1d_long,
+    'acoustic2d_lossless': acoustic2d_lossless,
+    'acoustic2d_lossy': acoustic2d_lossy,
+    'acoustic2d_wide': acoustic2d_wide,
+    'acoustic2d_boundaries': acoustic2d_boundaries,
+    'acoustic3daxi_lossy': acoustic3daxi_lossy,
+    'acoustic3daxi_lossless': acoustic3daxi_lossless,
+    'thermal2d': thermal2d,
+    'thermal3daxi': thermal3daxi,
+    'thermal1d': thermal1d,
+}
+
+
+def component_names(field):
+    for names in (('pressure', 'velocity'), ('pressure', 'velocity_x', 'velocity_y'),
+                  ('temperature', 'heat_flux'), ('temperature', 'heat_flux_x', 'heat_flux_y')):
+        if all(hasattr(field, n) for n in names) and len(names) == (2 if not hasattr(field, 'y')
+                                                                   else 3):
+            return names
+    raise TypeError('unknown field type')
+
+
+def collect(field):
+    """Final values and probe signals of a field that was stepped through the pyfds API, as a flat
+    dict of arrays (the golden file layout)."""
+    out = {}
+    for name in component_names(field):
+        component = getattr(field, name)
+        out['values/' + name] = np.asarray(component.values, dtype=np.float64)
+        for k, output in enumerate(component.outputs):
+            out['signals/{}/{}'.format(name, k)] = np.asarray(output.signals, dtype=np.float64)
+    out['step'] = np.asarray(field.step)
+    return out
+
+
+def collect_stepper(stepper):
+    """Same layout from an ``oracle.restate`` stepper."""
+    out = {}
+    for name in stepper.components:
+        out['values/' + name] = stepper.values(name)
+        for k, signals in enumerate(stepper.signals(name)):
+            out['signals/{}/{}'.format(name, k)] = signals
+    out['step'] = np.asarray(stepper.step)
+    return out
+
+
+# ---- region index maps (pyfds/fields.py:391-533) -------------------------------------------------
+
+def region_cases(fds):
+    """Named region constructions whose ``indices`` (values *and* order) are pinned by goldens."""
+    f = fds.fields.Field2D(61, 1e-3, 47, 5e-4, 10, 1.0, int(5))
+    g = fds.fields.Field1D(50, 0.1, 10, 1.0, int(5))
+    cases = {
+        'line_h': f.get_line_region((2e-3, 3e-3, 40e-3, 3e-3)),
+        'line_h_rev': f.get_line_region((40e-3, 3e-3, 2e-3, 3e-3)),
+        'line_v': f.get_line_region((7e-3, 1e-3, 7e-3, 20e-3)),
+        'line_diag': f.get_line_region((0, 0, 23e-3, 23 * 5e-4)),
+        'line_diag_rev': f.get_line_region((30e-3, 2 * 5e-4, 10e-3, 22 * 5e-4)),
+        'line_shallow': f.get_line_region((1e-3, 1e-3, 58e-3, 9e-3)),
+        'line_steep': f.get_line_region((50e-3, 22e-3, 41e-3, 5e-4)),
+        'line_half': f.get_line_region((0, 0, 10e-3, 5 * 5e-4)),
+        'rect': f.get_rect_region((5e-3, 2e-3, 12e-3, 6e-3)),
+        'rect_neg': f.get_rect_region((30e-3, 10e-3, -7e-3, -4e-3)),
+        'rect_full': f.get_rect_region((0, 0, 60e-3, 23e-3)),
+        'tri_cw': f.get_tri_region((5e-3, 2e-3, 30e-3, 20e-3, 50e-3, 4e-3)),
+        'tri_ccw': f.get_tri_region((5e-3, 2e-3, 50e-3, 4e-3, 30e-3, 20e-3)),
+        'ellipse': f.get_ellipse_region((30e-3, 11e-3), (12e-3, 6e-3)),
+        'circle': f.get_ellipse_region((25e-3, 10e-3), 5e-3),
+        'point': f.get_point_region((13e-3, 7 * 5e-4)),
+        'line_1d': g.get_line_region((0.3, 2.5)),
+        'point_1d': g.get_point_region(4.9),
+    }
+    return cases
