@@ -1,0 +1,160 @@
+"""Parity of the CUDA path against the reference (-m gpu): every scenario of tests/scenarios.py is run
+through the drop-in's public API (`simulate()` -> ctypes -> C ABI -> sm_100a kernels) and compared
+
+* bit for bit (fp64 viewed as int64, so signed zeros count) with the golden fields and probe signals
+  that the REAL reference produced in the build container (tests/golden/, oracle/gen_golden.py);
+* bit for bit with the CPU restatement (oracle/restate.py) on larger grids and on cases that have no
+  golden file.
+
+The north-star tolerance is a relative L2 error <= 1e-12; bit equality is stricter and is what we
+assert. Nothing here reads /root/reference.
+"""
+
+import os
+
+import numpy as np
+import pytest
+
+import pyfds_b200 as fds
+import scenarios
+from conftest import bits
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def assert_same(got, expected, context=''):
+    assert sorted(got) == sorted(expected), context
+    for key in expected:
+        g, e = np.asarray(got[key]), np.asarray(expected[key])
+        assert g.shape == e.shape, (context, key, g.shape, e.shape)
+        if not np.array_equal(bits(g), bits(e)):
+            denom = np.linalg.norm(e.ravel()) or 1.0
+            rel = np.linalg.norm((g - e).ravel()) / denom
+            bad = int(np.sum(bits(g) != bits(e)))
+            raise AssertionError('{} {}: {} of {} values differ, rel L2 {:.3e}'.format(
+                context, key, bad, e.size, rel))
+
+
+@pytest.mark.parametrize('name', sorted(scenarios.SCENARIOS))
+def test_scenario_matches_reference_golden_bitwise(library, name):
+    field, steps = scenarios.SCENARIOS[name](fds)
+    first = steps // 3
+    field.simulate(first)                 # segmented exactly like the golden run
+    field.simulate(steps - first)
+    got = scenarios.collect(field)
+    gold = np.load(os.path.join(GOLDEN, name + '.npz'))
+    assert_same(got, {k: gold[k] for k in gold.files if k != 'versions'}, name)
+
+
+@pytest.mark.parametrize('name', ['acoustic2d_lossless', 'acoustic1d_lossy', 'thermal2d'])
+def test_single_steps_equal_one_run(library, name):
+    """sim_step() is the coupling seam (pyfds/coupling.py:81-87): host values must be coherent before
+    and after every single step, and n single steps must equal one n-step run."""
+    field, steps = scenarios.SCENARIOS[name](fds)
+    steps = min(steps, 25)
+    for _ in range(steps):
+        field.sim_step()
+        field.step += 1
+    other, _ = scenarios.SCENARIOS[name](fds)
+    other.simulate(steps)
+    names = scenarios.component_names(field)
+    for n in names:
+        assert np.array_equal(bits(getattr(field, n).values), bits(getattr(other, n).values)), n
+
+
+def _vs_oracle(field, steps, context):
+    stepper = restate.stepper_for(field)
+    stepper.run(steps)
+    field.simulate(steps)
+    assert_same(scenarios.collect(field), scenarios.collect_stepper(stepper), context)
+
+
+@pytest.mark.parametrize('lossy', [False, True])
+def test_acoustic2d_medium_grid_vs_oracle(library, lossy):
+    field, _ = scenarios._acoustic2d(fds, lossy=lossy, nx=512, ny=384, steps=40, seed=11)
+    _vs_oracle(field, 40, 'acoustic2d 512x384 lossy={}'.format(lossy))
+
+
+def test_acoustic2d_odd_sizes_vs_oracle(library):
+    field, _ = scenarios._acoustic2d(fds, lossy=False, nx=333, ny=127, steps=50, seed=12)
+    _vs_oracle(field, 50, 'acoustic2d 333x127')
+
+
+def test_axisymmetric_medium_grid_vs_oracle(library):
+    field, _ = scenarios._acoustic2d(fds, lossy=True, nx=256, ny=200, steps=30, seed=13,
+                                     klass='Acoustic3DAxi')
+    _vs_oracle(field, 30, 'acoustic3daxi 256x200')
+
+
+def test_thermal2d_medium_grid_vs_oracle(library):
+    field, _ = scenarios._thermal2d(fds, 'Thermal2D', 320, 256, 60, seed=14)
+    _vs_oracle(field, 60, 'thermal2d 320x256')
+
+
+def test_config2_shape_1024_vs_oracle(library):
+    """BASELINE.json config 2 (two materials, point source, rigid line, 4 probes) at 1024^2 with a
+    random initial state so that every cell is exercised ('parity variant')."""
+    field, _ = scenarios._acoustic2d(fds, lossy=False, nx=1024, ny=1024, steps=20, seed=15)
+    _vs_oracle(field, 20, 'acoustic2d 1024^2')
+
+
+def test_signal_too_short_raises_before_launch(library):
+    field, steps = scenarios.acoustic2d_lossless(fds)
+    field.simulate(steps)
+    with pytest.raises(IndexError):
+        field.simulate(1)          # the source signal has exactly `steps` samples
+
+
+def test_reset_and_rerun_reproduces(library):
+    field, steps = scenarios.acoustic1d_lossy(fds)
+    field.simulate(steps)
+    first = scenarios.collect(field)
+    field.reset()
+    for component in (field.pressure, field.velocity):
+        for output in component.outputs:
+            output.signals = []
+    field.simulate(steps)
+    assert_same(scenarios.collect(field), first, 'rerun after reset')
+
+
+def test_round_trip_properties_at_full_size(library):
+    """Size-independent properties at BASELINE.json's config-2 size (4096^2), where the oracle is too
+    slow for the default suite: (1) a zero field with no source stays exactly zero; (2) with a point
+    source the run is deterministic and the probes record the source cell exactly as the boundary
+    wrote it; (3) segmented and unsegmented runs agree bitwise."""
+    n = 4096
+    steps = 12
+    def build():
+        f = fds.Acoustic2D(t_delta=1e-7, t_samples=steps, x_delta=1e-3, x_samples=n, y_delta=1e-3,
+                           y_samples=n, material=fds.AcousticMaterial(1500, 1000))
+        f.add_material_region(f.get_rect_region((1024 * 1e-3, 1024 * 1e-3, 1024 * 1e-3, 1024 * 1e-3)),
+                              fds.AcousticMaterial(1200, 900))
+        return f
+    quiet = build()
+    quiet.simulate(3)
+    assert not quiet.pressure.values.any() and not quiet.velocity_x.values.any()
+
+    def run(segments):
+        f = build()
+        src = f.get_point_region((2048 * 1e-3, 2048 * 1e-3))
+        signal = np.sin(0.1 * np.arange(steps)) + 1.0
+        f.pressure.add_boundary(src, value=signal)           # not additive: p[src] = signal[step]
+        f.pressure.add_output(src)
+        f.velocity_x.add_boundary(f.get_line_region((0, 0, 0, (n - 1) * 1e-3)))
+        for count in segments:
+            f.simulate(count)
+        return f, signal
+    a, signal = run([steps])
+    b, _ = run([5, 4, 3])
+    assert np.array_equal(np.asarray(a.pressure.outputs[0].signals[0]), signal)
+    for name in ('pressure', 'velocity_x', 'velocity_y'):
+        assert np.array_equal(bits(getattr(a, name).values), bits(getattr(b, name).values)), name
+    # the disturbance travels at most one cell per step (leapfrog stencil reach)
+    p = a.pressure.values.reshape(n, n)
+    far = np.ones((n, n), dtype=bool)
+    far[2048 - steps - 1:2048 + steps + 2, 2048 - steps - 1:2048 + steps + 2] = False
+    assert not p[far].any()
+    assert p[2048, 2048 + steps - 2] != 0.0
