@@ -261,9 +261,14 @@ def halo_rows_for(field, world):
     return 2 if field._baked['lossy'] else 1
 
 
-def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=0):
+def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None):
     """Creates (or reuses) the device context of ``field`` and uploads what ``assemble_matrices``
-    froze: the material map and the coefficient tables. Returns the ``Engine``."""
+    froze: the material map and the coefficient tables. Returns the ``Engine``.
+
+    ``kernel``: 0 automatic, 1 one-step kernel, 2 streaming multi-step kernel (``fds_desc.kernel``);
+    defaults to the field attribute ``device_kernel`` (0 if absent)."""
+    if kernel is None:
+        kernel = getattr(field, 'device_kernel', 0)
     state = field.__dict__.get('_engine_state')
     if state is None:
         state = field.__dict__['_engine_state'] = _State()

@@ -127,6 +127,10 @@ struct fds_ctx {
     ncclComm *comm = nullptr;
     int rank = 0, world = 1;
 
+    bool use_stream2d = false; // streaming multi-step kernel selected
+    int chunk_rows = 0;       // rows per streaming task (0 = heuristic)
+    int max_k = kMaxStreamSteps;
+
     std::string err;
 };
 
@@ -320,6 +324,52 @@ const char *step2d_name(const fds_ctx *ctx) {
     return "none";
 }
 
+
+// ---- streaming multi-step kernel (fds_stream2d.cuh) ---------------------------------------------
+
+bool stream_supported(const fds_desc &d) {
+    return d.model == FDS_ACOUSTIC2D && !d.lossy && d.nx % 4 == 0 && d.nx >= kStripCells;
+}
+
+int stream_chunk_rows(const fds_ctx *ctx, long long rows, int n_strips) {
+    if (ctx->chunk_rows > 0) return ctx->chunk_rows;
+    // enough tasks for >= 2 waves of (SMs x resident warps), chunks between 32 and 256 rows
+    const long long slots = 148ll * 2 * kStreamWarps;
+    long long h = 256;
+    while (h > 32 && n_strips * ((rows + h - 1) / h) < 2 * slots) h /= 2;
+    return (int)h;
+}
+
+template <int K>
+int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a, const StepTables &t) {
+    auto kernel = stream2d_kernel<K>;
+    const int smem = kStreamWarps * kWarpRingBytes;
+    static bool configured = false;
+    if (!configured) {
+        FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const long long ctas = (a.n_tasks + kStreamWarps - 1) / kStreamWarps;
+    kernel<<<(unsigned)ctas, kStreamWarps * 32, smem, ctx->stream>>>(a, t);
+    FDS_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, const StepTables &t, int k) {
+    const long long rows = a.row_end - a.row_begin;
+    if (rows <= 0) return 0;
+    a.n_strips = (int)((a.nx + kStripStride - 1) / kStripStride);
+    a.chunk_rows = stream_chunk_rows(ctx, rows, a.n_strips);
+    a.n_tasks = (long long)a.n_strips * ((rows + a.chunk_rows - 1) / a.chunk_rows);
+    switch (k) {
+        case 1: return launch_stream2d<1>(ctx, a, t);
+        case 2: return launch_stream2d<2>(ctx, a, t);
+        case 3: return launch_stream2d<3>(ctx, a, t);
+        case 4: return launch_stream2d<4>(ctx, a, t);
+    }
+    return fail(ctx, "stream2d: bad step count");
+}
+
 // 1-D tiling: owned cells per CTA, halo and steps per launch.
 struct Plan1D {
     int tile, halo, steps;
@@ -446,6 +496,42 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                                                   : "step1d_kernel<acoustic,lossless>";
                 ctx->last_steps_per_launch = p.steps;
                 ctx->last_launches += 1;
+            } else if (ctx->use_stream2d) {
+                Stream2DArgs a{};
+                for (int c = 0; c < 3; ++c) {
+                    a.in[c] = origin(ctx, ctx->cur, c);
+                    a.out[c] = origin(ctx, ctx->cur ^ 1, c);
+                }
+                a.nx = ctx->d.nx;
+                a.sig_index = sig0 + s;
+                a.ring_row = ring_row;
+                const long long rows = ctx->d.rows;
+                const bool multi = ctx->comm && ctx->world > 1;
+                int k = (int)std::min<long long>(ctx->max_k, chunk_steps - in_chunk);
+                if (multi) k = std::min<int>(k, ctx->d.halo_rows);
+                if (multi) {
+                    // the k outermost rows of either side travel while the interior is computed
+                    const long long band = std::min<long long>(ctx->d.halo_rows, rows);
+                    a.row_begin = 0; a.row_end = band;
+                    if (dispatch_stream2d(ctx, a, t, k)) return 1;
+                    a.row_begin = std::max(band, rows - band); a.row_end = rows;
+                    if (dispatch_stream2d(ctx, a, t, k)) return 1;
+                    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
+                    FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
+                    if (exchange_halos(ctx, ctx->cur ^ 1)) return 1;
+                    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+                    a.row_begin = band; a.row_end = std::max(band, rows - band);
+                    if (dispatch_stream2d(ctx, a, t, k)) return 1;
+                    FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+                    ctx->last_launches += 3;
+                } else {
+                    a.row_begin = 0; a.row_end = rows;
+                    if (dispatch_stream2d(ctx, a, t, k)) return 1;
+                    ctx->last_launches += 1;
+                }
+                advanced = k;
+                ctx->last_steps_per_launch = std::max<long long>(ctx->last_steps_per_launch, k);
+                ctx->last_kernel = "stream2d_kernel<acoustic2d,lossless>";
             } else {
                 Step2DArgs a{};
                 for (int c = 0; c < 3; ++c) {
@@ -584,6 +670,15 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
     ctx->axi = (d.model == FDS_ACOUSTIC3DAXI || d.model == FDS_THERMAL3DAXI);
     ctx->owned = d.rows * d.nx;
     ctx->halo = (long long)d.halo_rows * d.nx;
+    if (d.kernel == 2 && !stream_supported(d)) {
+        delete ctx;
+        return fail(nullptr, "fds_create: the streaming kernel needs lossless Acoustic2D with nx % 4 "
+                             "== 0 and nx >= 128");
+    }
+    ctx->use_stream2d = d.kernel != 1 && stream_supported(d);
+    if (const char *env = getenv("FDS_CHUNK_ROWS")) ctx->chunk_rows = atoi(env);
+    if (const char *env = getenv("FDS_MAX_K"))
+        ctx->max_k = std::max(1, std::min(kMaxStreamSteps, atoi(env)));
     // >= 9 rows + 4096 cells of padding, rounded so that the origin stays 512-byte aligned
     long long pad = (one_d ? 0 : 9 * d.nx) + 4096;
     pad = (pad + ctx->halo + 63) / 64 * 64 - ctx->halo;

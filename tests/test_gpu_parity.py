@@ -158,3 +158,64 @@ def test_round_trip_properties_at_full_size(library):
     far[2048 - steps - 1:2048 + steps + 2, 2048 - steps - 1:2048 + steps + 2] = False
     assert not p[far].any()
     assert p[2048, 2048 + steps - 2] != 0.0
+
+
+# ---- streaming multi-step kernel vs one-step kernel -------------------------------------------------
+
+def _stream_case(nx, ny, steps, seed, kernel):
+    """Boundaries, sources and probes placed on strip seams (x = 119, 120, 121, 240), on the halo
+    lanes, on the first/last rows and on chunk seams."""
+    f = fds.Acoustic2D(t_delta=1e-7, t_samples=steps, x_delta=1e-3, x_samples=nx, y_delta=1e-3,
+                       y_samples=ny, material=fds.AcousticMaterial(1500, 1000))
+    f.device_kernel = kernel
+    f.add_material_region(f.get_rect_region((100e-3, 10e-3, 45e-3, 30e-3)),
+                          fds.AcousticMaterial(1200, 900))
+    f.add_material_region(f.get_rect_region((119e-3, 20e-3, 2e-3, 40e-3)),
+                          fds.AcousticMaterial(1350, 950))
+    scenarios._randomise(f, ('pressure', 'velocity_x', 'velocity_y'), seed)
+    Y = (ny - 1) * 1e-3
+    f.velocity_x.add_boundary(f.get_line_region((0, 0, 0, Y)))
+    f.velocity_x.add_boundary(f.get_line_region((120e-3, 0, 120e-3, Y)), value=1e-6, additive=True)
+    f.velocity_y.add_boundary(f.get_line_region((0, 32e-3, (nx - 1) * 1e-3, 32e-3)))
+    f.pressure.add_boundary(f.get_line_region((0, 0, (nx - 1) * 1e-3, 0)))
+    f.pressure.add_boundary(f.get_line_region((0, Y, (nx - 1) * 1e-3, Y)), value=2e-4)
+    for k, x in enumerate((119, 120, 121, 240, 0, nx - 1)):
+        f.pressure.add_boundary(f.get_point_region((x * 1e-3, (5 + 9 * k) * 1e-3)),
+                                value=scenarios._pulse(steps, 10 + k, 6), additive=True)
+        f.pressure.add_output(f.get_point_region((x * 1e-3, (5 + 9 * k) * 1e-3)))
+        f.velocity_x.add_output(f.get_point_region((x * 1e-3, (6 + 9 * k) * 1e-3)))
+        f.velocity_y.add_output(f.get_point_region((x * 1e-3, 32e-3)))
+    f.pressure.add_output(f.get_line_region((100e-3, 31e-3, 140e-3, 31e-3)))
+    f.velocity_y.add_output(f.get_point_region((0, 0)))
+    f.velocity_y.add_output(f.get_point_region(((nx - 1) * 1e-3, Y)))
+    return f
+
+
+@pytest.mark.parametrize('nx,ny,steps', [(256, 70, 23), (128, 33, 9), (484, 150, 16)])
+def test_streaming_kernel_equals_one_step_kernel(library, nx, ny, steps):
+    results = []
+    for kernel in (1, 2):
+        f = _stream_case(nx, ny, steps, seed=31, kernel=kernel)
+        f.simulate(steps // 2)
+        f.simulate(steps - steps // 2)
+        results.append(scenarios.collect(f))
+        name = f.__dict__['_engine_state'].engine.last_launch_info()[2]
+        assert ('stream2d' in name) == (kernel == 2), name
+    assert_same(results[1], results[0], 'stream vs step {}x{}'.format(nx, ny))
+
+
+def test_streaming_kernel_vs_oracle_with_seams(library):
+    f = _stream_case(364, 90, 18, seed=32, kernel=2)
+    _vs_oracle(f, 18, 'stream2d 364x90')
+
+
+@pytest.mark.parametrize('max_k,chunk', [(1, 0), (2, 16), (3, 7), (4, 5)])
+def test_streaming_kernel_step_counts_and_chunking(library, max_k, chunk, monkeypatch):
+    """Every K (steps per launch) and odd chunk heights must give the same bits."""
+    monkeypatch.setenv('FDS_MAX_K', str(max_k))
+    monkeypatch.setenv('FDS_CHUNK_ROWS', str(chunk))
+    f = _stream_case(256, 61, 13, seed=33, kernel=2)
+    f.simulate(13)
+    g = _stream_case(256, 61, 13, seed=33, kernel=1)
+    g.simulate(13)
+    assert_same(scenarios.collect(f), scenarios.collect(g), 'K={} chunk={}'.format(max_k, chunk))
