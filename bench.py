@@ -38,7 +38,7 @@ BYTES_PER_CELL_UPDATE = 48        # p, vx, vy: fp64 read + write
 METRIC = 'Acoustic2D Gcell-updates/s'
 
 
-def build_field(fds, nx, ny, t_samples):
+def build_field(fds, nx, ny, t_samples, wall=True):
     """BASELINE.json configs[1] (SURVEY.md 8d 'C2 inputs'), scaled with the grid."""
     fld = fds.Acoustic2D(t_delta=1e-7, t_samples=t_samples, x_delta=1e-3, x_samples=nx,
                          y_delta=1e-3, y_samples=ny, material=fds.AcousticMaterial(1500, 1000))
@@ -49,7 +49,8 @@ def build_field(fds, nx, ny, t_samples):
     signal = np.sin(0.1 * k) * np.exp(-((k - 200) / 60) ** 2)
     fld.pressure.add_boundary(fld.get_point_region(((nx // 2) * 1e-3, (ny // 2) * 1e-3)),
                               value=signal, additive=True)
-    fld.velocity_x.add_boundary(fld.get_line_region((0, 0, 0, (ny - 1) * 1e-3)))
+    if wall:
+        fld.velocity_x.add_boundary(fld.get_line_region((0, 0, 0, (ny - 1) * 1e-3)))
     for m in range(1, 5):
         fld.pressure.add_output(fld.get_point_region(((m * nx // 8) * 1e-3, (m * ny // 8) * 1e-3)))
     return fld
@@ -193,6 +194,7 @@ def main():
     parser.add_argument('--kernel', type=int, default=0, help='0 auto, 1 one-step, 2 streaming')
     parser.add_argument('--no-cpu-baseline', action='store_true')
     parser.add_argument('--no-e2e', action='store_true')
+    parser.add_argument('--no-wall', action='store_true', help='experiment: drop the x=0 rigid line')
     args = parser.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -217,7 +219,7 @@ def main():
     nx, rows = args.size, args.size
     ny = rows * world
     total_steps = args.warmup + args.steps
-    field = build_field(fds, nx, ny, total_steps + 1)
+    field = build_field(fds, nx, ny, total_steps + 1, wall=not args.no_wall)
     field.assemble_matrices()
 
     # ---- device-resident run --------------------------------------------------------------------
@@ -281,7 +283,7 @@ def main():
         e2e = {'value': cells * args.steps / seconds / 1e9, 'unit': 'Gcell-updates/s',
                'h2d_bytes_per_step': state_bytes / args.steps,
                'd2h_bytes_per_step': (state_bytes + 4 * 8 * args.steps) / args.steps,
-               'seconds': seconds,
+               'seconds': seconds, 'phases': api_field.__dict__.get('_last_run_profile'),
                'what': 'field.simulate({}) from host numpy arrays: upload of p/vx/vy, boundary and '
                        'probe tables, {} steps, download of p/vx/vy and probe signals'.format(
                            args.steps, args.steps)}

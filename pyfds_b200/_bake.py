@@ -17,7 +17,7 @@ import numpy as np
 
 from . import regions as reg
 
-MAX_MATERIALS = 63
+MAX_MATERIALS = 31
 
 
 class MaterialSnapshot:

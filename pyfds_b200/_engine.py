@@ -357,14 +357,20 @@ def _host_values(component, num_points):
 
 
 def run(field, n_steps, progress_logger=None, advance=True):
-    """``n_steps`` x ``sim_step`` on the device: upload values, step, download values and probes."""
+    """``n_steps`` x ``sim_step`` on the device: upload values, step, download values and probes.
+    Wall-clock seconds of the phases are left in ``field.__dict__['_last_run_profile']``."""
+    import time
+    clock = time.perf_counter
+    t0 = clock()
     engine = prepare(field)
     first_step = field.step
     n_slots, layout = upload_run_tables(field, engine, first_step, n_steps)
+    t1 = clock()
 
     components = _components(field)
     for c, component in enumerate(components):
         engine.upload_state(c, _host_values(component, field.num_points))
+    t2 = clock()
 
     chunk = n_steps
     if n_slots:
@@ -381,6 +387,7 @@ def run(field, n_steps, progress_logger=None, advance=True):
             for s in range(first_step + done, first_step + done + count):
                 progress_logger.log(s)
         done += count
+    t3 = clock()
 
     for c, component in enumerate(components):
         target = component.values
@@ -390,6 +397,10 @@ def run(field, n_steps, progress_logger=None, advance=True):
             engine.download_state(c, out=target)
         else:
             component.values = engine.download_state(c)
+    t4 = clock()
+    field.__dict__['_last_run_profile'] = {
+        'prepare_and_tables_s': t1 - t0, 'upload_state_s': t2 - t1, 'step_s': t3 - t2,
+        'download_state_s': t4 - t3}
     if advance:
         field.step += n_steps
 

@@ -92,17 +92,25 @@ struct fds_ctx {
     long long pad = 0;        // pad cells per side (beyond the halo)
     long long alloc = 0;      // cells per buffer
     double *buf[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
-    uint8_t *map = nullptr;
+    map_t *map = nullptr;
     bool map_uploaded = false;
     double *tab = nullptr;
     double *ctab = nullptr;
     double *cvec = nullptr;
     int cur = 0;
 
-    DevArray bcells[3], boffsets[3], balpha[3], bvalue[3], bsignal[3];
+    DevArray bcells[3], boffsets[3], balpha[3], bvalue[3], bsignal[3], browptr[3];
     long long n_bcells[3] = {0, 0, 0};
-    DevArray pcells[3], pslots[3];
+    DevArray pcells[3], pslots[3], prowptr[3];
     long long n_probes[3] = {0, 0, 0};
+    std::vector<long long> host_bcells[3];   // host copies: strip weights of the streaming kernel
+    std::vector<long long> host_ccells[3];
+    // cells whose single scalar operation is applied inline: per component the cells and their class
+    DevArray ccells[3], cclass[3];
+    long long n_ccells[3] = {0, 0, 0};
+    double cls_alpha[3][kMaxClasses] = {}, cls_value[3][kMaxClasses] = {};
+    DevArray strip_order;
+    int n_strips_ordered = 0;
     DevArray flagged;         // cells whose flag bits are currently set
     long long n_flagged = 0;
     bool flags_dirty = false;
@@ -128,6 +136,9 @@ struct fds_ctx {
     int rank = 0, world = 1;
 
     bool use_stream2d = false; // streaming multi-step kernel selected
+    StepTables *d_tables = nullptr;   // device copy of the tables for the streaming kernel's slow path
+    int *task_counters = nullptr;     // pool of zeroed work counters, one per streaming launch
+    int next_counter = 0;
     int chunk_rows = 0;       // rows per streaming task (0 = heuristic)
     int max_k = kMaxStreamSteps;
 
@@ -187,39 +198,63 @@ int dev_upload(fds_ctx *ctx, DevArray &a, const void *host, size_t bytes) {
     return 0;
 }
 
-__global__ void flag_kernel(uint8_t *map, const long long *cells, long long n, uint8_t set_mask,
-                            uint8_t clear_mask) {
+// Sets / clears bits of map entries; `values` (optional) holds a per-cell value that is shifted into
+// place (boundary-operation classes). Entries are 16 bit, the update is atomic on the 32-bit word.
+__global__ void flag_kernel(map_t *map, const long long *cells, const int *values, int shift,
+                            long long n, unsigned set_mask, unsigned clear_mask) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    // several table entries may name the same cell: make the read-modify-write atomic on the word
-    const long long c = cells[k];
-    unsigned int *word = reinterpret_cast<unsigned int *>(
-        reinterpret_cast<uintptr_t>(map + c) & ~uintptr_t(3));
-    const int shift = 8 * (int)(reinterpret_cast<uintptr_t>(map + c) & 3);
-    if (clear_mask) atomicAnd(word, ~((unsigned int)clear_mask << shift));
-    if (set_mask) atomicOr(word, (unsigned int)set_mask << shift);
+    map_t *entry = map + cells[k];
+    unsigned int *word =
+        reinterpret_cast<unsigned int *>(reinterpret_cast<uintptr_t>(entry) & ~uintptr_t(3));
+    const int pos = 8 * (int)(reinterpret_cast<uintptr_t>(entry) & 3);
+    unsigned set = set_mask;
+    if (values) set |= (unsigned)values[k] << shift;
+    if (clear_mask) atomicAnd(word, ~(clear_mask << pos));
+    if (set) atomicOr(word, set << pos);
 }
 
-int launch_flags(fds_ctx *ctx, const long long *cells, long long n, uint8_t set_mask,
-                 uint8_t clear_mask) {
+int launch_flags(fds_ctx *ctx, const long long *cells, const int *values, int shift, long long n,
+                 unsigned set_mask, unsigned clear_mask) {
     if (n <= 0) return 0;
     const int threads = 256;
     const long long blocks = (n + threads - 1) / threads;
-    flag_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->map + ctx->pad + ctx->halo,
-                                                               cells, n, set_mask, clear_mask);
+    flag_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
+        ctx->map + ctx->pad + ctx->halo, cells, values, shift, n, set_mask, clear_mask);
     FDS_CUDA(ctx, cudaGetLastError());
     return 0;
+}
+
+__global__ void widen_ids_kernel(map_t *map, const uint8_t *ids, long long n) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) map[k] = ids[k];
+}
+
+// Per-row index of a sorted cell list: entry k = first position whose cell lies in local row >= k
+// (rows counted from the first halo row).
+int upload_row_ptr(fds_ctx *ctx, DevArray &dst, const long long *cells, int64_t n) {
+    const long long total_rows = (ctx->dims == 1) ? 1 : ctx->d.rows + 2 * (long long)ctx->d.halo_rows;
+    std::vector<int> ptr((size_t)total_rows + 1, 0);
+    int64_t k = 0;
+    for (long long r = 0; r <= total_rows; ++r) {
+        const long long first_cell = r * ctx->d.nx - ctx->halo;   // first cell of row r
+        while (k < n && cells[k] < first_cell) ++k;
+        ptr[(size_t)r] = (int)k;
+    }
+    ptr[(size_t)total_rows] = (int)n;
+    return dev_upload(ctx, dst, ptr.data(), ptr.size() * sizeof(int));
 }
 
 // Rebuilds the per-cell flag bits from the boundary and probe tables.
 int refresh_flags(fds_ctx *ctx) {
     if (!ctx->flags_dirty) return 0;
+    const unsigned all_bits = kFlagBound | kFlagProbe | kClassMask;
     if (ctx->n_flagged)
-        if (launch_flags(ctx, (const long long *)ctx->flagged.ptr, ctx->n_flagged, 0,
-                         kFlagBound | kFlagProbe))
+        if (launch_flags(ctx, (const long long *)ctx->flagged.ptr, nullptr, 0, ctx->n_flagged, 0,
+                         all_bits))
             return 1;
     long long total = 0;
-    for (int c = 0; c < 3; ++c) total += ctx->n_bcells[c] + ctx->n_probes[c];
+    for (int c = 0; c < 3; ++c) total += ctx->n_bcells[c] + ctx->n_probes[c] + ctx->n_ccells[c];
     if (ctx->flagged.bytes < (size_t)total * 8) {
         if (ctx->flagged.ptr) {
             FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -233,20 +268,27 @@ int refresh_flags(fds_ctx *ctx) {
         ctx->flagged.bytes = (size_t)total * 8;
     }
     long long at = 0;
+    long long *dst = (long long *)ctx->flagged.ptr;
     for (int c = 0; c < 3; ++c) {
-        const long long nb = ctx->n_bcells[c], np = ctx->n_probes[c];
-        long long *dst = (long long *)ctx->flagged.ptr;
+        const long long nb = ctx->n_bcells[c], np = ctx->n_probes[c], nc = ctx->n_ccells[c];
         if (nb) {
             FDS_CUDA(ctx, cudaMemcpyAsync(dst + at, ctx->bcells[c].ptr, nb * 8,
                                           cudaMemcpyDeviceToDevice, ctx->stream));
-            if (launch_flags(ctx, dst + at, nb, kFlagBound, 0)) return 1;
+            if (launch_flags(ctx, dst + at, nullptr, 0, nb, kFlagBound, 0)) return 1;
             at += nb;
         }
         if (np) {
             FDS_CUDA(ctx, cudaMemcpyAsync(dst + at, ctx->pcells[c].ptr, np * 8,
                                           cudaMemcpyDeviceToDevice, ctx->stream));
-            if (launch_flags(ctx, dst + at, np, kFlagProbe, 0)) return 1;
+            if (launch_flags(ctx, dst + at, nullptr, 0, np, kFlagProbe, 0)) return 1;
             at += np;
+        }
+        if (nc) {
+            FDS_CUDA(ctx, cudaMemcpyAsync(dst + at, ctx->ccells[c].ptr, nc * 8,
+                                          cudaMemcpyDeviceToDevice, ctx->stream));
+            if (launch_flags(ctx, dst + at, (const int *)ctx->cclass[c].ptr, class_shift(c), nc, 0, 0))
+                return 1;
+            at += nc;
         }
     }
     ctx->n_flagged = total;
@@ -270,9 +312,11 @@ StepTables make_tables(fds_ctx *ctx) {
         t.bound[c].alpha = (const double *)ctx->balpha[c].ptr;
         t.bound[c].value = (const double *)ctx->bvalue[c].ptr;
         t.bound[c].signal = (const int *)ctx->bsignal[c].ptr;
+        t.bound[c].row_ptr = (const int *)ctx->browptr[c].ptr;
         t.bound[c].n_cells = (int)ctx->n_bcells[c];
         t.probe[c].cells = (const long long *)ctx->pcells[c].ptr;
         t.probe[c].slots = (const int *)ctx->pslots[c].ptr;
+        t.probe[c].row_ptr = (const int *)ctx->prowptr[c].ptr;
         t.probe[c].n = (int)ctx->n_probes[c];
     }
     t.signals = (const double *)ctx->signals.ptr;
@@ -280,6 +324,10 @@ StepTables make_tables(fds_ctx *ctx) {
     t.sig_first_step = ctx->sig_first;
     t.ring = (double *)ctx->ring.ptr;
     t.n_slots = (int)ctx->n_slots;
+    t.rows.nx = ctx->d.nx;
+    t.rows.halo_cells = ctx->halo;
+    memcpy(t.cls_alpha, ctx->cls_alpha, sizeof(t.cls_alpha));
+    memcpy(t.cls_value, ctx->cls_value, sizeof(t.cls_value));
     return t;
 }
 
@@ -331,17 +379,26 @@ bool stream_supported(const fds_desc &d) {
     return d.model == FDS_ACOUSTIC2D && !d.lossy && d.nx % 4 == 0 && d.nx >= kStripCells;
 }
 
-int stream_chunk_rows(const fds_ctx *ctx, long long rows, int n_strips) {
+constexpr int kCounterPool = 4096;
+
+int stream_chunk_rows(const fds_ctx *ctx, long long rows, int n_strips, int k) {
     if (ctx->chunk_rows > 0) return ctx->chunk_rows;
-    // enough tasks for >= 2 waves of (SMs x resident warps), chunks between 32 and 256 rows
-    const long long slots = 148ll * 2 * kStreamWarps;
-    long long h = 256;
-    while (h > 32 && n_strips * ((rows + h - 1) / h) < 2 * slots) h /= 2;
-    return (int)h;
+    // A task costs about t = (chunk + 2k + ring fill) row times; with dynamic distribution over the
+    // 148 SMs x 2 CTAs x 4 warps the makespan is about tasks * t / slots plus half a task of tail.
+    const double slots = 148.0 * 2 * kStreamWarps;
+    long long best = 64;
+    double best_cost = -1;
+    for (long long h : {32, 48, 64, 96, 128, 192, 256, 384, 512}) {
+        const double tasks = (double)n_strips * (double)((rows + h - 1) / h);
+        const double t = (double)std::min(h, rows) + 2 * k + 4;
+        const double cost = std::max(tasks, slots) * t / slots + 0.5 * t;
+        if (best_cost < 0 || cost < best_cost) { best = h; best_cost = cost; }
+    }
+    return (int)best;
 }
 
 template <int K>
-int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a, const StepTables &t) {
+int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
     auto kernel = stream2d_kernel<K>;
     const int smem = kStreamWarps * kWarpRingBytes;
     static bool configured = false;
@@ -349,23 +406,55 @@ int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a, const StepTables &t) {
         FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    const long long ctas = (a.n_tasks + kStreamWarps - 1) / kStreamWarps;
-    kernel<<<(unsigned)ctas, kStreamWarps * 32, smem, ctx->stream>>>(a, t);
+    // persistent CTAs (2 per SM) pull tasks from a counter
+    const long long want = (a.n_tasks + kStreamWarps - 1) / kStreamWarps;
+    const long long ctas = std::min<long long>(want, 148 * 2);
+    kernel<<<(unsigned)ctas, kStreamWarps * 32, smem, ctx->stream>>>(a);
     FDS_CUDA(ctx, cudaGetLastError());
     return 0;
 }
 
-int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, const StepTables &t, int k) {
+int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     const long long rows = a.row_end - a.row_begin;
     if (rows <= 0) return 0;
     a.n_strips = (int)((a.nx + kStripStride - 1) / kStripStride);
-    a.chunk_rows = stream_chunk_rows(ctx, rows, a.n_strips);
-    a.n_tasks = (long long)a.n_strips * ((rows + a.chunk_rows - 1) / a.chunk_rows);
+    a.chunk_rows = stream_chunk_rows(ctx, rows, a.n_strips, k);
+    a.n_tasks = (int)(a.n_strips * ((rows + a.chunk_rows - 1) / a.chunk_rows));
+    if (ctx->next_counter == kCounterPool) {
+        FDS_CUDA(ctx, cudaMemsetAsync(ctx->task_counters, 0, sizeof(int) * kCounterPool, ctx->stream));
+        ctx->next_counter = 0;
+    }
+    if (ctx->n_strips_ordered != a.n_strips) {
+        // strips that carry boundary cells (slow path) are handed out first (longest task first)
+        std::vector<long long> weight((size_t)a.n_strips, 0);
+        for (int c = 0; c < 3; ++c) {
+            for (long long cell : ctx->host_bcells[c]) {      // table lookups: expensive
+                const long long col = ((cell % a.nx) + a.nx) % a.nx;
+                weight[(size_t)std::min<long long>(col / kStripStride, a.n_strips - 1)] += 8;
+            }
+            for (long long cell : ctx->host_ccells[c]) {      // inline classes: cheap
+                const long long col = ((cell % a.nx) + a.nx) % a.nx;
+                weight[(size_t)std::min<long long>(col / kStripStride, a.n_strips - 1)] += 1;
+            }
+        }
+        std::vector<int> order((size_t)a.n_strips);
+        for (int k = 0; k < a.n_strips; ++k) order[(size_t)k] = k;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int x, int y) { return weight[(size_t)x] > weight[(size_t)y]; });
+        if (dev_upload(ctx, ctx->strip_order, order.data(), order.size() * sizeof(int))) return 1;
+        ctx->n_strips_ordered = a.n_strips;
+    }
+    a.strip_order = (const int *)ctx->strip_order.ptr;
+    a.n_chunks = (int)((rows + a.chunk_rows - 1) / a.chunk_rows);
+    a.task_counter = ctx->task_counters + ctx->next_counter++;
+    a.map = ctx->map + ctx->pad + ctx->halo;
+    a.tab = ctx->tab;
+    a.tables = ctx->d_tables;
     switch (k) {
-        case 1: return launch_stream2d<1>(ctx, a, t);
-        case 2: return launch_stream2d<2>(ctx, a, t);
-        case 3: return launch_stream2d<3>(ctx, a, t);
-        case 4: return launch_stream2d<4>(ctx, a, t);
+        case 1: return launch_stream2d<1>(ctx, a);
+        case 2: return launch_stream2d<2>(ctx, a);
+        case 3: return launch_stream2d<3>(ctx, a);
+        case 4: return launch_stream2d<4>(ctx, a);
     }
     return fail(ctx, "stream2d: bad step count");
 }
@@ -380,7 +469,7 @@ struct Plan1D {
 Plan1D plan_1d(const fds_ctx *ctx, long long steps_left) {
     Plan1D p{};
     const long long n = ctx->d.nx;
-    const int max_width = 13000;
+    const int max_width = 12000;
     if (n + 4 <= max_width) {  // the whole line in one CTA: no neighbours, any number of steps
         p.tile = (int)n;
         p.halo = 2;
@@ -392,7 +481,7 @@ Plan1D plan_1d(const fds_ctx *ctx, long long steps_left) {
         p.ctas = (n + p.tile - 1) / p.tile;
         p.steps = (int)std::min<long long>(steps_left, p.halo / 2);
     }
-    p.smem = (size_t)(p.tile + 2 * p.halo) * 17 + 16;
+    p.smem = (size_t)(p.tile + 2 * p.halo) * (16 + sizeof(map_t)) + 16;
     return p;
 }
 
@@ -454,6 +543,9 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
     }
 
     StepTables t = make_tables(ctx);
+    if (ctx->use_stream2d)
+        FDS_CUDA(ctx, cudaMemcpyAsync(ctx->d_tables, &t, sizeof(StepTables), cudaMemcpyHostToDevice,
+                                      ctx->stream));
     const long long half = ctx->ring_half;
     const long long sig0 = first_step - ctx->sig_first;
     ctx->last_launches = 0;
@@ -513,20 +605,20 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                     // the k outermost rows of either side travel while the interior is computed
                     const long long band = std::min<long long>(ctx->d.halo_rows, rows);
                     a.row_begin = 0; a.row_end = band;
-                    if (dispatch_stream2d(ctx, a, t, k)) return 1;
+                    if (dispatch_stream2d(ctx, a, k)) return 1;
                     a.row_begin = std::max(band, rows - band); a.row_end = rows;
-                    if (dispatch_stream2d(ctx, a, t, k)) return 1;
+                    if (dispatch_stream2d(ctx, a, k)) return 1;
                     FDS_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
                     FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
                     if (exchange_halos(ctx, ctx->cur ^ 1)) return 1;
                     FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
                     a.row_begin = band; a.row_end = std::max(band, rows - band);
-                    if (dispatch_stream2d(ctx, a, t, k)) return 1;
+                    if (dispatch_stream2d(ctx, a, k)) return 1;
                     FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
                     ctx->last_launches += 3;
                 } else {
                     a.row_begin = 0; a.row_end = rows;
-                    if (dispatch_stream2d(ctx, a, t, k)) return 1;
+                    if (dispatch_stream2d(ctx, a, k)) return 1;
                     ctx->last_launches += 1;
                 }
                 advanced = k;
@@ -648,7 +740,7 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
     if (!one_d && d.nx < 2)
         return fail(nullptr, "fds_create: 2-D models need at least two samples along x");
     if (d.n_materials < 1 || d.n_materials >= kMaxMaterials)
-        return fail(nullptr, "fds_create: 1..63 distinct materials supported");
+        return fail(nullptr, "fds_create: 1..31 distinct materials supported");
     if (d.halo_rows < 0 || d.halo_rows > 64)
         return fail(nullptr, "fds_create: halo_rows out of range");
     int n_dev = 0;
@@ -713,12 +805,16 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
     for (int b = 0; b < 2; ++b)
         for (int c = 0; c < ctx->ncomp; ++c)
             FDS_TRY(dev_alloc(ctx, (void **)&ctx->buf[b][c], (size_t)ctx->alloc * 8, true));
-    FDS_TRY(dev_alloc(ctx, (void **)&ctx->map, (size_t)ctx->alloc, true));
+    FDS_TRY(dev_alloc(ctx, (void **)&ctx->map, (size_t)ctx->alloc * sizeof(map_t), true));
     FDS_TRY(dev_alloc(ctx, (void **)&ctx->tab, sizeof(double) * FDS_TAB_COUNT * kMaxMaterials, true));
     if (ctx->axi) {
         FDS_TRY(dev_alloc(ctx, (void **)&ctx->ctab,
                           sizeof(double) * FDS_CTAB_COUNT * (d.n_materials + 1) * d.nx, true));
         FDS_TRY(dev_alloc(ctx, (void **)&ctx->cvec, sizeof(double) * FDS_CVEC_COUNT * d.nx, true));
+    }
+    if (ctx->use_stream2d) {
+        FDS_TRY(dev_alloc(ctx, (void **)&ctx->d_tables, sizeof(StepTables), true));
+        FDS_TRY(dev_alloc(ctx, (void **)&ctx->task_counters, sizeof(int) * kCounterPool, true));
     }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         ctx->err = "device initialisation failed";
@@ -743,13 +839,17 @@ void fds_destroy(fds_ctx *ctx) {
     if (ctx->tab) cudaFree(ctx->tab);
     if (ctx->ctab) cudaFree(ctx->ctab);
     if (ctx->cvec) cudaFree(ctx->cvec);
+    if (ctx->d_tables) cudaFree(ctx->d_tables);
+    if (ctx->task_counters) cudaFree(ctx->task_counters);
     for (int c = 0; c < 3; ++c) {
         DevArray *arrays[] = {&ctx->bcells[c], &ctx->boffsets[c], &ctx->balpha[c], &ctx->bvalue[c],
-                              &ctx->bsignal[c], &ctx->pcells[c], &ctx->pslots[c]};
+                              &ctx->bsignal[c], &ctx->pcells[c], &ctx->pslots[c],
+                              &ctx->browptr[c], &ctx->prowptr[c], &ctx->ccells[c], &ctx->cclass[c]};
         for (DevArray *a : arrays)
             if (a->ptr) cudaFree(a->ptr);
     }
     if (ctx->flagged.ptr) cudaFree(ctx->flagged.ptr);
+    if (ctx->strip_order.ptr) cudaFree(ctx->strip_order.ptr);
     if (ctx->signals.ptr) cudaFree(ctx->signals.ptr);
     if (ctx->ring.ptr) cudaFree(ctx->ring.ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -771,9 +871,18 @@ int fds_upload_material_map(fds_ctx *ctx, const uint8_t *ids, int64_t n) {
         if (ids[k] > ctx->d.n_materials)
             return fail(ctx, "fds_upload_material_map: id exceeds n_materials");
     FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
-    FDS_CUDA(ctx, cudaMemcpyAsync(ctx->map + ctx->pad, ids, (size_t)n, cudaMemcpyHostToDevice,
-                                  ctx->stream));
-    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint8_t *staging = nullptr;
+    FDS_CUDA(ctx, cudaMalloc(&staging, (size_t)n));
+    cudaError_t e = cudaMemcpyAsync(staging, ids, (size_t)n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        widen_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->map + ctx->pad,
+                                                                              staging, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(staging);
+    if (e != cudaSuccess)
+        return fail(ctx, std::string("fds_upload_material_map: ") + cudaGetErrorString(e));
     ctx->map_uploaded = true;
     ctx->n_flagged = 0;      // the upload overwrote all flag bits
     ctx->flags_dirty = true;
@@ -844,12 +953,56 @@ int fds_upload_boundaries(fds_ctx *ctx, int32_t component, const int64_t *cells,
     }
     FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
     const int c = component;
-    if (dev_upload(ctx, ctx->bcells[c], cells, (size_t)n_cells * 8)) return 1;
-    if (dev_upload(ctx, ctx->boffsets[c], offsets, (size_t)(n_cells ? n_cells + 1 : 0) * 4)) return 1;
-    if (dev_upload(ctx, ctx->balpha[c], alpha, (size_t)n_ops * 8)) return 1;
-    if (dev_upload(ctx, ctx->bvalue[c], value, (size_t)n_ops * 8)) return 1;
-    if (dev_upload(ctx, ctx->bsignal[c], signal, (size_t)n_ops * 4)) return 1;
-    ctx->n_bcells[c] = n_cells;
+
+    // Cells with exactly one scalar operation get a class (applied inline by the kernels, no table
+    // access); all others stay in the lookup table of the slow path.
+    int n_classes = 1;
+    for (int k = 0; k < kMaxClasses; ++k) ctx->cls_alpha[c][k] = ctx->cls_value[c][k] = 0.0;
+    std::vector<long long> class_cells, slow_cells;
+    std::vector<int> class_ids, slow_offsets, slow_signal;
+    std::vector<double> slow_alpha, slow_value;
+    slow_offsets.push_back(0);
+    for (int64_t k = 0; k < n_cells; ++k) {
+        const int b = offsets[k], e = offsets[k + 1];
+        int cls = 0;
+        if (e - b == 1 && signal[b] < 0) {
+            for (int j = 1; j < n_classes && !cls; ++j)
+                if (memcmp(&ctx->cls_alpha[c][j], &alpha[b], 8) == 0 &&
+                    memcmp(&ctx->cls_value[c][j], &value[b], 8) == 0)
+                    cls = j;
+            if (!cls && n_classes < kMaxClasses) {
+                cls = n_classes++;
+                ctx->cls_alpha[c][cls] = alpha[b];
+                ctx->cls_value[c][cls] = value[b];
+            }
+        }
+        if (cls) {
+            class_cells.push_back(cells[k]);
+            class_ids.push_back(cls);
+        } else {
+            slow_cells.push_back(cells[k]);
+            for (int o = b; o < e; ++o) {
+                slow_alpha.push_back(alpha[o]);
+                slow_value.push_back(value[o]);
+                slow_signal.push_back(signal[o]);
+            }
+            slow_offsets.push_back((int)slow_alpha.size());
+        }
+    }
+    const size_t ns = slow_cells.size(), nops = slow_alpha.size(), nc = class_cells.size();
+    if (dev_upload(ctx, ctx->bcells[c], slow_cells.data(), ns * 8)) return 1;
+    if (dev_upload(ctx, ctx->boffsets[c], slow_offsets.data(), (ns ? ns + 1 : 0) * 4)) return 1;
+    if (dev_upload(ctx, ctx->balpha[c], slow_alpha.data(), nops * 8)) return 1;
+    if (dev_upload(ctx, ctx->bvalue[c], slow_value.data(), nops * 8)) return 1;
+    if (dev_upload(ctx, ctx->bsignal[c], slow_signal.data(), nops * 4)) return 1;
+    if (upload_row_ptr(ctx, ctx->browptr[c], slow_cells.data(), (int64_t)ns)) return 1;
+    if (dev_upload(ctx, ctx->ccells[c], class_cells.data(), nc * 8)) return 1;
+    if (dev_upload(ctx, ctx->cclass[c], class_ids.data(), nc * 4)) return 1;
+    ctx->host_bcells[c] = slow_cells;
+    ctx->host_ccells[c] = class_cells;
+    ctx->n_strips_ordered = 0;
+    ctx->n_bcells[c] = (long long)ns;
+    ctx->n_ccells[c] = (long long)nc;
     ctx->flags_dirty = true;
     return 0;
 }
@@ -885,6 +1038,7 @@ int fds_upload_probes(fds_ctx *ctx, int32_t component, const int64_t *cells, con
     FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
     if (dev_upload(ctx, ctx->pcells[component], cells, (size_t)n * 8)) return 1;
     if (dev_upload(ctx, ctx->pslots[component], slots, (size_t)n * 4)) return 1;
+    if (upload_row_ptr(ctx, ctx->prowptr[component], (const long long *)cells, n)) return 1;
     ctx->n_probes[component] = n;
     ctx->n_slots = n_slots_total;
     ctx->flags_dirty = true;

@@ -13,31 +13,55 @@
 
 namespace fds {
 
-constexpr int kMaxMaterials = 64;         // 6-bit material id in the per-cell map byte
-constexpr uint8_t kIdMask = 0x3F;
-constexpr uint8_t kFlagBound = 0x40;      // some component has a boundary operation on this cell
-constexpr uint8_t kFlagProbe = 0x80;      // some component has a probe on this cell
+// Per-cell map entry (16 bit):
+//   bits 0-4   material id (0 = void, 1..31)
+//   bit  5     some component has boundary operations that need the table lookup (slow path)
+//   bit  6     some component has a probe on this cell
+//   bits 7-9   class of the constant boundary operation on component 0 (0 = none)
+//   bits 10-12 ... on component 1,  bits 13-15 ... on component 2
+// A cell whose boundary list for a component is exactly ONE scalar operation (a Dirichlet wall, a
+// constant additive source) gets a class: v = alpha[class]*v + value[class] is applied inline, without
+// any table access. Everything else (signals, several operations on one cell) takes the slow path.
+typedef uint16_t map_t;
+constexpr int kMaxMaterials = 32;
+constexpr unsigned kIdMask = 0x1F;
+constexpr unsigned kFlagBound = 0x20;
+constexpr unsigned kFlagProbe = 0x40;
+constexpr unsigned kClassMask = 0xFF80;
+constexpr int kClassBits = 3;
+constexpr int kMaxClasses = 8;            // class 0 = none
+__host__ __device__ constexpr int class_shift(int comp) { return 7 + kClassBits * comp; }
 
-// CSR table of boundary operations for one component (fds_upload_boundaries).
+// CSR table of boundary operations for one component (fds_upload_boundaries). `row_ptr[k]` is the
+// first entry of `cells` that lies in local row k (counted from the first halo row), so a lookup only
+// searches the handful of entries of one grid row.
 struct BoundTable {
     const long long *cells;
     const int *offsets;
     const double *alpha;
     const double *value;
     const int *signal;
+    const int *row_ptr;
     int n_cells;
 };
 
-// Probe points of one component (fds_upload_probes).
+// Probe points of one component (fds_upload_probes), with the same per-row index.
 struct ProbeTable {
     const long long *cells;
     const int *slots;
+    const int *row_ptr;
     int n;
+};
+
+// Geometry needed to find the row of a cell on the slow path.
+struct RowIndex {
+    long long nx;
+    long long halo_cells;   // cells between the first halo row and local cell 0
 };
 
 // Everything a step kernel needs besides the state pointers. Passed by value (kernel parameter).
 struct StepTables {
-    const uint8_t *map;        // material id + flags, origin at local cell 0
+    const map_t *map;          // material id + flags + classes, origin at local cell 0
     const double *tab;         // [FDS_TAB_COUNT][kMaxMaterials]
     const double *ctab;        // [FDS_CTAB_COUNT][n_materials + 1][nx]   (axisymmetric only)
     const double *cvec;        // [FDS_CVEC_COUNT][nx]                    (axisymmetric only)
@@ -48,6 +72,9 @@ struct StepTables {
     long long sig_first_step;
     double *ring;              // probe records [ring_steps][n_slots]
     int n_slots;
+    RowIndex rows;
+    double cls_alpha[3][kMaxClasses];   // constant boundary operations by class
+    double cls_value[3][kMaxClasses];
 };
 
 __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
@@ -63,36 +90,63 @@ __device__ __forceinline__ double diff2(double fa, double ua, double fb, double 
     return add(acc0(mul(-fa, ua)), mul(fb, ub));
 }
 
+// Inline constant boundary operation of component `comp` (class bits of the map entry).
+__device__ __forceinline__ double apply_class(const double (*alpha)[kMaxClasses],
+                                              const double (*value)[kMaxClasses], int comp,
+                                              unsigned entry, double v) {
+    const unsigned k = (entry >> class_shift(comp)) & (kMaxClasses - 1);
+    return k ? add(mul(alpha[comp][k], v), value[comp][k]) : v;
+}
+
+// Position of `cell` in the sorted array `cells[lo, hi)` or the position of the first larger entry.
+// Boundary lines and rectangles are runs of consecutive cells, so the entry is usually exactly
+// `cell - cells[lo]` places after `lo`; otherwise fall back to a binary search.
+__device__ __forceinline__ int lower_bound_cell(const long long *__restrict__ cells, int lo, int hi,
+                                                long long cell) {
+    if (lo >= hi) return hi;
+    const long long guess = lo + (cell - __ldg(cells + lo));
+    if (guess >= lo && guess < hi && __ldg(cells + guess) == cell) {
+        // duplicates (probes) sit next to each other: step back to the first one
+        int g = (int)guess;
+        while (g > lo && __ldg(cells + g - 1) == cell) --g;
+        return g;
+    }
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(cells + mid) < cell) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
 // Applies all boundary operations of `cell` in list order:  v = alpha*v + value
 // (pyfds/regions.py:136-145 applied by pyfds/fields.py:598-600).
-__device__ __noinline__ double apply_bounds(const BoundTable t, const double *__restrict__ signals,
-                                            long long sig_steps, long long sig_index,
-                                            long long cell, double v) {
-    int lo = 0, hi = t.n_cells;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (t.cells[mid] < cell) lo = mid + 1; else hi = mid;
-    }
-    if (lo < t.n_cells && t.cells[lo] == cell) {
-        const int end = t.offsets[lo + 1];
-        for (int o = t.offsets[lo]; o < end; ++o) {
-            const int s = t.signal[o];
-            const double val = s >= 0 ? signals[(long long)s * sig_steps + sig_index] : t.value[o];
-            v = add(mul(t.alpha[o], v), val);
+__device__ __noinline__ double apply_bounds(const BoundTable t, const RowIndex ri,
+                                            const double *__restrict__ signals, long long sig_steps,
+                                            long long sig_index, long long cell, double v) {
+    if (t.n_cells == 0) return v;
+    const long long row = (cell + ri.halo_cells) / ri.nx;
+    const int hi = __ldg(t.row_ptr + row + 1);
+    const int k = lower_bound_cell(t.cells, __ldg(t.row_ptr + row), hi, cell);
+    if (k < hi && __ldg(t.cells + k) == cell) {
+        const int end = __ldg(t.offsets + k + 1);
+        for (int o = __ldg(t.offsets + k); o < end; ++o) {
+            const int s = __ldg(t.signal + o);
+            const double val =
+                s >= 0 ? __ldg(signals + (long long)s * sig_steps + sig_index) : __ldg(t.value + o);
+            v = add(mul(__ldg(t.alpha + o), v), val);
         }
     }
     return v;
 }
 
 // Stores `v` into every probe slot attached to `cell` (pyfds/fields.py:606-611).
-__device__ __noinline__ void write_probes(const ProbeTable t, double *__restrict__ record,
-                                          long long cell, double v) {
-    int lo = 0, hi = t.n;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        if (t.cells[mid] < cell) lo = mid + 1; else hi = mid;
-    }
-    for (; lo < t.n && t.cells[lo] == cell; ++lo) record[t.slots[lo]] = v;
+__device__ __noinline__ void write_probes(const ProbeTable t, const RowIndex ri,
+                                          double *__restrict__ record, long long cell, double v) {
+    if (t.n == 0) return;
+    const long long row = (cell + ri.halo_cells) / ri.nx;
+    const int hi = __ldg(t.row_ptr + row + 1);
+    int k = lower_bound_cell(t.cells, __ldg(t.row_ptr + row), hi, cell);
+    for (; k < hi && __ldg(t.cells + k) == cell; ++k) record[__ldg(t.slots + k)] = v;
 }
 
 }  // namespace fds

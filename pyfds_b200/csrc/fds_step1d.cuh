@@ -25,7 +25,7 @@ struct Step1DArgs {
 };
 
 constexpr int k1DThreads = 1024;
-constexpr int k1DMaxPerThread = 14;   // (tile + 2*halo) <= 14 * 1024 cells = 238 KB of state + ids
+constexpr int k1DMaxPerThread = 12;   // (tile + 2*halo) <= 12 * 1024 cells, 18 bytes each
 
 template <bool THERMAL, bool LOSSY>
 __global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, StepTables t) {
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, Ste
     const int width = a.tile + 2 * a.halo;
     double *s = reinterpret_cast<double *>(smem_raw);     // scalar component
     double *u = s + width;                                // vector component
-    uint8_t *id = reinterpret_cast<uint8_t *>(u + width); // material id + flags
+    map_t *id = reinterpret_cast<map_t *>(u + width);      // material id + flags + classes
     __shared__ double tabs[FDS_TAB_COUNT][kMaxMaterials];
 
     const int tid = threadIdx.x;
@@ -56,16 +56,15 @@ __global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, Ste
 
         // 1. boundaries and probes of the scalar component
         for (int l = tid; l < width; l += k1DThreads) {
-            const uint8_t f = id[l];
-            if (f & (kFlagBound | kFlagProbe)) {
+            const unsigned f = id[l];
+            if (f & (kFlagBound | kFlagProbe | kClassMask)) {
                 const long long g = origin + l;
-                double v = s[l];
-                if (f & kFlagBound) {
-                    v = apply_bounds(t.bound[0], t.signals, t.sig_steps, sig, g, v);
-                    s[l] = v;
-                }
+                double v = apply_class(t.cls_alpha, t.cls_value, 0, f, s[l]);
+                if (f & kFlagBound)
+                    v = apply_bounds(t.bound[0], t.rows, t.signals, t.sig_steps, sig, g, v);
+                s[l] = v;
                 if ((f & kFlagProbe) && l >= a.halo && l < a.halo + a.tile)
-                    write_probes(t.probe[0], record, g, v);
+                    write_probes(t.probe[0], t.rows, record, g, v);
             }
         }
         __syncthreads();
@@ -97,14 +96,15 @@ __global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, Ste
         for (int r = 0; r < k1DMaxPerThread; ++r) {
             const int l = tid + r * k1DThreads;
             if (l >= 2 && l < width - 2 && (id[l] & kIdMask)) {
-                const uint8_t f = id[l];
+                const unsigned f = id[l];
                 double v = unew[r];
-                if (f & (kFlagBound | kFlagProbe)) {
+                if (f & (kFlagBound | kFlagProbe | kClassMask)) {
                     const long long g = origin + l;
+                    v = apply_class(t.cls_alpha, t.cls_value, 1, f, v);
                     if (f & kFlagBound)
-                        v = apply_bounds(t.bound[1], t.signals, t.sig_steps, sig, g, v);
+                        v = apply_bounds(t.bound[1], t.rows, t.signals, t.sig_steps, sig, g, v);
                     if ((f & kFlagProbe) && l >= a.halo && l < a.halo + a.tile)
-                        write_probes(t.probe[1], record, g, v);
+                        write_probes(t.probe[1], t.rows, record, g, v);
                 }
                 u[l] = v;
             }

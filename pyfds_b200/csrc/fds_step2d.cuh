@@ -47,14 +47,14 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
     if (x >= a.nx) return;
     const long long nx = a.nx;
     const long long i = (a.row_begin + blockIdx.x) * nx + x;
-    const uint8_t *__restrict__ map = t.map;
+    const map_t *__restrict__ map = t.map;
     const double *__restrict__ sin_ = a.in[0];
     const double *__restrict__ uin = a.in[1];
     const double *__restrict__ win = a.in[2];
 
     // ---- all loads first ------------------------------------------------------------------------
     // map bytes / scalar field at the 5-point stencil
-    uint8_t m0 = map[i], mxm = map[i - 1], mxp = map[i + 1], mym = map[i - nx], myp = map[i + nx];
+    unsigned m0 = map[i], mxm = map[i - 1], mxp = map[i + 1], mym = map[i - nx], myp = map[i + nx];
     double s0 = sin_[i], sxm = sin_[i - 1], sxp = sin_[i + 1], sym = sin_[i - nx],
            syp = sin_[i + nx];
     double u0 = 0, u1 = 0, w0 = 0, w1 = 0;
@@ -65,8 +65,8 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
     // viscous operator: old vector components around cells i, i+1 (x) and i, i+nx (y)
     double ua[2] = {0, 0}, ub[2] = {0, 0}, ul = 0, ur = 0;         // vx at j-nx, j+nx; i-1, i+2
     double wa = 0, wb = 0, wl[2] = {0, 0}, wr[2] = {0, 0};         // vy at i-nx, i+2nx; j-1, j+1
-    uint8_t mxa[2] = {0, 0}, mxb[2] = {0, 0}, mx2 = 0;             // map at i-nx+k, i+nx+k, i+2
-    uint8_t myl = 0, my2 = 0;                                      // map at i+nx-1, i+2nx
+    unsigned mxa[2] = {0, 0}, mxb[2] = {0, 0}, mx2 = 0;            // map at i-nx+k, i+nx+k, i+2
+    unsigned myl = 0, my2 = 0;                                     // map at i+nx-1, i+2nx
     if (kVisc) {
         ua[0] = uin[i - nx]; ua[1] = uin[i - nx + 1];
         ub[0] = uin[i + nx]; ub[1] = uin[i + nx + 1];
@@ -80,35 +80,41 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
         myl = map[i + nx - 1]; my2 = map[i + 2 * nx];
     }
 
-    auto tab = [&](int which, uint8_t m) {
+    auto tab = [&](int which, unsigned m) {
         return __ldg(t.tab + which * kMaxMaterials + (m & kIdMask));
     };
-    auto ctab = [&](int which, uint8_t m, long long col) {
+    auto ctab = [&](int which, unsigned m, long long col) {
         return __ldg(t.ctab + ((long long)which * n_mat1 + (m & kIdMask)) * nx + col);
+    };
+
+    // boundary operations of one cell and component: the inline constant class, else the table
+    auto bound = [&](int comp, unsigned m, long long cell, double v) {
+        if (m & (kFlagBound | ((kMaxClasses - 1u) << class_shift(comp)))) {
+            v = apply_class(t.cls_alpha, t.cls_value, comp, m, v);
+            if (m & kFlagBound)
+                v = apply_bounds(t.bound[comp], t.rows, t.signals, t.sig_steps, a.sig_index, cell, v);
+        }
+        return v;
     };
 
     // ---- step 1: boundaries and probes of the scalar component ----------------------------------
     double *__restrict__ record = t.ring + a.ring_row * t.n_slots;
-    const uint8_t any = m0 | mxm | mxp | mym | myp;
-    if (any & kFlagBound) {
-        if (m0 & kFlagBound) s0 = apply_bounds(t.bound[0], t.signals, t.sig_steps, a.sig_index, i, s0);
-        if (mxm & kFlagBound)
-            sxm = apply_bounds(t.bound[0], t.signals, t.sig_steps, a.sig_index, i - 1, sxm);
-        if (mxp & kFlagBound)
-            sxp = apply_bounds(t.bound[0], t.signals, t.sig_steps, a.sig_index, i + 1, sxp);
-        if (mym & kFlagBound)
-            sym = apply_bounds(t.bound[0], t.signals, t.sig_steps, a.sig_index, i - nx, sym);
-        if (myp & kFlagBound)
-            syp = apply_bounds(t.bound[0], t.signals, t.sig_steps, a.sig_index, i + nx, syp);
+    const unsigned any = m0 | mxm | mxp | mym | myp;
+    if (any & (kFlagBound | kClassMask)) {
+        s0 = bound(0, m0, i, s0);
+        sxm = bound(0, mxm, i - 1, sxm);
+        sxp = bound(0, mxp, i + 1, sxp);
+        sym = bound(0, mym, i - nx, sym);
+        syp = bound(0, myp, i + nx, syp);
     }
-    if (m0 & kFlagProbe) write_probes(t.probe[0], record, i, s0);
+    if (m0 & kFlagProbe) write_probes(t.probe[0], t.rows, record, i, s0);
 
     // ---- step 2/3: x component at cells i and i+1 ------------------------------------------------
     double ux[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const long long j = i + k;
-        const uint8_t mj = k ? mxp : m0, mjm = k ? m0 : mxm;
+        const unsigned mj = k ? mxp : m0, mjm = k ? m0 : mxm;
         const double sj = k ? sxp : s0, sjm = k ? s0 : sxm;
         // A_vx_p p  |  A_qx_t T : backward difference, offsets [-1, 0]
         const double d = diff2(tab(FDS_TAB_GX, mjm), sjm, tab(FDS_TAB_GX, mj), sj);
@@ -119,7 +125,7 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
             const double old = k ? u1 : u0;
             if (kVisc) {
                 const long long col = wrap_col(x + k, nx);
-                const uint8_t mc = k ? mx2 : mxp;            // material of cell j+1
+                const unsigned mc = k ? mx2 : mxp;           // material of cell j+1
                 const double um = k ? u0 : ul, up = k ? ur : u1;
                 double cm1, cp1;
                 if (kAxi) {
@@ -150,18 +156,16 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
                 v = sub(old, d);
             }
         }
-        if (mj & kFlagBound)
-            v = apply_bounds(t.bound[1], t.signals, t.sig_steps, a.sig_index, j, v);
-        ux[k] = v;
+        ux[k] = bound(1, mj, j, v);
     }
-    if (m0 & kFlagProbe) write_probes(t.probe[1], record, i, ux[0]);
+    if (m0 & kFlagProbe) write_probes(t.probe[1], t.rows, record, i, ux[0]);
 
     // ---- step 2/3: y component at cells i and i+nx -----------------------------------------------
     double uy[2];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
         const long long j = i + k * nx;
-        const uint8_t mj = k ? myp : m0, mjm = k ? m0 : mym;
+        const unsigned mj = k ? myp : m0, mjm = k ? m0 : mym;
         const double sj = k ? syp : s0, sjm = k ? s0 : sym;
         const double d = diff2(tab(FDS_TAB_GY, mjm), sjm, tab(FDS_TAB_GY, mj), sj);
         double v;
@@ -171,8 +175,8 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
             const double old = k ? w1 : w0;
             if (kVisc) {
                 // a_vy_vy is the same matrix as a_vx_vx (pyfds/acoustics.py:108,202)
-                const uint8_t ma = k ? m0 : mym, mb = k ? my2 : myp;
-                const uint8_t ml = k ? myl : mxm, mr = k ? mxb[1] : mxp;
+                const unsigned ma = k ? m0 : mym, mb = k ? my2 : myp;
+                const unsigned ml = k ? myl : mxm, mr = k ? mxb[1] : mxp;
                 const double below = k ? w0 : wa, above = k ? wb : w1;
                 double cm1, cp1;
                 if (kAxi) {
@@ -192,11 +196,9 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
                 v = sub(old, d);
             }
         }
-        if (mj & kFlagBound)
-            v = apply_bounds(t.bound[2], t.signals, t.sig_steps, a.sig_index, j, v);
-        uy[k] = v;
+        uy[k] = bound(2, mj, j, v);
     }
-    if (m0 & kFlagProbe) write_probes(t.probe[2], record, i, uy[0]);
+    if (m0 & kFlagProbe) write_probes(t.probe[2], t.rows, record, i, uy[0]);
 
     // ---- step 4: scalar update, forward differences with offsets [0, +1] and [0, +nx] -----------
     double fx0, fx1, f0 = ux[0], f1 = ux[1];

@@ -34,18 +34,26 @@ constexpr int kStripStride = kStripCells - 2 * kStripHalo;   // 120 owned cells 
 constexpr int kRingDepth = 6;        // rows in flight per warp
 constexpr int kStreamWarps = 4;      // warps per CTA
 constexpr int kMaxStreamSteps = 4;   // K
-constexpr int kSlotBytes = 3 * kStripCells * 8 + 160;         // p, vx, vy rows + 144 map bytes (padded)
-constexpr int kWarpRingBytes = kRingDepth * kSlotBytes + 64;  // + mbarriers
+constexpr int kMapWindowBytes = kStripCells * 2 + 16;         // 128 map entries + alignment slack
+constexpr int kSlotBytes = 3 * kStripCells * 8 + kMapWindowBytes + 16;   // p, vx, vy rows + map
+constexpr int kScratchBytes = 32 * 64;                        // slow path: 8 doubles per lane
+constexpr int kWarpRingBytes = kRingDepth * kSlotBytes + kScratchBytes + 64;   // + mbarriers
 
 struct Stream2DArgs {
     const double *in[3];
     double *out[3];
+    const map_t *map;      // material id + flags + classes, origin at local cell 0
+    const double *tab;     // coefficient tables [FDS_TAB_COUNT][kMaxMaterials]
+    const StepTables *tables;   // device copy, read on the slow path (boundaries, probes) only
+    int *task_counter;     // dynamic task distribution (zero before the launch)
+    const int *strip_order;   // strips sorted by expected cost, most expensive first
     long long nx;          // row length, multiple of 4
     long long row_begin;   // rows [row_begin, row_end) are produced
     long long row_end;
     int chunk_rows;        // rows per task
     int n_strips;
-    long long n_tasks;
+    int n_chunks;
+    int n_tasks;
     long long sig_index;   // first step - sig_first_step
     long long ring_row;    // probe record of the first step
 };
@@ -94,35 +102,66 @@ __device__ __forceinline__ double shfl_down1(double v) {
     return __shfl_down_sync(0xffffffffu, v, 1);
 }
 
+// Slow path, taken only by rows that carry a boundary operation or a probe: applies the boundary
+// operations of `n_comp` consecutive components (first_comp, first_comp + 1) to this lane's 4 cells and
+// records probes. Values travel through a per-lane shared-memory scratch so that the call site stays a
+// handful of instructions (the pipeline itself must fit the instruction cache).
+__device__ __noinline__ void stream_slow_cells(const StepTables *__restrict__ tp, int first_comp,
+                                               int n_comp, long long sig, long long record_row,
+                                               long long cell0, unsigned long long ids, bool owned,
+                                               double *scratch) {
+    for (int k = 0; k < n_comp; ++k) {
+        const int comp = first_comp + k;
+        for (int c = 0; c < 4; ++c) {
+            const unsigned f = (unsigned)(ids >> (16 * c));
+            if (!(f & (kFlagBound | kFlagProbe))) continue;
+            double v = scratch[4 * k + c];
+            if (f & kFlagBound) {
+                v = apply_bounds(tp->bound[comp], tp->rows, tp->signals, tp->sig_steps, sig,
+                                 cell0 + c, v);
+                scratch[4 * k + c] = v;
+            }
+            if ((f & kFlagProbe) && owned)
+                write_probes(tp->probe[comp], tp->rows, tp->ring + record_row * tp->n_slots,
+                             cell0 + c, v);
+        }
+    }
+}
+
 // Row metadata that travels through the pipeline with the row.
 struct RowInfo {
-    unsigned ids;      // 4 map bytes of this lane's cells
+    unsigned long long ids;   // the 4 map entries of this lane's cells
     int uniform;       // material id shared by all 128 cells of the row, or -1
-    bool any_bound;    // some cell of the row (any lane) carries a boundary operation
-    bool any_probe;
+    bool flagged;      // some cell of the row (any lane) needs the slow path (table lookup, probe)
+    unsigned classed;  // bit c set: some cell of the row (any lane) carries an inline constant
+                       // boundary operation on component c
 };
 
 template <int K>
-__global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2DArgs a, StepTables t) {
+__global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2DArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double tabs[4][kMaxMaterials];   // FDS_TAB_GX, GY, FX, FY
+    __shared__ double cls_alpha[3][kMaxClasses], cls_value[3][kMaxClasses];
 
-    for (int k = threadIdx.x; k < 4 * kMaxMaterials; k += blockDim.x) (&tabs[0][0])[k] = t.tab[k];
+    for (int k = threadIdx.x; k < 4 * kMaxMaterials; k += blockDim.x) (&tabs[0][0])[k] = a.tab[k];
+    for (int k = threadIdx.x; k < 3 * kMaxClasses; k += blockDim.x) {
+        (&cls_alpha[0][0])[k] = (&a.tables->cls_alpha[0][0])[k];
+        (&cls_value[0][0])[k] = (&a.tables->cls_value[0][0])[k];
+    }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long task = (long long)blockIdx.x * kStreamWarps + warp;
-    if (task >= a.n_tasks) return;
     const long long nx = a.nx;
-    const int strip = (int)(task % a.n_strips);
-    const long long chunk = task / a.n_strips;
-    const long long ys = a.row_begin + chunk * a.chunk_rows;
-    const long long ye = min(ys + (long long)a.chunk_rows, a.row_end);
-    const long long xs = (long long)strip * kStripStride - kStripHalo;   // column of lane 0, cell 0
-    const long long r0 = ys - K, r1 = ye + K;                            // rows streamed in
-
     unsigned char *ring = smem_raw + warp * kWarpRingBytes;
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(ring + kRingDepth * kSlotBytes);
+    double *scratch = reinterpret_cast<double *>(ring + kRingDepth * kSlotBytes) + lane * 8;
+    unsigned long long *bars =
+        reinterpret_cast<unsigned long long *>(ring + kRingDepth * kSlotBytes + kScratchBytes);
+
+    // shared-memory read pattern: two conflict-free 16-byte loads per field (lanes 4-7 of every
+    // quarter-warp take the upper half first)
+    const int swap = (lane >> 2) & 1;
+    const int off_a = lane * 32 + swap * 16, off_b = lane * 32 + (swap ^ 1) * 16;
+    unsigned phase_bits = 0;   // parity of every ring slot (the barriers live across tasks)
 
     if (lane == 0) {
         for (int d = 0; d < kRingDepth; ++d) mbar_init(&bars[d], 1);
@@ -130,194 +169,221 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2D
     }
     __syncwarp();
 
-    auto issue = [&](long long r, int slot) {
-        const long long base = r * nx + xs;             // flat cell index of the strip start
-        const long long base16 = base & ~15LL;          // map bytes: 16-byte aligned window
-        unsigned char *dst = ring + slot * kSlotBytes;
-        mbar_expect_tx(&bars[slot], 3 * kStripCells * 8 + 144);
-        bulk_load(dst, a.in[0] + base, kStripCells * 8, &bars[slot]);
-        bulk_load(dst + kStripCells * 8, a.in[1] + base, kStripCells * 8, &bars[slot]);
-        bulk_load(dst + 2 * kStripCells * 8, a.in[2] + base, kStripCells * 8, &bars[slot]);
-        bulk_load(dst + 3 * kStripCells * 8, t.map + base16, 144, &bars[slot]);
-    };
-    if (lane == 0)
-        for (int d = 0; d < kRingDepth && r0 + d < r1; ++d) issue(r0 + d, d);
+    for (;;) {
+        // ---- next task: (strip, chunk of rows), handed out dynamically ---------------------------
+        int task = 0;
+        if (lane == 0) task = atomicAdd(a.task_counter, 1);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= a.n_tasks) break;
+        const int strip = __ldg(a.strip_order + task / a.n_chunks);
+        const long long chunk = task % a.n_chunks;
+        const long long ys = a.row_begin + chunk * a.chunk_rows;
+        const long long ye = min(ys + (long long)a.chunk_rows, a.row_end);
+        const long long xs = (long long)strip * kStripStride - kStripHalo;   // column of lane 0
+        const long long r0 = ys - K, r1 = ye + K;                            // rows streamed in
 
-    // pipeline state: per stage the previous row's p (after boundaries), new vx, new vy
-    double pb[K][4], un[K][4], vn[K][4];
-    RowInfo info[K + 1];
-#pragma unroll
-    for (int s = 0; s < K; ++s)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) pb[s][c] = un[s][c] = vn[s][c] = 0.0;
-#pragma unroll
-    for (int s = 0; s <= K; ++s) info[s] = RowInfo{0u, 0, false, false};
+        auto issue = [&](long long r, int slot) {
+            const long long base = r * nx + xs;         // flat cell index of the strip start
+            const long long base8 = base & ~7LL;        // map entries: 16-byte aligned window
+            unsigned char *dst = ring + slot * kSlotBytes;
+            mbar_expect_tx(&bars[slot], 3 * kStripCells * 8 + kMapWindowBytes);
+            bulk_load(dst, a.in[0] + base, kStripCells * 8, &bars[slot]);
+            bulk_load(dst + kStripCells * 8, a.in[1] + base, kStripCells * 8, &bars[slot]);
+            bulk_load(dst + 2 * kStripCells * 8, a.in[2] + base, kStripCells * 8, &bars[slot]);
+            bulk_load(dst + 3 * kStripCells * 8, a.map + base8, kMapWindowBytes, &bars[slot]);
+        };
+        if (lane == 0)
+            for (int d = 0; d < kRingDepth && r0 + d < r1; ++d) issue(r0 + d, d);
 
-    // owned cells of this lane: the 120 inner cells of the strip that lie inside the row
-    const long long x0 = xs + 4 * lane;
-    const bool lane_owned = lane >= 1 && lane <= 30 && x0 < nx;
-    // shared-memory read pattern: two conflict-free 16-byte loads per field (lanes 4-7 of every
-    // quarter-warp take the upper half first)
-    const int swap = (lane >> 2) & 1;
-    const int off_a = lane * 32 + swap * 16, off_b = lane * 32 + (swap ^ 1) * 16;
+        // pipeline state: per stage the previous row's p (after boundaries), new vx, new vy
+        double pb[K][4], un[K][4], vn[K][4];
+        RowInfo info[K + 1];
+#pragma unroll
+        for (int s = 0; s < K; ++s)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) pb[s][c] = un[s][c] = vn[s][c] = 0.0;
+#pragma unroll
+        for (int s = 0; s <= K; ++s) info[s] = RowInfo{0ull, 0, false, 0u};
 
-    int slot = 0;
-    unsigned parity = 0;
-    for (long long r = r0; r < r1; ++r) {
-        mbar_wait(&bars[slot], parity);
-        const unsigned char *src = ring + slot * kSlotBytes;
-        double cur[3][4];
-#pragma unroll
-        for (int f = 0; f < 3; ++f) {
-            const double2 va = *reinterpret_cast<const double2 *>(src + f * kStripCells * 8 + off_a);
-            const double2 vb = *reinterpret_cast<const double2 *>(src + f * kStripCells * 8 + off_b);
-            cur[f][0] = swap ? vb.x : va.x;
-            cur[f][1] = swap ? vb.y : va.y;
-            cur[f][2] = swap ? va.x : vb.x;
-            cur[f][3] = swap ? va.y : vb.y;
-        }
-        const long long base = r * nx + xs;
-        const unsigned idw = *reinterpret_cast<const unsigned *>(
-            src + 3 * kStripCells * 8 + (int)(base & 15LL) + 4 * lane);
-        __syncwarp();
-        if (lane == 0 && r + kRingDepth < r1) issue(r + kRingDepth, slot);
-        if (++slot == kRingDepth) { slot = 0; parity ^= 1; }
+        // owned cells of this lane: the 120 inner cells of the strip that lie inside the row
+        const long long x0 = xs + 4 * lane;
+        const bool lane_owned = lane >= 1 && lane <= 30 && x0 < nx;
+        long long cell_r = r0 * nx + x0;    // flat index of this lane's first cell in row r
+        const int map_step = (int)(nx & 7LL);
+        int map_off = (int)((r0 * nx + xs) & 7LL);   // (r * nx + xs) & 7: entry offset in the window
 
-        // metadata of the new row (once per row, reused by all K stages)
-#pragma unroll
-        for (int s = K; s > 0; --s) info[s] = info[s - 1];
-        {
-            const unsigned first = __shfl_sync(0xffffffffu, idw, 0) & kIdMask;
-            const bool uni = __all_sync(0xffffffffu, (idw & 0x3f3f3f3fu) == first * 0x01010101u);
-            info[0].ids = idw;
-            info[0].uniform = uni ? (int)first : -1;
-            info[0].any_bound = __any_sync(0xffffffffu, idw & 0x40404040u);
-            info[0].any_probe = __any_sync(0xffffffffu, idw & 0x80808080u);
-        }
-
-#pragma unroll
-        for (int s = 0; s < K; ++s) {
-            // stage s: cur = row q at level s  ->  cur = row q-1 at level s+1
-            const long long q = r - s;
-            const RowInfo &ri = info[s], &rp = info[s + 1];
-            const long long cell0 = q * nx + x0;
-            const long long sig = a.sig_index + s;
-            double *__restrict__ record = t.ring + (a.ring_row + s) * t.n_slots;
-            const bool owned_row = lane_owned && q >= ys && q < ye;
-
-            // 1. boundaries and probes of p (row q)
-            if (ri.any_bound) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if ((ri.ids >> (8 * c)) & kFlagBound)
-                        cur[0][c] = apply_bounds(t.bound[0], t.signals, t.sig_steps, sig, cell0 + c,
-                                                 cur[0][c]);
-            }
-            if (ri.any_probe && owned_row) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    if ((ri.ids >> (8 * c)) & kFlagProbe)
-                        write_probes(t.probe[0], record, cell0 + c, cur[0][c]);
-            }
-
-            // 2. new vx, vy of row q (backward differences of p), their boundaries and probes;
-            // 3. new p of row q-1 (forward differences of the new vx, vy).
-            // `coef` yields the material coefficient of a cell: gx(c) for row q, cell c-1 (c = 0 is
-            // the left-hand lane's last cell); gyc/fyc(c) row q; gyp/fxp/fyp(c) row q-1 (fxp(4) is the
-            // right-hand lane's first cell).
-            double nu[4], nv[4], np[4];
-            auto math = [&](const auto &coef) {
-                const double p_left = shfl_up1(cur[0][3]);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const double pl = c ? cur[0][c - 1] : p_left;
-                    nu[c] = sub(cur[1][c], diff2(coef.gx(c), pl, coef.gx(c + 1), cur[0][c]));
-                    nv[c] = sub(cur[2][c], diff2(coef.gyp(c), pb[s][c], coef.gyc(c), cur[0][c]));
-                }
-                if (ri.any_bound) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if ((ri.ids >> (8 * c)) & kFlagBound) {
-                            nu[c] = apply_bounds(t.bound[1], t.signals, t.sig_steps, sig, cell0 + c,
-                                                 nu[c]);
-                            nv[c] = apply_bounds(t.bound[2], t.signals, t.sig_steps, sig, cell0 + c,
-                                                 nv[c]);
-                        }
-                }
-                if (ri.any_probe && owned_row) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        if ((ri.ids >> (8 * c)) & kFlagProbe) {
-                            write_probes(t.probe[1], record, cell0 + c, nu[c]);
-                            write_probes(t.probe[2], record, cell0 + c, nv[c]);
-                        }
-                }
-                const double u_right = shfl_down1(un[s][0]);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const double ur = c < 3 ? un[s][c + 1] : u_right;
-                    const double divx = diff2(coef.fxp(c), un[s][c], coef.fxp(c + 1), ur);
-                    const double divy = diff2(coef.fyp(c), vn[s][c], coef.fyc(c), nv[c]);
-                    np[c] = sub(pb[s][c], add(divx, divy));
-                }
-            };
-            if (ri.uniform >= 0 && ri.uniform == rp.uniform) {
-                // all 256 cells of rows q-1 and q share one material: four coefficients in registers
-                struct {
-                    double g0, g1, f0, f1;
-                    __device__ double gx(int) const { return g0; }
-                    __device__ double gyc(int) const { return g1; }
-                    __device__ double gyp(int) const { return g1; }
-                    __device__ double fxp(int) const { return f0; }
-                    __device__ double fyp(int) const { return f1; }
-                    __device__ double fyc(int) const { return f1; }
-                } coef{tabs[FDS_TAB_GX][ri.uniform], tabs[FDS_TAB_GY][ri.uniform],
-                       tabs[FDS_TAB_FX][ri.uniform], tabs[FDS_TAB_FY][ri.uniform]};
-                math(coef);
-            } else {
-                struct {
-                    const double (*tabs)[kMaxMaterials];
-                    unsigned cur_ids, prev_ids, left, right;
-                    __device__ int mc(int c) const { return (cur_ids >> (8 * c)) & kIdMask; }
-                    __device__ int mp(int c) const { return (prev_ids >> (8 * c)) & kIdMask; }
-                    __device__ double gx(int c) const {
-                        return tabs[FDS_TAB_GX][c ? mc(c - 1) : (int)((left >> 24) & kIdMask)];
-                    }
-                    __device__ double gyc(int c) const { return tabs[FDS_TAB_GY][mc(c)]; }
-                    __device__ double gyp(int c) const { return tabs[FDS_TAB_GY][mp(c)]; }
-                    __device__ double fxp(int c) const {
-                        return tabs[FDS_TAB_FX][c < 4 ? mp(c) : (int)(right & kIdMask)];
-                    }
-                    __device__ double fyp(int c) const { return tabs[FDS_TAB_FY][mp(c)]; }
-                    __device__ double fyc(int c) const { return tabs[FDS_TAB_FY][mc(c)]; }
-                } coef{tabs, ri.ids, rp.ids,
-                       __shfl_up_sync(0xffffffffu, ri.ids, 1),       // lane-1, row q
-                       __shfl_down_sync(0xffffffffu, rp.ids, 1)};    // lane+1, row q-1
-                math(coef);
-            }
-
-            // 4. hand row q-1 (level s+1) to the next stage, keep row q for the next iteration
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const double keep_p = cur[0][c];
-                cur[0][c] = np[c];
-                cur[1][c] = un[s][c];
-                cur[2][c] = vn[s][c];
-                pb[s][c] = keep_p;
-                un[s][c] = nu[c];
-                vn[s][c] = nv[c];
-            }
-        }
-
-        // row r-K at level K
-        const long long orow = r - K;
-        if (lane_owned && orow >= ys && orow < ye) {
-            const long long o = orow * nx + x0;
+        int slot = 0;
+        for (long long r = r0; r < r1; ++r) {
+            mbar_wait(&bars[slot], (phase_bits >> slot) & 1u);
+            phase_bits ^= 1u << slot;
+            const unsigned char *src = ring + slot * kSlotBytes;
+            double cur[3][4];
 #pragma unroll
             for (int f = 0; f < 3; ++f) {
-                *reinterpret_cast<double2 *>(a.out[f] + o) = make_double2(cur[f][0], cur[f][1]);
-                *reinterpret_cast<double2 *>(a.out[f] + o + 2) = make_double2(cur[f][2], cur[f][3]);
+                const double2 va =
+                    *reinterpret_cast<const double2 *>(src + f * kStripCells * 8 + off_a);
+                const double2 vb =
+                    *reinterpret_cast<const double2 *>(src + f * kStripCells * 8 + off_b);
+                cur[f][0] = swap ? vb.x : va.x;
+                cur[f][1] = swap ? vb.y : va.y;
+                cur[f][2] = swap ? va.x : vb.x;
+                cur[f][3] = swap ? va.y : vb.y;
             }
+            const unsigned long long idw = *reinterpret_cast<const unsigned long long *>(
+                src + 3 * kStripCells * 8 + 2 * map_off + 8 * lane);
+            map_off = (map_off + map_step) & 7;
+            __syncwarp();
+            if (lane == 0 && r + kRingDepth < r1) issue(r + kRingDepth, slot);
+            if (++slot == kRingDepth) slot = 0;
+
+            // metadata of the new row (once per row, reused by all K stages)
+#pragma unroll
+            for (int s = K; s > 0; --s) info[s] = info[s - 1];
+            {
+                const unsigned long long first = __shfl_sync(0xffffffffu, idw, 0) & kIdMask;
+                const bool uni = __all_sync(0xffffffffu, (idw & 0x001f001f001f001full) ==
+                                                             first * 0x0001000100010001ull);
+                info[0].ids = idw;
+                info[0].uniform = uni ? (int)first : -1;
+                info[0].flagged = __any_sync(0xffffffffu, (idw & 0x0060006000600060ull) != 0);
+                info[0].classed = 0u;
+                if (__any_sync(0xffffffffu, (idw & 0xff80ff80ff80ff80ull) != 0)) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const unsigned long long m = 0x0007000700070007ull << class_shift(c);
+                        if (__any_sync(0xffffffffu, (idw & m) != 0)) info[0].classed |= 1u << c;
+                    }
+                }
+            }
+
+#pragma unroll
+            for (int s = 0; s < K; ++s) {
+                // stage s: cur = row q = r - s at level s  ->  cur = row q-1 at level s+1
+                const RowInfo &ri = info[s], &rp = info[s + 1];
+
+                // 1. boundaries and probes of p (row q)
+                if (ri.classed & 1u) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        cur[0][c] = apply_class(cls_alpha, cls_value, 0,
+                                                (unsigned)(ri.ids >> (16 * c)), cur[0][c]);
+                }
+                if (ri.flagged) {
+                    const long long q = r - s;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) scratch[c] = cur[0][c];
+                    stream_slow_cells(a.tables, 0, 1, a.sig_index + s, a.ring_row + s,
+                                      cell_r - s * nx, ri.ids,
+                                      lane_owned && q >= ys && q < ye, scratch);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) cur[0][c] = scratch[c];
+                }
+
+                // 2. new vx, vy of row q (backward differences of p), their boundaries and probes;
+                // 3. new p of row q-1 (forward differences of the new vx, vy).
+                // `coef` yields the material coefficient of a cell: gx(c) for row q, cell c-1 (c = 0
+                // is the left-hand lane's last cell); gyc/fyc(c) row q; gyp/fxp/fyp(c) row q-1
+                // (fxp(4) is the right-hand lane's first cell).
+                double nu[4], nv[4], np[4];
+                auto math = [&](const auto &coef) {
+                    const double p_left = shfl_up1(cur[0][3]);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const double pl = c ? cur[0][c - 1] : p_left;
+                        nu[c] = sub(cur[1][c], diff2(coef.gx(c), pl, coef.gx(c + 1), cur[0][c]));
+                        nv[c] = sub(cur[2][c], diff2(coef.gyp(c), pb[s][c], coef.gyc(c), cur[0][c]));
+                    }
+                    if (ri.classed & 2u) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            nu[c] = apply_class(cls_alpha, cls_value, 1,
+                                                (unsigned)(ri.ids >> (16 * c)), nu[c]);
+                    }
+                    if (ri.classed & 4u) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            nv[c] = apply_class(cls_alpha, cls_value, 2,
+                                                (unsigned)(ri.ids >> (16 * c)), nv[c]);
+                    }
+                    if (ri.flagged) {
+                        const long long q = r - s;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { scratch[c] = nu[c]; scratch[4 + c] = nv[c]; }
+                        stream_slow_cells(a.tables, 1, 2, a.sig_index + s, a.ring_row + s,
+                                          cell_r - s * nx, ri.ids,
+                                          lane_owned && q >= ys && q < ye, scratch);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) { nu[c] = scratch[c]; nv[c] = scratch[4 + c]; }
+                    }
+                    const double u_right = shfl_down1(un[s][0]);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const double ur = c < 3 ? un[s][c + 1] : u_right;
+                        const double divx = diff2(coef.fxp(c), un[s][c], coef.fxp(c + 1), ur);
+                        const double divy = diff2(coef.fyp(c), vn[s][c], coef.fyc(c), nv[c]);
+                        np[c] = sub(pb[s][c], add(divx, divy));
+                    }
+                };
+                if (ri.uniform >= 0 && ri.uniform == rp.uniform) {
+                    // all 256 cells of rows q-1 and q share one material: 4 coefficients in registers
+                    struct {
+                        double g0, g1, f0, f1;
+                        __device__ double gx(int) const { return g0; }
+                        __device__ double gyc(int) const { return g1; }
+                        __device__ double gyp(int) const { return g1; }
+                        __device__ double fxp(int) const { return f0; }
+                        __device__ double fyp(int) const { return f1; }
+                        __device__ double fyc(int) const { return f1; }
+                    } coef{tabs[FDS_TAB_GX][ri.uniform], tabs[FDS_TAB_GY][ri.uniform],
+                           tabs[FDS_TAB_FX][ri.uniform], tabs[FDS_TAB_FY][ri.uniform]};
+                    math(coef);
+                } else {
+                    struct {
+                        const double (*tabs)[kMaxMaterials];
+                        unsigned long long cur_ids, prev_ids, left, right;
+                        __device__ int mc(int c) const { return (int)(cur_ids >> (16 * c)) & kIdMask; }
+                        __device__ int mp(int c) const { return (int)(prev_ids >> (16 * c)) & kIdMask; }
+                        __device__ double gx(int c) const {
+                            return tabs[FDS_TAB_GX][c ? mc(c - 1) : (int)((left >> 48) & kIdMask)];
+                        }
+                        __device__ double gyc(int c) const { return tabs[FDS_TAB_GY][mc(c)]; }
+                        __device__ double gyp(int c) const { return tabs[FDS_TAB_GY][mp(c)]; }
+                        __device__ double fxp(int c) const {
+                            return tabs[FDS_TAB_FX][c < 4 ? mp(c) : (int)(right & kIdMask)];
+                        }
+                        __device__ double fyp(int c) const { return tabs[FDS_TAB_FY][mp(c)]; }
+                        __device__ double fyc(int c) const { return tabs[FDS_TAB_FY][mc(c)]; }
+                    } coef{tabs, ri.ids, rp.ids,
+                           __shfl_up_sync(0xffffffffu, ri.ids, 1),       // lane-1, row q
+                           __shfl_down_sync(0xffffffffu, rp.ids, 1)};    // lane+1, row q-1
+                    math(coef);
+                }
+
+                // 4. hand row q-1 (level s+1) to the next stage, keep row q for the next iteration
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double keep_p = cur[0][c];
+                    cur[0][c] = np[c];
+                    cur[1][c] = un[s][c];
+                    cur[2][c] = vn[s][c];
+                    pb[s][c] = keep_p;
+                    un[s][c] = nu[c];
+                    vn[s][c] = nv[c];
+                }
+            }
+
+            // row r-K at level K
+            const long long orow = r - K;
+            if (lane_owned && orow >= ys && orow < ye) {
+                const long long o = cell_r - K * nx;
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    *reinterpret_cast<double2 *>(a.out[f] + o) = make_double2(cur[f][0], cur[f][1]);
+                    *reinterpret_cast<double2 *>(a.out[f] + o + 2) =
+                        make_double2(cur[f][2], cur[f][3]);
+                }
+            }
+            cell_r += nx;
         }
     }
 }

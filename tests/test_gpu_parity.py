@@ -164,30 +164,37 @@ def test_round_trip_properties_at_full_size(library):
 
 def _stream_case(nx, ny, steps, seed, kernel):
     """Boundaries, sources and probes placed on strip seams (x = 119, 120, 121, 240), on the halo
-    lanes, on the first/last rows and on chunk seams."""
+    lanes, on the first/last rows and on chunk seams (coordinates clamped to small grids)."""
+    def X(k):
+        return min(k, nx - 1) * 1e-3
+
+    def Y(k):
+        return min(k, ny - 1) * 1e-3
+
     f = fds.Acoustic2D(t_delta=1e-7, t_samples=steps, x_delta=1e-3, x_samples=nx, y_delta=1e-3,
                        y_samples=ny, material=fds.AcousticMaterial(1500, 1000))
     f.device_kernel = kernel
-    f.add_material_region(f.get_rect_region((100e-3, 10e-3, 45e-3, 30e-3)),
+    f.add_material_region(f.get_rect_region((X(100), Y(10), X(145) - X(100), Y(40) - Y(10))),
                           fds.AcousticMaterial(1200, 900))
-    f.add_material_region(f.get_rect_region((119e-3, 20e-3, 2e-3, 40e-3)),
+    f.add_material_region(f.get_rect_region((X(119), Y(20), X(121) - X(119), Y(60) - Y(20))),
                           fds.AcousticMaterial(1350, 950))
     scenarios._randomise(f, ('pressure', 'velocity_x', 'velocity_y'), seed)
-    Y = (ny - 1) * 1e-3
-    f.velocity_x.add_boundary(f.get_line_region((0, 0, 0, Y)))
-    f.velocity_x.add_boundary(f.get_line_region((120e-3, 0, 120e-3, Y)), value=1e-6, additive=True)
-    f.velocity_y.add_boundary(f.get_line_region((0, 32e-3, (nx - 1) * 1e-3, 32e-3)))
-    f.pressure.add_boundary(f.get_line_region((0, 0, (nx - 1) * 1e-3, 0)))
-    f.pressure.add_boundary(f.get_line_region((0, Y, (nx - 1) * 1e-3, Y)), value=2e-4)
+    top = Y(ny)
+    f.velocity_x.add_boundary(f.get_line_region((0, 0, 0, top)))
+    f.velocity_x.add_boundary(f.get_line_region((X(120), 0, X(120), top)), value=1e-6,
+                              additive=True)
+    f.velocity_y.add_boundary(f.get_line_region((0, Y(32), X(nx), Y(32))))
+    f.pressure.add_boundary(f.get_line_region((0, 0, X(nx), 0)))
+    f.pressure.add_boundary(f.get_line_region((0, top, X(nx), top)), value=2e-4)
     for k, x in enumerate((119, 120, 121, 240, 0, nx - 1)):
-        f.pressure.add_boundary(f.get_point_region((x * 1e-3, (5 + 9 * k) * 1e-3)),
+        f.pressure.add_boundary(f.get_point_region((X(x), Y(5 + 9 * k))),
                                 value=scenarios._pulse(steps, 10 + k, 6), additive=True)
-        f.pressure.add_output(f.get_point_region((x * 1e-3, (5 + 9 * k) * 1e-3)))
-        f.velocity_x.add_output(f.get_point_region((x * 1e-3, (6 + 9 * k) * 1e-3)))
-        f.velocity_y.add_output(f.get_point_region((x * 1e-3, 32e-3)))
-    f.pressure.add_output(f.get_line_region((100e-3, 31e-3, 140e-3, 31e-3)))
+        f.pressure.add_output(f.get_point_region((X(x), Y(5 + 9 * k))))
+        f.velocity_x.add_output(f.get_point_region((X(x), Y(6 + 9 * k))))
+        f.velocity_y.add_output(f.get_point_region((X(x), Y(32))))
+    f.pressure.add_output(f.get_line_region((X(100), Y(31), X(140), Y(31))))
     f.velocity_y.add_output(f.get_point_region((0, 0)))
-    f.velocity_y.add_output(f.get_point_region(((nx - 1) * 1e-3, Y)))
+    f.velocity_y.add_output(f.get_point_region((X(nx), top)))
     return f
 
 
