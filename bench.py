@@ -234,8 +234,6 @@ def main():
     rng = np.random.default_rng(1 + rank)
     for c in range(3):
         engine.upload_state(c, 1e-3 * rng.standard_normal(engine.owned))
-    if run is not None:
-        run.exchange_initial()
 
     def barrier():
         engine.sync()

@@ -551,6 +551,14 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
     ctx->last_launches = 0;
     ctx->last_steps_per_launch = 1;
 
+    if (ctx->comm && ctx->world > 1 && ctx->dims == 2) {
+        // the neighbours' rows of the current state (fresh upload, or a previous call's last step)
+        FDS_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
+        FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
+        if (exchange_halos(ctx, ctx->cur)) return 1;
+        FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+        FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+    }
     FDS_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
     long long done = 0;
     long long chunk = 0;
@@ -1083,15 +1091,6 @@ int fds_step(fds_ctx *ctx, int64_t first_step, int64_t n_steps, double *probes_o
     if (n_steps < 0) return fail(ctx, "fds_step: negative step count");
     if (ctx->n_slots > 0 && n_steps > 0 && !probes_out)
         return fail(ctx, "fds_step: probes are configured but probes_out is NULL");
-    if (ctx->comm && ctx->world > 1 && ctx->dims == 2) {
-        // neighbours need our current rows before the first step
-        FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
-        FDS_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
-        FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
-        if (exchange_halos(ctx, ctx->cur)) return 1;
-        FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
-        FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
-    }
     if (run_steps(ctx, first_step, n_steps, true)) return 1;
     FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     FDS_CUDA(ctx, cudaStreamSynchronize(ctx->drain));

@@ -1,0 +1,154 @@
+"""Multi-GPU runs: one process per GPU, the grid cut into contiguous y-slabs.
+
+The reference is single-process and has nothing comparable. The flat cell index
+``x + y * nx`` (``pyfds/fields.py:377``) makes a y-slab a contiguous index range and every stencil
+neighbour lies within +-nx of a cell, so a slab needs ``reach`` rows of its neighbours per time step:
+1 row for the lossless leapfrog, 2 rows when the viscous 5-point operator is active. A launch that
+advances k steps therefore consumes ``k * reach`` halo rows; after each launch the outermost rows of all
+state components travel to the neighbour slabs (``ncclSend``/``ncclRecv`` pairs inside
+``libfdsb200.so``, on a separate stream, while the interior rows are being computed).
+
+``torch.distributed`` is only plumbing here: it hands the NCCL unique id from rank 0 to the other ranks
+and gathers probe records; none of the field data moves through it.
+"""
+
+import numpy as np
+
+from . import _engine
+
+#: steps per launch of the streaming kernel = halo rows it needs on a lossless grid
+STREAM_STEPS = 4
+
+
+def partition_rows(ny, world):
+    """Balanced contiguous row ranges: list of ``(row0, rows)`` for ranks 0..world-1."""
+    base, extra = divmod(int(ny), int(world))
+    parts, row0 = [], 0
+    for rank in range(world):
+        rows = base + (1 if rank < extra else 0)
+        parts.append((row0, rows))
+        row0 += rows
+    return parts
+
+
+def is_lossy(field):
+    """True if any material region has a non-zero absorption coefficient (acoustic models)."""
+    if not field.matrices_assembled:
+        field.assemble_matrices()
+    return any(values.get('absorption_coef', 0) != 0
+               for _, values in field._baked['snapshot'].entries)
+
+
+def stencil_reach(field):
+    """Rows of neighbour data one time step needs on either side of a slab."""
+    return 2 if is_lossy(field) else 1
+
+
+def streaming_eligible(field):
+    nx = field.x.samples
+    return field._device_model == 'acoustic2d' and not is_lossy(field) and nx % 4 == 0 and nx >= 128
+
+
+def halo_rows_for(field, world, kernel=0):
+    """Halo rows per side of a slab context: the reach of one step, times the steps per launch when
+    the streaming kernel will run."""
+    if world <= 1:
+        return 0
+    if kernel != 1 and streaming_eligible(field):
+        return STREAM_STEPS * stencil_reach(field)
+    return stencil_reach(field)
+
+
+def _broadcast_unique_id(rank):
+    import torch.distributed as dist
+    payload = [_engine.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(payload, src=0)
+    return payload[0]
+
+
+class SlabRun:
+    """The slab of ``field`` owned by ``rank``: device context, NCCL communicator and a ``simulate``
+    that mirrors ``Field.simulate`` for the rows this rank owns.
+
+    Every rank constructs the same ``field`` (same script, SPMD). Host ``values`` arrays stay full
+    size; a rank uploads and refreshes only its own rows -- use ``gather`` to assemble whole fields.
+    """
+
+    def __init__(self, field, rank, world, device=0, kernel=None, unique_id=None):
+        if not hasattr(field, 'y'):
+            raise ValueError('Only 2-D fields are partitioned; 1-D problems stay on one GPU.')
+        if not field.matrices_assembled:
+            field.assemble_matrices()
+        if kernel is None:
+            kernel = getattr(field, 'device_kernel', 0)
+        self.field, self.rank, self.world = field, rank, world
+        self.row0, self.rows = partition_rows(field.y.samples, world)[rank]
+        self.halo_rows = halo_rows_for(field, world, kernel)
+        if world > 1 and self.rows < self.halo_rows:
+            raise ValueError('Slabs of {} rows are thinner than the {} halo rows needed.'.format(
+                self.rows, self.halo_rows))
+        self.engine = _engine.prepare(field, device=device, row0=self.row0, rows=self.rows,
+                                      halo_rows=self.halo_rows, kernel=kernel)
+        if world > 1:
+            if unique_id is None:
+                unique_id = _broadcast_unique_id(rank)
+            self.engine.comm_init(unique_id, rank, world)
+
+    @property
+    def cells(self):
+        nx = self.field.x.samples
+        return slice(self.row0 * nx, (self.row0 + self.rows) * nx)
+
+    def upload_state(self):
+        for c, name in enumerate(self.field._device_components):
+            values = _engine._host_values(getattr(self.field, name), self.field.num_points)
+            self.engine.upload_state(c, values[self.cells])
+
+    def download_state(self):
+        for c, name in enumerate(self.field._device_components):
+            component = getattr(self.field, name)
+            values = np.ascontiguousarray(component.values, dtype=np.float64)
+            values[self.cells] = self.engine.download_state(c)
+            component.values = values
+
+    def simulate(self, num_steps, gather_probes=True):
+        """Advances the slab ``num_steps`` steps. Probe signals are summed over ranks (every probe
+        point is owned by exactly one slab) so that each rank ends up with complete ``signals``."""
+        field, engine = self.field, self.engine
+        first_step = field.step
+        n_slots, layout = _engine.upload_run_tables(field, engine, first_step, num_steps)
+        self.upload_state()
+        records = engine.step(first_step, num_steps, n_slots)
+        self.download_state()
+        if n_slots:
+            if gather_probes and self.world > 1:
+                import torch
+                import torch.distributed as dist
+                # gloo/NCCL agnostic: go through a tensor on the backend's device
+                backend = dist.get_backend()
+                tensor = torch.from_numpy(records)
+                if backend == 'nccl':
+                    tensor = tensor.cuda()
+                dist.all_reduce(tensor)
+                records = tensor.cpu().numpy()
+            _engine._append_signals(layout, records)
+        field.step += num_steps
+
+    def gather(self):
+        """All-gathers the owned rows so that every rank holds the complete ``values`` arrays."""
+        if self.world == 1:
+            return
+        import torch
+        import torch.distributed as dist
+        nx = self.field.x.samples
+        parts = partition_rows(self.field.y.samples, self.world)
+        for name in self.field._device_components:
+            component = getattr(self.field, name)
+            values = np.ascontiguousarray(component.values, dtype=np.float64)
+            for src, (row0, rows) in enumerate(parts):
+                block = torch.from_numpy(values[row0 * nx:(row0 + rows) * nx].copy())
+                if dist.get_backend() == 'nccl':
+                    block = block.cuda()
+                dist.broadcast(block, src=src)
+                values[row0 * nx:(row0 + rows) * nx] = block.cpu().numpy()
+            component.values = values
