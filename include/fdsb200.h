@@ -87,7 +87,7 @@ typedef struct fds_desc {
     int32_t halo_rows;    /* rows of neighbour data kept on either side (0 on a single GPU) */
     int32_t lossy;        /* non-zero if any material has absorption_coef != 0 (acoustic models) */
     int32_t n_materials;  /* real materials, ids 1..n_materials (<= 31) */
-    int32_t kernel;       /* 0 = automatic, 1 = force the one-step reference kernel, 2 = force the
+    int32_t kernel;       /* 0 = automatic, 1 = one-step kernel on global memory, 3 = one-step tile kernel, 2 = force the
                              streaming multi-step kernel (fails if the model/grid does not support it) */
 } fds_desc;
 

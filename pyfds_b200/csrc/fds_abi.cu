@@ -136,10 +136,12 @@ struct fds_ctx {
     int rank = 0, world = 1;
 
     bool use_stream2d = false; // streaming multi-step kernel selected
+    bool use_tile2d = false;   // shared-memory tile kernel selected (one step per launch)
     StepTables *d_tables = nullptr;   // device copy of the tables for the streaming kernel's slow path
     int *task_counters = nullptr;     // pool of zeroed work counters, one per streaming launch
     int next_counter = 0;
     int chunk_rows = 0;       // rows per streaming task (0 = heuristic)
+    int tile_rows = 0;        // owned rows per tile of the tile kernel (0 = default)
     int max_k = kMaxStreamSteps;
 
     std::string err;
@@ -333,10 +335,47 @@ StepTables make_tables(fds_ctx *ctx) {
 
 // ---- kernel dispatch ----------------------------------------------------------------------------
 
+constexpr int kCounterPool = 4096;
+
+int *next_counter(fds_ctx *ctx) {
+    if (ctx->next_counter == kCounterPool) {
+        if (cudaMemsetAsync(ctx->task_counters, 0, sizeof(int) * kCounterPool, ctx->stream) !=
+            cudaSuccess)
+            return nullptr;
+        ctx->next_counter = 0;
+    }
+    return ctx->task_counters + ctx->next_counter++;
+}
+
 template <int MODEL, bool LOSSY>
 int launch_step2d(fds_ctx *ctx, const Step2DArgs &a, const StepTables &t) {
     const long long rows = a.row_end - a.row_begin;
     if (rows <= 0) return 0;
+    if (ctx->use_tile2d) {
+        constexpr bool thermal = (MODEL == FDS_THERMAL2D || MODEL == FDS_THERMAL3DAXI);
+        Tile2DArgs g{};
+        g.rows_below = 1;
+        g.rows_above = (LOSSY && !thermal) ? 2 : 1;
+        g.tile_h = thermal ? 64 : 24;
+        if (ctx->tile_rows > 0) g.tile_h = ctx->tile_rows;
+        g.tiles_x = (int)((a.nx + kTileW - 1) / kTileW);
+        g.n_tiles = (int)(g.tiles_x * ((rows + g.tile_h - 1) / g.tile_h));
+        g.counter = next_counter(ctx);
+        if (!g.counter) return fail(ctx, "tile2d: counter reset failed");
+        const int tile_rows = g.tile_h + g.rows_below + g.rows_above;
+        const int smem = tile_rows * kTilePitch * ((thermal ? 1 : 3) * 8 + (int)sizeof(map_t));
+        auto kernel = tile2d_kernel<MODEL, LOSSY>;
+        static int configured = 0;
+        if (configured < smem) {
+            FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               smem));
+            configured = smem;
+        }
+        const int ctas = std::min(g.n_tiles, 148 * 2);
+        kernel<<<ctas, kTileThreads, smem, ctx->stream>>>(a, t, ctx->d.n_materials + 1, g);
+        FDS_CUDA(ctx, cudaGetLastError());
+        return 0;
+    }
     dim3 grid((unsigned)rows, (unsigned)((a.nx + 255) / 256));
     step2d_kernel<MODEL, LOSSY><<<grid, 256, 0, ctx->stream>>>(a, t, ctx->d.n_materials + 1);
     FDS_CUDA(ctx, cudaGetLastError());
@@ -361,6 +400,16 @@ int dispatch_step2d(fds_ctx *ctx, const Step2DArgs &a, const StepTables &t) {
 }
 
 const char *step2d_name(const fds_ctx *ctx) {
+    if (ctx->use_tile2d) {
+        switch (ctx->d.model) {
+            case FDS_ACOUSTIC2D: return ctx->d.lossy ? "tile2d_kernel<acoustic2d,lossy>"
+                                                     : "tile2d_kernel<acoustic2d,lossless>";
+            case FDS_ACOUSTIC3DAXI: return ctx->d.lossy ? "tile2d_kernel<acoustic3daxi,lossy>"
+                                                        : "tile2d_kernel<acoustic3daxi,lossless>";
+            case FDS_THERMAL2D: return "tile2d_kernel<thermal2d>";
+            case FDS_THERMAL3DAXI: return "tile2d_kernel<thermal3daxi>";
+        }
+    }
     switch (ctx->d.model) {
         case FDS_ACOUSTIC2D: return ctx->d.lossy ? "step2d_kernel<acoustic2d,lossy>"
                                                  : "step2d_kernel<acoustic2d,lossless>";
@@ -376,10 +425,9 @@ const char *step2d_name(const fds_ctx *ctx) {
 // ---- streaming multi-step kernel (fds_stream2d.cuh) ---------------------------------------------
 
 bool stream_supported(const fds_desc &d) {
-    return d.model == FDS_ACOUSTIC2D && !d.lossy && d.nx % 4 == 0 && d.nx >= kStripCells;
+    const bool model_ok = (d.model == FDS_ACOUSTIC2D && !d.lossy) || d.model == FDS_THERMAL2D;
+    return model_ok && d.nx % 4 == 0 && d.nx >= kStripCells;
 }
-
-constexpr int kCounterPool = 4096;
 
 int stream_chunk_rows(const fds_ctx *ctx, long long rows, int n_strips, int k) {
     if (ctx->chunk_rows > 0) return ctx->chunk_rows;
@@ -397,9 +445,9 @@ int stream_chunk_rows(const fds_ctx *ctx, long long rows, int n_strips, int k) {
     return (int)best;
 }
 
-template <int K>
+template <int K, bool THERMAL>
 int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
-    auto kernel = stream2d_kernel<K>;
+    auto kernel = stream2d_kernel<K, THERMAL>;
     const int smem = kStreamWarps * kWarpRingBytes;
     static bool configured = false;
     if (!configured) {
@@ -420,10 +468,6 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     a.n_strips = (int)((a.nx + kStripStride - 1) / kStripStride);
     a.chunk_rows = stream_chunk_rows(ctx, rows, a.n_strips, k);
     a.n_tasks = (int)(a.n_strips * ((rows + a.chunk_rows - 1) / a.chunk_rows));
-    if (ctx->next_counter == kCounterPool) {
-        FDS_CUDA(ctx, cudaMemsetAsync(ctx->task_counters, 0, sizeof(int) * kCounterPool, ctx->stream));
-        ctx->next_counter = 0;
-    }
     if (ctx->n_strips_ordered != a.n_strips) {
         // strips that carry boundary cells (slow path) are handed out first (longest task first)
         std::vector<long long> weight((size_t)a.n_strips, 0);
@@ -446,15 +490,25 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     }
     a.strip_order = (const int *)ctx->strip_order.ptr;
     a.n_chunks = (int)((rows + a.chunk_rows - 1) / a.chunk_rows);
-    a.task_counter = ctx->task_counters + ctx->next_counter++;
+    a.task_counter = next_counter(ctx);
+    if (!a.task_counter) return fail(ctx, "stream2d: counter reset failed");
     a.map = ctx->map + ctx->pad + ctx->halo;
     a.tab = ctx->tab;
     a.tables = ctx->d_tables;
-    switch (k) {
-        case 1: return launch_stream2d<1>(ctx, a);
-        case 2: return launch_stream2d<2>(ctx, a);
-        case 3: return launch_stream2d<3>(ctx, a);
-        case 4: return launch_stream2d<4>(ctx, a);
+    if (ctx->thermal) {
+        switch (k) {
+            case 1: return launch_stream2d<1, true>(ctx, a);
+            case 2: return launch_stream2d<2, true>(ctx, a);
+            case 3: return launch_stream2d<3, true>(ctx, a);
+            case 4: return launch_stream2d<4, true>(ctx, a);
+        }
+    } else {
+        switch (k) {
+            case 1: return launch_stream2d<1, false>(ctx, a);
+            case 2: return launch_stream2d<2, false>(ctx, a);
+            case 3: return launch_stream2d<3, false>(ctx, a);
+            case 4: return launch_stream2d<4, false>(ctx, a);
+        }
     }
     return fail(ctx, "stream2d: bad step count");
 }
@@ -609,6 +663,8 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 const bool multi = ctx->comm && ctx->world > 1;
                 int k = (int)std::min<long long>(ctx->max_k, chunk_steps - in_chunk);
                 if (multi) k = std::min<int>(k, ctx->d.halo_rows);
+                // thermal fluxes are derived data: stored only by the launch that ends the call
+                a.write_vector = (s + k == n_steps);
                 if (multi) {
                     // the k outermost rows of either side travel while the interior is computed
                     const long long band = std::min<long long>(ctx->d.halo_rows, rows);
@@ -631,7 +687,8 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 }
                 advanced = k;
                 ctx->last_steps_per_launch = std::max<long long>(ctx->last_steps_per_launch, k);
-                ctx->last_kernel = "stream2d_kernel<acoustic2d,lossless>";
+                ctx->last_kernel = ctx->thermal ? "stream2d_kernel<thermal2d>"
+                                                : "stream2d_kernel<acoustic2d,lossless>";
             } else {
                 Step2DArgs a{};
                 for (int c = 0; c < 3; ++c) {
@@ -772,10 +829,17 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
     ctx->halo = (long long)d.halo_rows * d.nx;
     if (d.kernel == 2 && !stream_supported(d)) {
         delete ctx;
-        return fail(nullptr, "fds_create: the streaming kernel needs lossless Acoustic2D with nx % 4 "
-                             "== 0 and nx >= 128");
+        return fail(nullptr, "fds_create: the streaming kernel needs lossless Acoustic2D or Thermal2D "
+                             "with nx % 4 == 0 and nx >= 128");
     }
-    ctx->use_stream2d = d.kernel != 1 && stream_supported(d);
+    ctx->use_stream2d = (d.kernel == 0 || d.kernel == 2) && stream_supported(d);
+    ctx->use_tile2d = !one_d && !ctx->use_stream2d && (d.kernel == 0 || d.kernel == 3) &&
+                      d.nx % 8 == 0 && d.nx >= kTileW;
+    if (d.kernel == 3 && !ctx->use_tile2d) {
+        delete ctx;
+        return fail(nullptr, "fds_create: the tile kernel needs a 2-D model with nx % 8 == 0, nx >= 128");
+    }
+    if (const char *env = getenv("FDS_TILE_ROWS")) ctx->tile_rows = atoi(env);
     if (const char *env = getenv("FDS_CHUNK_ROWS")) ctx->chunk_rows = atoi(env);
     if (const char *env = getenv("FDS_MAX_K"))
         ctx->max_k = std::max(1, std::min(kMaxStreamSteps, atoi(env)));
@@ -820,10 +884,8 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
                           sizeof(double) * FDS_CTAB_COUNT * (d.n_materials + 1) * d.nx, true));
         FDS_TRY(dev_alloc(ctx, (void **)&ctx->cvec, sizeof(double) * FDS_CVEC_COUNT * d.nx, true));
     }
-    if (ctx->use_stream2d) {
-        FDS_TRY(dev_alloc(ctx, (void **)&ctx->d_tables, sizeof(StepTables), true));
-        FDS_TRY(dev_alloc(ctx, (void **)&ctx->task_counters, sizeof(int) * kCounterPool, true));
-    }
+    FDS_TRY(dev_alloc(ctx, (void **)&ctx->d_tables, sizeof(StepTables), true));
+    FDS_TRY(dev_alloc(ctx, (void **)&ctx->task_counters, sizeof(int) * kCounterPool, true));
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         ctx->err = "device initialisation failed";
         return bail(0);

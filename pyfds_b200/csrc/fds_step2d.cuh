@@ -37,30 +37,46 @@ __device__ __forceinline__ long long wrap_col(long long col, long long nx) {
     return col < 0 ? col + nx : (col >= nx ? col - nx : col);
 }
 
-template <int MODEL, bool LOSSY>
-__global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t, int n_mat1) {
+// Geometry of the shared-memory tile kernel.
+constexpr int kTileW = 128;                       // owned cells per tile row
+constexpr int kTileHaloX = 8;                     // extra cells either side (16-byte aligned map rows)
+constexpr int kTilePitch = kTileW + 2 * kTileHaloX;
+constexpr int kTileThreads = 256;
+
+struct Tile2DArgs {
+    int tile_h;          // owned rows per tile
+    int rows_below;      // extra rows loaded below / above the owned rows
+    int rows_above;
+    int tiles_x;
+    int n_tiles;
+    int *counter;        // dynamic tile distribution (zero before the launch)
+};
+
+// One complete `sim_step` for cell i. sp/up/wp/mp point AT the cell in a view of the three state
+// components and the map whose rows are `pitch` elements apart (global memory: pitch = nx; the
+// shared-memory tile: pitch = kTilePitch); x is the cell's column, i its local flat index (for the
+// boundary/probe tables and the output).
+template <int MODEL, bool LOSSY, bool FLAGS>
+__device__ __forceinline__ void cell_body(const Step2DArgs &a, const StepTables &t, int n_mat1,
+                                            long long i, long long x, long long pitch,
+                                            const double *__restrict__ sp,
+                                            const double *__restrict__ up,
+                                            const double *__restrict__ wp,
+                                            const map_t *__restrict__ mp,
+                                            const double (*__restrict__ tabs)[kMaxMaterials]) {
     constexpr bool kAxi = (MODEL == FDS_ACOUSTIC3DAXI || MODEL == FDS_THERMAL3DAXI);
     constexpr bool kThermal = (MODEL == FDS_THERMAL2D || MODEL == FDS_THERMAL3DAXI);
     constexpr bool kVisc = LOSSY && !kThermal;
-
-    const long long x = (long long)blockIdx.y * blockDim.x + threadIdx.x;
-    if (x >= a.nx) return;
     const long long nx = a.nx;
-    const long long i = (a.row_begin + blockIdx.x) * nx + x;
-    const map_t *__restrict__ map = t.map;
-    const double *__restrict__ sin_ = a.in[0];
-    const double *__restrict__ uin = a.in[1];
-    const double *__restrict__ win = a.in[2];
 
     // ---- all loads first ------------------------------------------------------------------------
     // map bytes / scalar field at the 5-point stencil
-    unsigned m0 = map[i], mxm = map[i - 1], mxp = map[i + 1], mym = map[i - nx], myp = map[i + nx];
-    double s0 = sin_[i], sxm = sin_[i - 1], sxp = sin_[i + 1], sym = sin_[i - nx],
-           syp = sin_[i + nx];
+    unsigned m0 = mp[0], mxm = mp[-1], mxp = mp[1], mym = mp[-pitch], myp = mp[pitch];
+    double s0 = sp[0], sxm = sp[-1], sxp = sp[1], sym = sp[-pitch], syp = sp[pitch];
     double u0 = 0, u1 = 0, w0 = 0, w1 = 0;
     if (!kThermal) {
-        u0 = uin[i]; u1 = uin[i + 1];
-        w0 = win[i]; w1 = win[i + nx];
+        u0 = up[0]; u1 = up[1];
+        w0 = wp[0]; w1 = wp[pitch];
     }
     // viscous operator: old vector components around cells i, i+1 (x) and i, i+nx (y)
     double ua[2] = {0, 0}, ub[2] = {0, 0}, ul = 0, ur = 0;         // vx at j-nx, j+nx; i-1, i+2
@@ -68,28 +84,26 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
     unsigned mxa[2] = {0, 0}, mxb[2] = {0, 0}, mx2 = 0;            // map at i-nx+k, i+nx+k, i+2
     unsigned myl = 0, my2 = 0;                                     // map at i+nx-1, i+2nx
     if (kVisc) {
-        ua[0] = uin[i - nx]; ua[1] = uin[i - nx + 1];
-        ub[0] = uin[i + nx]; ub[1] = uin[i + nx + 1];
-        ul = uin[i - 1]; ur = uin[i + 2];
-        wa = win[i - nx]; wb = win[i + 2 * nx];
-        wl[0] = win[i - 1]; wl[1] = win[i + nx - 1];
-        wr[0] = win[i + 1]; wr[1] = win[i + nx + 1];
-        mxa[0] = mym; mxa[1] = map[i - nx + 1];
-        mxb[0] = myp; mxb[1] = map[i + nx + 1];
-        mx2 = map[i + 2];
-        myl = map[i + nx - 1]; my2 = map[i + 2 * nx];
+        ua[0] = up[-pitch]; ua[1] = up[1 - pitch];
+        ub[0] = up[pitch]; ub[1] = up[pitch + 1];
+        ul = up[-1]; ur = up[2];
+        wa = wp[-pitch]; wb = wp[2 * pitch];
+        wl[0] = wp[-1]; wl[1] = wp[pitch - 1];
+        wr[0] = wp[1]; wr[1] = wp[pitch + 1];
+        mxa[0] = mym; mxa[1] = mp[1 - pitch];
+        mxb[0] = myp; mxb[1] = mp[pitch + 1];
+        mx2 = mp[2];
+        myl = mp[pitch - 1]; my2 = mp[2 * pitch];
     }
 
-    auto tab = [&](int which, unsigned m) {
-        return __ldg(t.tab + which * kMaxMaterials + (m & kIdMask));
-    };
+    auto tab = [&](int which, unsigned m) { return tabs[which][m & kIdMask]; };
     auto ctab = [&](int which, unsigned m, long long col) {
         return __ldg(t.ctab + ((long long)which * n_mat1 + (m & kIdMask)) * nx + col);
     };
 
     // boundary operations of one cell and component: the inline constant class, else the table
     auto bound = [&](int comp, unsigned m, long long cell, double v) {
-        if (m & (kFlagBound | ((kMaxClasses - 1u) << class_shift(comp)))) {
+        if (FLAGS && (m & (kFlagBound | ((kMaxClasses - 1u) << class_shift(comp))))) {
             v = apply_class(t.cls_alpha, t.cls_value, comp, m, v);
             if (m & kFlagBound)
                 v = apply_bounds(t.bound[comp], t.rows, t.signals, t.sig_steps, a.sig_index, cell, v);
@@ -100,14 +114,14 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
     // ---- step 1: boundaries and probes of the scalar component ----------------------------------
     double *__restrict__ record = t.ring + a.ring_row * t.n_slots;
     const unsigned any = m0 | mxm | mxp | mym | myp;
-    if (any & (kFlagBound | kClassMask)) {
+    if (FLAGS && (any & (kFlagBound | kClassMask))) {
         s0 = bound(0, m0, i, s0);
         sxm = bound(0, mxm, i - 1, sxm);
         sxp = bound(0, mxp, i + 1, sxp);
         sym = bound(0, mym, i - nx, sym);
         syp = bound(0, myp, i + nx, syp);
     }
-    if (m0 & kFlagProbe) write_probes(t.probe[0], t.rows, record, i, s0);
+    if (FLAGS && (m0 & kFlagProbe)) write_probes(t.probe[0], t.rows, record, i, s0);
 
     // ---- step 2/3: x component at cells i and i+1 ------------------------------------------------
     double ux[2];
@@ -158,7 +172,7 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
         }
         ux[k] = bound(1, mj, j, v);
     }
-    if (m0 & kFlagProbe) write_probes(t.probe[1], t.rows, record, i, ux[0]);
+    if (FLAGS && (m0 & kFlagProbe)) write_probes(t.probe[1], t.rows, record, i, ux[0]);
 
     // ---- step 2/3: y component at cells i and i+nx -----------------------------------------------
     double uy[2];
@@ -198,7 +212,7 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
         }
         uy[k] = bound(2, mj, j, v);
     }
-    if (m0 & kFlagProbe) write_probes(t.probe[2], t.rows, record, i, uy[0]);
+    if (FLAGS && (m0 & kFlagProbe)) write_probes(t.probe[2], t.rows, record, i, uy[0]);
 
     // ---- step 4: scalar update, forward differences with offsets [0, +1] and [0, +nx] -----------
     double fx0, fx1, f0 = ux[0], f1 = ux[1];
@@ -219,6 +233,135 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
     if (!kThermal || a.write_vector) {
         a.out[1][i] = ux[0];
         a.out[2][i] = uy[0];
+    }
+}
+
+// Cells whose 5-point neighbourhood carries no boundary operation, class or probe (almost all) take a
+// body with every flag test compiled out.
+template <int MODEL, bool LOSSY>
+__device__ __forceinline__ void cell_update(const Step2DArgs &a, const StepTables &t, int n_mat1,
+                                            long long i, long long x, long long pitch,
+                                            const double *__restrict__ sp,
+                                            const double *__restrict__ up,
+                                            const double *__restrict__ wp,
+                                            const map_t *__restrict__ mp,
+                                            const double (*__restrict__ tabs)[kMaxMaterials]) {
+    const unsigned any = mp[0] | mp[-1] | mp[1] | mp[-pitch] | mp[pitch];
+    if (any & (kFlagBound | kFlagProbe | kClassMask))
+        cell_body<MODEL, LOSSY, true>(a, t, n_mat1, i, x, pitch, sp, up, wp, mp, tabs);
+    else
+        cell_body<MODEL, LOSSY, false>(a, t, n_mat1, i, x, pitch, sp, up, wp, mp, tabs);
+}
+
+// One thread per cell, operands straight from global memory (L1/L2 provide the neighbour reuse).
+template <int MODEL, bool LOSSY>
+__global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t, int n_mat1) {
+    __shared__ double tabs[FDS_TAB_COUNT][kMaxMaterials];
+    for (int k = threadIdx.x; k < FDS_TAB_COUNT * n_mat1; k += blockDim.x)
+        tabs[k / n_mat1][k % n_mat1] = t.tab[(k / n_mat1) * kMaxMaterials + k % n_mat1];
+    __syncthreads();
+    const long long x = (long long)blockIdx.y * blockDim.x + threadIdx.x;
+    if (x >= a.nx) return;
+    const long long i = (a.row_begin + blockIdx.x) * a.nx + x;
+    cell_update<MODEL, LOSSY>(a, t, n_mat1, i, x, a.nx, a.in[0] + i, a.in[1] + i, a.in[2] + i,
+                              t.map + i, tabs);
+}
+
+__device__ __forceinline__ unsigned tile_smem_addr(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+
+// Tile kernel: a CTA stages a (tile_h + halo rows) x 144-cell tile of every input component and of
+// the map in shared memory with bulk async copies (TMA, one mbarrier), computes the 128 x tile_h owned
+// cells from shared memory with the same `cell_update`, and takes the next tile from an atomic counter.
+// Two CTAs per SM: one computes while the other one's copies are in flight, so DRAM latency is hidden
+// by bytes in flight in shared memory instead of registers (the one-step kernel above is latency
+// bound: profiles/prof_r1_step2d_b.md). Needs nx % 8 == 0 (16-byte aligned map rows).
+template <int MODEL, bool LOSSY>
+__global__ void __launch_bounds__(kTileThreads, 2)
+tile2d_kernel(Step2DArgs a, StepTables t, int n_mat1, Tile2DArgs g) {
+    constexpr bool kThermal = (MODEL == FDS_THERMAL2D || MODEL == FDS_THERMAL3DAXI);
+    constexpr int kFields = kThermal ? 1 : 3;
+    extern __shared__ __align__(16) unsigned char tile_raw[];
+    __shared__ unsigned long long bar;
+    __shared__ int next_tile[2];
+    __shared__ double tabs[FDS_TAB_COUNT][kMaxMaterials];
+
+    const int rows = g.tile_h + g.rows_below + g.rows_above;
+    double *fs = reinterpret_cast<double *>(tile_raw);                 // [kFields][rows][pitch]
+    map_t *fm = reinterpret_cast<map_t *>(fs + (size_t)kFields * rows * kTilePitch);
+    const int tid = threadIdx.x;
+    const long long nx = a.nx;
+
+    for (int k = tid; k < FDS_TAB_COUNT * kMaxMaterials; k += kTileThreads)
+        (&tabs[0][0])[k] = t.tab[k];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(tile_smem_addr(&bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    unsigned parity = 0;
+    for (int it = 0;; ++it) {
+        if (tid == 0) next_tile[it & 1] = atomicAdd(g.counter, 1);
+        __syncthreads();                 // also: every thread is done with the previous tile
+        const int tile = next_tile[it & 1];
+        if (tile >= g.n_tiles) break;
+        const long long x0 = (long long)(tile % g.tiles_x) * kTileW;
+        const long long y0 = a.row_begin + (long long)(tile / g.tiles_x) * g.tile_h;
+
+        if (tid < 32) {
+            // generic-proxy reads of the previous tile are ordered before the async-proxy writes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (tid == 0) {
+                const unsigned bytes = (unsigned)rows * (kFields * kTilePitch * 8 + kTilePitch * 2);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                                 tile_smem_addr(&bar)),
+                             "r"(bytes)
+                             : "memory");
+            }
+            __syncwarp();
+            for (int r = tid; r < rows; r += 32) {
+                const long long base = (y0 - g.rows_below + r) * nx + x0 - kTileHaloX;
+#pragma unroll
+                for (int f = 0; f < kFields; ++f)
+                    asm volatile(
+                        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+                        "[%1], %2, [%3];" ::"r"(tile_smem_addr(fs + ((size_t)f * rows + r) * kTilePitch)),
+                        "l"(a.in[f] + base), "r"(kTilePitch * 8), "r"(tile_smem_addr(&bar))
+                        : "memory");
+                asm volatile(
+                    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], "
+                    "%2, [%3];" ::"r"(tile_smem_addr(fm + (size_t)r * kTilePitch)),
+                    "l"(t.map + base), "r"(kTilePitch * 2), "r"(tile_smem_addr(&bar))
+                    : "memory");
+            }
+        }
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "TWAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra TDONE_%=;\n"
+            "bra TWAIT_%=;\n"
+            "TDONE_%=:\n"
+            "}\n" ::"r"(tile_smem_addr(&bar)),
+            "r"(parity)
+            : "memory");
+        parity ^= 1u;
+
+        const int cells = kTileW * g.tile_h;
+        for (int k = tid; k < cells; k += kTileThreads) {
+            const int lx = k % kTileW, ly = k / kTileW;
+            const long long x = x0 + lx, row = y0 + ly;
+            if (x >= nx || row >= a.row_end) continue;
+            const size_t li = (size_t)(ly + g.rows_below) * kTilePitch + lx + kTileHaloX;
+            const double *sp = fs + li;
+            const double *up = kThermal ? sp : fs + (size_t)rows * kTilePitch + li;
+            const double *wp = kThermal ? sp : fs + (size_t)2 * rows * kTilePitch + li;
+            cell_update<MODEL, LOSSY>(a, t, n_mat1, row * nx + x, x, kTilePitch, sp, up, wp, fm + li,
+                                      tabs);
+        }
     }
 }
 

@@ -56,6 +56,7 @@ struct Stream2DArgs {
     int n_tasks;
     long long sig_index;   // first step - sig_first_step
     long long ring_row;    // probe record of the first step
+    int write_vector;      // thermal: store the flux components of the last step as well
 };
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) {
@@ -137,7 +138,10 @@ struct RowInfo {
                        // boundary operation on component c
 };
 
-template <int K>
+// THERMAL: Thermal2D (pyfds/thermal.py:92-107) -- same pipeline with the temperature as the only
+// state: the flux components are not read (q = -(A_q_t T) overwrites them, they are not accumulated)
+// and only stored when the host asks for them after the last step of a call.
+template <int K, bool THERMAL>
 __global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2DArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double tabs[4][kMaxMaterials];   // FDS_TAB_GX, GY, FX, FY
@@ -186,10 +190,12 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2D
             const long long base = r * nx + xs;         // flat cell index of the strip start
             const long long base8 = base & ~7LL;        // map entries: 16-byte aligned window
             unsigned char *dst = ring + slot * kSlotBytes;
-            mbar_expect_tx(&bars[slot], 3 * kStripCells * 8 + kMapWindowBytes);
+            mbar_expect_tx(&bars[slot], (THERMAL ? 1 : 3) * kStripCells * 8 + kMapWindowBytes);
             bulk_load(dst, a.in[0] + base, kStripCells * 8, &bars[slot]);
-            bulk_load(dst + kStripCells * 8, a.in[1] + base, kStripCells * 8, &bars[slot]);
-            bulk_load(dst + 2 * kStripCells * 8, a.in[2] + base, kStripCells * 8, &bars[slot]);
+            if (!THERMAL) {
+                bulk_load(dst + kStripCells * 8, a.in[1] + base, kStripCells * 8, &bars[slot]);
+                bulk_load(dst + 2 * kStripCells * 8, a.in[2] + base, kStripCells * 8, &bars[slot]);
+            }
             bulk_load(dst + 3 * kStripCells * 8, a.map + base8, kMapWindowBytes, &bars[slot]);
         };
         if (lane == 0)
@@ -220,6 +226,11 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2D
             double cur[3][4];
 #pragma unroll
             for (int f = 0; f < 3; ++f) {
+                if (THERMAL && f > 0) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) cur[f][c] = 0.0;
+                    continue;
+                }
                 const double2 va =
                     *reinterpret_cast<const double2 *>(src + f * kStripCells * 8 + off_a);
                 const double2 vb =
@@ -290,8 +301,10 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2D
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const double pl = c ? cur[0][c - 1] : p_left;
-                        nu[c] = sub(cur[1][c], diff2(coef.gx(c), pl, coef.gx(c + 1), cur[0][c]));
-                        nv[c] = sub(cur[2][c], diff2(coef.gyp(c), pb[s][c], coef.gyc(c), cur[0][c]));
+                        const double dx_ = diff2(coef.gx(c), pl, coef.gx(c + 1), cur[0][c]);
+                        const double dy_ = diff2(coef.gyp(c), pb[s][c], coef.gyc(c), cur[0][c]);
+                        nu[c] = THERMAL ? -dx_ : sub(cur[1][c], dx_);
+                        nv[c] = THERMAL ? -dy_ : sub(cur[2][c], dy_);
                     }
                     if (ri.classed & 2u) {
 #pragma unroll
@@ -378,6 +391,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2D
                 const long long o = cell_r - K * nx;
 #pragma unroll
                 for (int f = 0; f < 3; ++f) {
+                    if (THERMAL && f > 0 && !a.write_vector) continue;
                     *reinterpret_cast<double2 *>(a.out[f] + o) = make_double2(cur[f][0], cur[f][1]);
                     *reinterpret_cast<double2 *>(a.out[f] + o + 2) =
                         make_double2(cur[f][2], cur[f][3]);

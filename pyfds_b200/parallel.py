@@ -46,7 +46,9 @@ def stencil_reach(field):
 
 def streaming_eligible(field):
     nx = field.x.samples
-    return field._device_model == 'acoustic2d' and not is_lossy(field) and nx % 4 == 0 and nx >= 128
+    model_ok = (field._device_model == 'acoustic2d' and not is_lossy(field)) or \
+        field._device_model == 'thermal2d'
+    return model_ok and nx % 4 == 0 and nx >= 128
 
 
 def halo_rows_for(field, world, kernel=0):

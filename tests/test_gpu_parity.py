@@ -226,3 +226,26 @@ def test_streaming_kernel_step_counts_and_chunking(library, max_k, chunk, monkey
     g = _stream_case(256, 61, 13, seed=33, kernel=1)
     g.simulate(13)
     assert_same(scenarios.collect(f), scenarios.collect(g), 'K={} chunk={}'.format(max_k, chunk))
+
+
+# ---- shared-memory tile kernel vs one-step kernel --------------------------------------------------
+
+@pytest.mark.parametrize('builder,args', [
+    ('_acoustic2d', dict(lossy=True, nx=264, ny=75, steps=12, seed=51)),
+    ('_acoustic2d', dict(lossy=False, nx=136, ny=50, steps=12, seed=52, klass='Acoustic3DAxi')),
+    ('_acoustic2d', dict(lossy=True, nx=392, ny=61, steps=10, seed=53, klass='Acoustic3DAxi')),
+    ('_thermal2d', dict(klass='Thermal2D', nx=272, ny=131, steps=14, seed=54)),
+    ('_thermal2d', dict(klass='Thermal3DAxi', nx=128, ny=70, steps=14, seed=55)),
+])
+def test_tile_kernel_equals_one_step_kernel(library, builder, args, monkeypatch):
+    monkeypatch.setenv('FDS_TILE_ROWS', '9')         # several tiles in y even on small grids
+    results = []
+    for kernel in (1, 3):
+        f, steps = getattr(scenarios, builder)(fds, **args)
+        f.device_kernel = kernel
+        f.simulate(steps // 2)
+        f.simulate(steps - steps // 2)
+        results.append(scenarios.collect(f))
+        name = f.__dict__['_engine_state'].engine.last_launch_info()[2]
+        assert ('tile2d' in name) == (kernel == 3), name
+    assert_same(results[1], results[0], 'tile vs step {}'.format(args))
