@@ -143,6 +143,11 @@ int fds_upload_probes(fds_ctx *ctx, int32_t component, const int64_t *cells, con
 /* Copies n = rows * nx owned values of one component from / to host memory. */
 int fds_upload_state(fds_ctx *ctx, int32_t component, const double *values, int64_t n);
 int fds_download_state(fds_ctx *ctx, int32_t component, double *values, int64_t n);
+/* Optional: page-locks a host array that will be used repeatedly with fds_upload_state /
+ * fds_download_state (`values` arrays are updated in place by the reference, pyfds/acoustics.py:117),
+ * so that the copies run as direct DMA. The caller must unregister before the memory is freed. */
+int fds_host_register(void *host, int64_t bytes);
+int fds_host_unregister(void *host);
 /* Zeroes all components on the device (`Field.reset`, pyfds/fields.py:121-127). */
 int fds_reset_state(fds_ctx *ctx);
 

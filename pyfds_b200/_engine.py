@@ -74,6 +74,8 @@ def load_library():
         'fds_upload_probes': (ct.c_int, [p, i32, p, p, i64, i64]),
         'fds_upload_state': (ct.c_int, [p, i32, p, i64]),
         'fds_download_state': (ct.c_int, [p, i32, p, i64]),
+        'fds_host_register': (ct.c_int, [p, i64]),
+        'fds_host_unregister': (ct.c_int, [p]),
         'fds_reset_state': (ct.c_int, [p]),
         'fds_step': (ct.c_int, [p, i64, i64, p]),
         'fds_step_async': (ct.c_int, [p, i64, i64]),
@@ -235,6 +237,16 @@ def comm_unique_id():
 # host driver
 # ---------------------------------------------------------------------------------------------
 
+#: host arrays at least this large are page-locked while a field keeps using them
+PIN_THRESHOLD_BYTES = 32 << 20
+
+
+def _unregister_all(lib, pinned):
+    for _, (array, address) in list(pinned.items()):
+        lib.fds_host_unregister(ct.c_void_p(address))
+    pinned.clear()
+
+
 class _State:
     """Per-field device state; lives in ``field.__dict__['_engine_state']`` and is never pickled."""
 
@@ -242,6 +254,27 @@ class _State:
         self.engine = None
         self.epoch = -1
         self.key = None
+        # component index -> (array, address): arrays currently page-locked (the reference keeps
+        # updating the same ``values`` arrays in place, so the registration is reused call after call;
+        # holding the array keeps its memory alive until it is unregistered)
+        self.pinned = {}
+        self._finalizer = None
+
+    def pin(self, lib, index, array):
+        """Page-locks ``array`` for component ``index`` unless it already is; best effort."""
+        if array.nbytes < PIN_THRESHOLD_BYTES or not array.flags.writeable:
+            return
+        address = array.ctypes.data
+        current = self.pinned.get(index)
+        if current is not None and current[1] == address and current[0] is array:
+            return
+        if current is not None:
+            lib.fds_host_unregister(ct.c_void_p(current[1]))
+            del self.pinned[index]
+        if lib.fds_host_register(ct.c_void_p(address), array.nbytes) == 0:
+            self.pinned[index] = (array, address)
+            if self._finalizer is None:
+                self._finalizer = weakref.finalize(self, _unregister_all, lib, self.pinned)
 
 
 def _components(field):
@@ -368,8 +401,16 @@ def run(field, n_steps, progress_logger=None, advance=True):
     t1 = clock()
 
     components = _components(field)
+    state = field.__dict__['_engine_state']
+    host = []
     for c, component in enumerate(components):
-        engine.upload_state(c, _host_values(component, field.num_points))
+        values = _host_values(component, field.num_points)
+        if values is component.values:
+            state.pin(engine.lib, c, values)
+        host.append(values)
+    t1b = clock()
+    for c, values in enumerate(host):
+        engine.upload_state(c, values)
     t2 = clock()
 
     chunk = n_steps
@@ -399,7 +440,8 @@ def run(field, n_steps, progress_logger=None, advance=True):
             component.values = engine.download_state(c)
     t4 = clock()
     field.__dict__['_last_run_profile'] = {
-        'prepare_and_tables_s': t1 - t0, 'upload_state_s': t2 - t1, 'step_s': t3 - t2,
+        'prepare_and_tables_s': t1 - t0, 'page_lock_s': t1b - t1, 'upload_state_s': t2 - t1b,
+        'step_s': t3 - t2,
         'download_state_s': t4 - t3}
     if advance:
         field.step += n_steps

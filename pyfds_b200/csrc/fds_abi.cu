@@ -18,6 +18,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -122,6 +125,7 @@ struct fds_ctx {
     long long ring_half = 0;  // steps per ring half
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
+    std::vector<int> host_pslots[3];   // host copies of the probe slot lists
 
     cudaStream_t stream = nullptr, drain = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_half[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
@@ -295,6 +299,20 @@ int refresh_flags(fds_ctx *ctx) {
     }
     ctx->n_flagged = total;
     ctx->flags_dirty = false;
+    return 0;
+}
+
+
+// ---- host <-> device state copies -----------------------------------------------------------------
+// One DMA per array. NumPy arrays are pageable; the host side may page-lock the arrays it reuses
+// (fds_host_register) so that these copies run at PCIe rate instead of through the driver's bounce
+// buffers.
+int state_copy(fds_ctx *ctx, void *device, void *host, size_t bytes, bool to_device) {
+    if (to_device)
+        FDS_CUDA(ctx, cudaMemcpyAsync(device, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    else
+        FDS_CUDA(ctx, cudaMemcpyAsync(host, device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
@@ -589,10 +607,12 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
         const size_t need = (size_t)n_steps * ctx->n_slots * 8;
         if (ctx->pinned_bytes < need) {
             if (ctx->pinned) cudaFreeHost(ctx->pinned);
+
             ctx->pinned = nullptr;
             ctx->pinned_bytes = 0;
-            FDS_CUDA(ctx, cudaMallocHost(&ctx->pinned, need));
-            ctx->pinned_bytes = need;
+            const size_t alloc_bytes = std::max<size_t>(need, 1u << 20);
+            FDS_CUDA(ctx, cudaHostAlloc(&ctx->pinned, alloc_bytes, cudaHostAllocPortable));
+            ctx->pinned_bytes = alloc_bytes;
         }
     }
 
@@ -775,6 +795,42 @@ int exchange_halos(fds_ctx *ctx, int which) {
 // exported entry points
 // =================================================================================================
 
+namespace {
+// FDS_DEBUG_SEGV=1: print a native backtrace (module + offset, resolvable with addr2line) on SIGSEGV
+void segv_handler(int sig, siginfo_t *si, void *) {
+    {
+        char line[128];
+        const int len = snprintf(line, sizeof(line), "[fds segv] fault address %p\n", si->si_addr);
+        if (len > 0) (void)!write(2, line, (size_t)len);
+    }
+    void *frames[64];
+    const int n = backtrace(frames, 64);
+    for (int k = 0; k < n; ++k) {
+        Dl_info info;
+        if (dladdr(frames[k], &info) && info.dli_fname) {
+            char line[512];
+            const int len = snprintf(line, sizeof(line), "[fds segv] %s +0x%lx %s\n", info.dli_fname,
+                                     (unsigned long)((char *)frames[k] - (char *)info.dli_fbase),
+                                     info.dli_sname ? info.dli_sname : "?");
+            if (len > 0) (void)!write(2, line, (size_t)len);
+        }
+    }
+    signal(sig, SIG_DFL);
+    raise(sig);
+}
+struct SegvInstaller {
+    SegvInstaller() {
+        if (getenv("FDS_DEBUG_SEGV")) {
+            struct sigaction sa;
+            memset(&sa, 0, sizeof(sa));
+            sa.sa_sigaction = segv_handler;
+            sa.sa_flags = SA_SIGINFO;
+            sigaction(SIGSEGV, &sa, nullptr);
+        }
+    }
+} g_segv_installer;
+}  // namespace
+
 extern "C" {
 
 int fds_device_count(void) {
@@ -923,6 +979,7 @@ void fds_destroy(fds_ctx *ctx) {
     if (ctx->signals.ptr) cudaFree(ctx->signals.ptr);
     if (ctx->ring.ptr) cudaFree(ctx->ring.ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+
     cudaEvent_t events[] = {ctx->ev_half[0], ctx->ev_half[1], ctx->ev_drained[0], ctx->ev_drained[1],
                             ctx->ev_t0, ctx->ev_t1, ctx->ev_edge, ctx->ev_comm};
     for (cudaEvent_t ev : events)
@@ -1109,6 +1166,7 @@ int fds_upload_probes(fds_ctx *ctx, int32_t component, const int64_t *cells, con
     if (dev_upload(ctx, ctx->pcells[component], cells, (size_t)n * 8)) return 1;
     if (dev_upload(ctx, ctx->pslots[component], slots, (size_t)n * 4)) return 1;
     if (upload_row_ptr(ctx, ctx->prowptr[component], (const long long *)cells, n)) return 1;
+    ctx->host_pslots[component].assign(slots, slots + n);
     ctx->n_probes[component] = n;
     ctx->n_slots = n_slots_total;
     ctx->flags_dirty = true;
@@ -1120,10 +1178,8 @@ int fds_upload_state(fds_ctx *ctx, int32_t component, const double *values, int6
     if (component < 0 || component >= ctx->ncomp) return fail(ctx, "fds_upload_state: bad component");
     if (n != ctx->owned) return fail(ctx, "fds_upload_state: expected rows * nx values");
     FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
-    FDS_CUDA(ctx, cudaMemcpyAsync(origin(ctx, ctx->cur, component), values, (size_t)n * 8,
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return 0;
+    return state_copy(ctx, origin(ctx, ctx->cur, component), const_cast<double *>(values),
+                       (size_t)n * 8, true);
 }
 
 int fds_download_state(fds_ctx *ctx, int32_t component, double *values, int64_t n) {
@@ -1132,9 +1188,26 @@ int fds_download_state(fds_ctx *ctx, int32_t component, double *values, int64_t 
         return fail(ctx, "fds_download_state: bad component");
     if (n != ctx->owned) return fail(ctx, "fds_download_state: expected rows * nx values");
     FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
-    FDS_CUDA(ctx, cudaMemcpyAsync(values, origin(ctx, ctx->cur, component), (size_t)n * 8,
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return state_copy(ctx, origin(ctx, ctx->cur, component), values, (size_t)n * 8, false);
+}
+
+int fds_host_register(void *host, int64_t bytes) {
+    if (!host || bytes <= 0) return fail(nullptr, "fds_host_register: bad argument");
+    cudaError_t e = cudaHostRegister(host, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, std::string("cudaHostRegister: ") + cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+int fds_host_unregister(void *host) {
+    if (!host) return fail(nullptr, "fds_host_unregister: null pointer");
+    cudaError_t e = cudaHostUnregister(host);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, std::string("cudaHostUnregister: ") + cudaGetErrorString(e));
+    }
     return 0;
 }
 
@@ -1162,14 +1235,8 @@ int fds_step(fds_ctx *ctx, int64_t first_step, int64_t n_steps, double *probes_o
         std::vector<char> mine((size_t)ctx->n_slots, 0);
         bool all = true;
         {
-            std::vector<int> slots;
-            for (int c = 0; c < ctx->ncomp; ++c) {
-                if (!ctx->n_probes[c]) continue;
-                slots.resize((size_t)ctx->n_probes[c]);
-                FDS_CUDA(ctx, cudaMemcpy(slots.data(), ctx->pslots[c].ptr,
-                                         (size_t)ctx->n_probes[c] * 4, cudaMemcpyDeviceToHost));
-                for (int s : slots) mine[(size_t)s] = 1;
-            }
+            for (int c = 0; c < ctx->ncomp; ++c)
+                for (int s : ctx->host_pslots[c]) mine[(size_t)s] = 1;
             for (char m : mine) all = all && m;
         }
         const double *src = (const double *)ctx->pinned;
