@@ -274,6 +274,7 @@ def main():
         for name in ('pressure', 'velocity_x', 'velocity_y'):
             getattr(api_field, name).values = 1e-3 * rng.standard_normal(cells)
         api_field.simulate(args.warmup)          # includes assembly, context creation, first copies
+        first_call = dict(api_field.__dict__.get('_last_run_profile') or {})
         t0 = time.perf_counter()
         api_field.simulate(args.steps)
         seconds = time.perf_counter() - t0
@@ -282,6 +283,7 @@ def main():
                'h2d_bytes_per_step': state_bytes / args.steps,
                'd2h_bytes_per_step': (state_bytes + 4 * 8 * args.steps) / args.steps,
                'seconds': seconds, 'phases': api_field.__dict__.get('_last_run_profile'),
+               'first_call_phases': first_call,
                'what': 'field.simulate({}) from host numpy arrays: upload of p/vx/vy, boundary and '
                        'probe tables, {} steps, download of p/vx/vy and probe signals'.format(
                            args.steps, args.steps)}

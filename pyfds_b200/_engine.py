@@ -405,8 +405,10 @@ def run(field, n_steps, progress_logger=None, advance=True):
     host = []
     for c, component in enumerate(components):
         values = _host_values(component, field.num_points)
-        if values is component.values:
-            state.pin(engine.lib, c, values)
+        own = component.values
+        if isinstance(own, np.ndarray) and own.ctypes.data == values.ctypes.data and \
+                own.nbytes == values.nbytes:
+            state.pin(engine.lib, c, own)
         host.append(values)
     t1b = clock()
     for c, values in enumerate(host):

@@ -541,15 +541,19 @@ struct Plan1D {
 Plan1D plan_1d(const fds_ctx *ctx, long long steps_left) {
     Plan1D p{};
     const long long n = ctx->d.nx;
-    const int max_width = 12000;
-    if (n + 4 <= max_width) {  // the whole line in one CTA: no neighbours, any number of steps
+    if (n <= 1536) {  // a short line in one CTA: no neighbours, any number of steps per launch
         p.tile = (int)n;
         p.halo = 2;
         p.ctas = 1;
         p.steps = (int)std::min<long long>(steps_left, 1 << 20);
     } else {
+        // several CTAs, 32 steps per launch on 64-cell halos; tiles sized for a few dozen CTAs
+        // (one SM steps ~1 cell per thread and barrier; more SMs beat fewer launches)
         p.halo = 64;
-        p.tile = 4096 - 2 * p.halo;
+        long long tile = (n + 47) / 48;
+        tile = (tile + 31) / 32 * 32;
+        p.tile = (int)std::max<long long>(512, std::min<long long>(tile, 4096 - 2 * p.halo));
+        if (ctx->tile_rows > 0) p.tile = ctx->tile_rows;      // FDS_TILE_ROWS: experiments
         p.ctas = (n + p.tile - 1) / p.tile;
         p.steps = (int)std::min<long long>(steps_left, p.halo / 2);
     }
@@ -888,6 +892,7 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
         return fail(nullptr, "fds_create: the streaming kernel needs lossless Acoustic2D or Thermal2D "
                              "with nx % 4 == 0 and nx >= 128");
     }
+    if (const char *env = getenv("FDS_TILE_ROWS")) ctx->tile_rows = atoi(env);
     ctx->use_stream2d = (d.kernel == 0 || d.kernel == 2) && stream_supported(d);
     ctx->use_tile2d = !one_d && !ctx->use_stream2d && (d.kernel == 0 || d.kernel == 3) &&
                       d.nx % 8 == 0 && d.nx >= kTileW;
