@@ -170,6 +170,14 @@ int fds_comm_unique_id(uint8_t id[128]);
 /* Joins the communicator; slab `rank` exchanges halo rows with rank-1 and rank+1. */
 int fds_comm_init(fds_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t world);
 
+/* Optional fused halo path (streaming kernel): the band rows of a slab are stored straight into the
+ * neighbour slabs' halo rows over NVLink peer memory from inside the step kernel, ordered by flags in
+ * peer memory, instead of ncclSend/ncclRecv after separate band launches. fds_peer_export writes
+ * 7 CUDA IPC handles of 64 bytes (six state buffers, one flag block); every rank passes the handles of
+ * rank-1 (side 0) and rank+1 (side 1) to fds_peer_import together with that neighbour's row count. */
+int fds_peer_export(fds_ctx *ctx, uint8_t *handles);
+int fds_peer_import(fds_ctx *ctx, int32_t side, const uint8_t *handles, int64_t neighbour_rows);
+
 /* --- measurement ------------------------------------------------------------------------------ */
 
 /* Device time in milliseconds of the step kernels launched by the last fds_step/fds_step_async call,

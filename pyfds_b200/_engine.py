@@ -82,6 +82,8 @@ def load_library():
         'fds_sync': (ct.c_int, [p]),
         'fds_comm_unique_id': (ct.c_int, [p]),
         'fds_comm_init': (ct.c_int, [p, p, i32, i32]),
+        'fds_peer_export': (ct.c_int, [p, p]),
+        'fds_peer_import': (ct.c_int, [p, i32, p, i64]),
         'fds_last_step_ms': (ct.c_int, [p, dptr]),
         'fds_last_launch_info': (ct.c_int, [p, ct.POINTER(i64), ct.POINTER(i64),
                                             ct.POINTER(ct.c_char_p)]),
@@ -219,6 +221,15 @@ class Engine:
 
     def device_bytes(self):
         return self.lib.fds_device_bytes(self.handle)
+
+    def peer_export(self):
+        buf = (ct.c_uint8 * (7 * 64))()
+        self._check(self.lib.fds_peer_export(self.handle, buf))
+        return bytes(buf)
+
+    def peer_import(self, side, handles, neighbour_rows):
+        buf = (ct.c_uint8 * (7 * 64)).from_buffer_copy(bytes(handles))
+        self._check(self.lib.fds_peer_import(self.handle, side, buf, neighbour_rows))
 
     def comm_init(self, unique_id, rank, world):
         buf = (ct.c_uint8 * 128).from_buffer_copy(bytes(unique_id))

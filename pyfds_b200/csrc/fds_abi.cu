@@ -139,6 +139,14 @@ struct fds_ctx {
     ncclComm *comm = nullptr;
     int rank = 0, world = 1;
 
+    // peer-memory halo path of the streaming kernel (multi-GPU): neighbours' buffers opened over IPC
+    unsigned *flags = nullptr;           // [0],[1]: halo-arrival flags written by the lower / upper
+                                         // neighbour; [2],[3]: counters of finished band tasks
+    void *peer_base[2][2][3] = {};       // [side][buffer][component] base pointers (IPC mappings)
+    unsigned *peer_flags[2] = {nullptr, nullptr};
+    long long peer_rows[2] = {0, 0};
+    bool peer_open[2] = {false, false};
+    unsigned launch_seq = 0;
     bool use_stream2d = false; // streaming multi-step kernel selected
     bool use_tile2d = false;   // shared-memory tile kernel selected (one step per launch)
     StepTables *d_tables = nullptr;   // device copy of the tables for the streaming kernel's slow path
@@ -463,9 +471,9 @@ int stream_chunk_rows(const fds_ctx *ctx, long long rows, int n_strips, int k) {
     return (int)best;
 }
 
-template <int K, bool THERMAL>
+template <int K, bool THERMAL, bool PEER>
 int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
-    auto kernel = stream2d_kernel<K, THERMAL>;
+    auto kernel = stream2d_kernel<K, THERMAL, PEER>;
     const int smem = kStreamWarps * kWarpRingBytes;
     static bool configured = false;
     if (!configured) {
@@ -481,11 +489,12 @@ int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
 }
 
 int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
-    const long long rows = a.row_end - a.row_begin;
-    if (rows <= 0) return 0;
+    const long long rows = a.row_end - a.row_begin - 2 * (long long)a.band_rows;   // interior rows
+    if (a.row_end - a.row_begin <= 0) return 0;
     a.n_strips = (int)((a.nx + kStripStride - 1) / kStripStride);
-    a.chunk_rows = stream_chunk_rows(ctx, rows, a.n_strips, k);
-    a.n_tasks = (int)(a.n_strips * ((rows + a.chunk_rows - 1) / a.chunk_rows));
+    a.chunk_rows = stream_chunk_rows(ctx, std::max<long long>(rows, 1), a.n_strips, k);
+    a.n_tasks = (int)(a.n_strips * ((std::max<long long>(rows, 0) + a.chunk_rows - 1) / a.chunk_rows));
+    if (a.band_rows > 0) a.n_tasks += 2 * a.n_strips;
     if (ctx->n_strips_ordered != a.n_strips) {
         // strips that carry boundary cells (slow path) are handed out first (longest task first)
         std::vector<long long> weight((size_t)a.n_strips, 0);
@@ -507,27 +516,27 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
         ctx->n_strips_ordered = a.n_strips;
     }
     a.strip_order = (const int *)ctx->strip_order.ptr;
-    a.n_chunks = (int)((rows + a.chunk_rows - 1) / a.chunk_rows);
+    a.n_chunks = std::max(1, (int)((rows + a.chunk_rows - 1) / a.chunk_rows));
     a.task_counter = next_counter(ctx);
     if (!a.task_counter) return fail(ctx, "stream2d: counter reset failed");
     a.map = ctx->map + ctx->pad + ctx->halo;
     a.tab = ctx->tab;
     a.tables = ctx->d_tables;
-    if (ctx->thermal) {
-        switch (k) {
-            case 1: return launch_stream2d<1, true>(ctx, a);
-            case 2: return launch_stream2d<2, true>(ctx, a);
-            case 3: return launch_stream2d<3, true>(ctx, a);
-            case 4: return launch_stream2d<4, true>(ctx, a);
-        }
-    } else {
-        switch (k) {
-            case 1: return launch_stream2d<1, false>(ctx, a);
-            case 2: return launch_stream2d<2, false>(ctx, a);
-            case 3: return launch_stream2d<3, false>(ctx, a);
-            case 4: return launch_stream2d<4, false>(ctx, a);
-        }
+    const bool peer = a.band_rows > 0;
+#define FDS_STREAM_CASE(K_)                                                                  \
+    case K_:                                                                                 \
+        if (ctx->thermal)                                                                    \
+            return peer ? launch_stream2d<K_, true, true>(ctx, a)                            \
+                        : launch_stream2d<K_, true, false>(ctx, a);                          \
+        return peer ? launch_stream2d<K_, false, true>(ctx, a)                               \
+                    : launch_stream2d<K_, false, false>(ctx, a);
+    switch (k) {
+        FDS_STREAM_CASE(1)
+        FDS_STREAM_CASE(2)
+        FDS_STREAM_CASE(3)
+        FDS_STREAM_CASE(4)
     }
+#undef FDS_STREAM_CASE
     return fail(ctx, "stream2d: bad step count");
 }
 
@@ -689,7 +698,35 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 if (multi) k = std::min<int>(k, ctx->d.halo_rows);
                 // thermal fluxes are derived data: stored only by the launch that ends the call
                 a.write_vector = (s + k == n_steps);
-                if (multi) {
+                const bool peer = multi && (ctx->rank == 0 || ctx->peer_open[0]) &&
+                                  (ctx->rank == ctx->world - 1 || ctx->peer_open[1]) &&
+                                  rows >= 3ll * ctx->d.halo_rows && !getenv("FDS_NO_PEER");
+                if (peer) {
+                    // one launch: band rows go to the neighbours' halos over NVLink from inside the
+                    // kernel, flags in peer memory order the launches of adjacent slabs
+                    const long long nx = ctx->d.nx;
+                    a.row_begin = 0; a.row_end = rows;
+                    a.band_rows = ctx->d.halo_rows;
+                    a.launch_id = ++ctx->launch_seq;
+                    a.wait_halos = (in_chunk > 0 || chunk > 0) ? 1 : 0;
+                    a.band_done = ctx->flags + 2;
+                    const long long off = ctx->pad + ctx->halo;
+                    for (int side = 0; side < 2; ++side) {
+                        const bool has = side == 0 ? ctx->rank > 0 : ctx->rank < ctx->world - 1;
+                        a.flag_in[side] = has ? ctx->flags + side : nullptr;
+                        a.flag_out[side] = has ? ctx->peer_flags[side] + (1 - side) : nullptr;
+                        for (int c = 0; c < 3; ++c) {
+                            double *base = has ? (double *)ctx->peer_base[side][ctx->cur ^ 1][c] : nullptr;
+                            // pre-offset: my local cell index addresses the neighbour's halo row
+                            a.peer_out[side][c] =
+                                !has ? nullptr
+                                     : side == 0 ? base + off + ctx->peer_rows[0] * nx
+                                                 : base + off - rows * nx;
+                        }
+                    }
+                    if (dispatch_stream2d(ctx, a, k)) return 1;
+                    ctx->last_launches += 1;
+                } else if (multi) {
                     // the k outermost rows of either side travel while the interior is computed
                     const long long band = std::min<long long>(ctx->d.halo_rows, rows);
                     a.row_begin = 0; a.row_end = band;
@@ -945,6 +982,7 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
                           sizeof(double) * FDS_CTAB_COUNT * (d.n_materials + 1) * d.nx, true));
         FDS_TRY(dev_alloc(ctx, (void **)&ctx->cvec, sizeof(double) * FDS_CVEC_COUNT * d.nx, true));
     }
+    FDS_TRY(dev_alloc(ctx, (void **)&ctx->flags, 4 * sizeof(unsigned), true));
     FDS_TRY(dev_alloc(ctx, (void **)&ctx->d_tables, sizeof(StepTables), true));
     FDS_TRY(dev_alloc(ctx, (void **)&ctx->task_counters, sizeof(int) * kCounterPool, true));
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -970,6 +1008,14 @@ void fds_destroy(fds_ctx *ctx) {
     if (ctx->tab) cudaFree(ctx->tab);
     if (ctx->ctab) cudaFree(ctx->ctab);
     if (ctx->cvec) cudaFree(ctx->cvec);
+    for (int side = 0; side < 2; ++side) {
+        if (!ctx->peer_open[side]) continue;
+        for (int b = 0; b < 2; ++b)
+            for (int c = 0; c < 3; ++c)
+                if (ctx->peer_base[side][b][c]) cudaIpcCloseMemHandle(ctx->peer_base[side][b][c]);
+        if (ctx->peer_flags[side]) cudaIpcCloseMemHandle(ctx->peer_flags[side]);
+    }
+    if (ctx->flags) cudaFree(ctx->flags);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->task_counters) cudaFree(ctx->task_counters);
     for (int c = 0; c < 3; ++c) {
@@ -1292,6 +1338,48 @@ int fds_comm_init(fds_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t wor
     FDS_NCCL(ctx, g_nccl.CommInitRank(&ctx->comm, world, uid, rank));
     ctx->rank = rank;
     ctx->world = world;
+    return 0;
+}
+
+int fds_peer_export(fds_ctx *ctx, uint8_t *handles) {
+    if (!ctx || !handles) return fail(ctx, "fds_peer_export: null argument");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    int at = 0;
+    for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 3; ++c, ++at) {
+            cudaIpcMemHandle_t h;
+            memset(&h, 0, sizeof(h));
+            if (ctx->buf[b][c]) FDS_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->buf[b][c]));
+            memcpy(handles + 64 * at, &h, 64);
+        }
+    cudaIpcMemHandle_t h;
+    FDS_CUDA(ctx, cudaIpcGetMemHandle(&h, ctx->flags));
+    memcpy(handles + 64 * at, &h, 64);
+    return 0;
+}
+
+int fds_peer_import(fds_ctx *ctx, int32_t side, const uint8_t *handles, int64_t neighbour_rows) {
+    if (!ctx || !handles) return fail(ctx, "fds_peer_import: null argument");
+    if (side < 0 || side > 1) return fail(ctx, "fds_peer_import: side must be 0 (lower) or 1 (upper)");
+    if (ctx->peer_open[side]) return fail(ctx, "fds_peer_import: side already imported");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    int at = 0;
+    for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 3; ++c, ++at) {
+            if (!ctx->buf[b][c]) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + 64 * at, 64);
+            FDS_CUDA(ctx, cudaIpcOpenMemHandle(&ctx->peer_base[side][b][c], h,
+                                               cudaIpcMemLazyEnablePeerAccess));
+        }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * at, 64);
+    void *flags = nullptr;
+    FDS_CUDA(ctx, cudaIpcOpenMemHandle(&flags, h, cudaIpcMemLazyEnablePeerAccess));
+    ctx->peer_flags[side] = (unsigned *)flags;
+    ctx->peer_rows[side] = neighbour_rows;
+    ctx->peer_open[side] = true;
     return 0;
 }
 

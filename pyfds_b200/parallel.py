@@ -95,6 +95,26 @@ class SlabRun:
             if unique_id is None:
                 unique_id = _broadcast_unique_id(rank)
             self.engine.comm_init(unique_id, rank, world)
+            self._open_peers()
+
+    def _open_peers(self):
+        """Maps the neighbour slabs' state buffers (CUDA IPC) so that the streaming kernel can store
+        its band rows straight into their halo rows over NVLink. Best effort: without it (no peer
+        access, other kernels) the halo rows travel by ncclSend/ncclRecv."""
+        import os
+        import torch.distributed as dist
+        if os.environ.get('FDS_NO_PEER') or not streaming_eligible(self.field):
+            return
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self.engine.peer_export())
+        parts = partition_rows(self.field.y.samples, self.world)
+        try:
+            if self.rank > 0:
+                self.engine.peer_import(0, handles[self.rank - 1], parts[self.rank - 1][1])
+            if self.rank < self.world - 1:
+                self.engine.peer_import(1, handles[self.rank + 1], parts[self.rank + 1][1])
+        except _engine.EngineError:
+            pass
 
     @property
     def cells(self):
