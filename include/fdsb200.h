@@ -170,9 +170,10 @@ int fds_comm_unique_id(uint8_t id[128]);
 /* Joins the communicator; slab `rank` exchanges halo rows with rank-1 and rank+1. */
 int fds_comm_init(fds_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t world);
 
-/* Optional fused halo path (streaming kernel): the band rows of a slab are stored straight into the
- * neighbour slabs' halo rows over NVLink peer memory from inside the step kernel, ordered by flags in
- * peer memory, instead of ncclSend/ncclRecv after separate band launches. fds_peer_export writes
+/* Optional peer-memory halo path: after every launch the outermost rows of a slab are copied straight
+ * into the neighbour slabs' halo rows over NVLink (their buffers are mapped through CUDA IPC) and the
+ * launches of adjacent slabs are ordered by flags in peer memory -- no ncclSend/ncclRecv, no separate
+ * band launches, no host involvement in the time loop. fds_peer_export writes
  * 7 CUDA IPC handles of 64 bytes (six state buffers, one flag block); every rank passes the handles of
  * rank-1 (side 0) and rank+1 (side 1) to fds_peer_import together with that neighbour's row count. */
 int fds_peer_export(fds_ctx *ctx, uint8_t *handles);

@@ -471,9 +471,9 @@ int stream_chunk_rows(const fds_ctx *ctx, long long rows, int n_strips, int k) {
     return (int)best;
 }
 
-template <int K, bool THERMAL, bool PEER>
+template <int K, bool THERMAL>
 int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
-    auto kernel = stream2d_kernel<K, THERMAL, PEER>;
+    auto kernel = stream2d_kernel<K, THERMAL>;
     const int smem = kStreamWarps * kWarpRingBytes;
     static bool configured = false;
     if (!configured) {
@@ -489,12 +489,11 @@ int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
 }
 
 int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
-    const long long rows = a.row_end - a.row_begin - 2 * (long long)a.band_rows;   // interior rows
-    if (a.row_end - a.row_begin <= 0) return 0;
+    const long long rows = a.row_end - a.row_begin;
+    if (rows <= 0) return 0;
     a.n_strips = (int)((a.nx + kStripStride - 1) / kStripStride);
-    a.chunk_rows = stream_chunk_rows(ctx, std::max<long long>(rows, 1), a.n_strips, k);
-    a.n_tasks = (int)(a.n_strips * ((std::max<long long>(rows, 0) + a.chunk_rows - 1) / a.chunk_rows));
-    if (a.band_rows > 0) a.n_tasks += 2 * a.n_strips;
+    a.chunk_rows = stream_chunk_rows(ctx, rows, a.n_strips, k);
+    a.n_tasks = (int)(a.n_strips * ((rows + a.chunk_rows - 1) / a.chunk_rows));
     if (ctx->n_strips_ordered != a.n_strips) {
         // strips that carry boundary cells (slow path) are handed out first (longest task first)
         std::vector<long long> weight((size_t)a.n_strips, 0);
@@ -516,20 +515,15 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
         ctx->n_strips_ordered = a.n_strips;
     }
     a.strip_order = (const int *)ctx->strip_order.ptr;
-    a.n_chunks = std::max(1, (int)((rows + a.chunk_rows - 1) / a.chunk_rows));
+    a.n_chunks = (int)((rows + a.chunk_rows - 1) / a.chunk_rows);
     a.task_counter = next_counter(ctx);
     if (!a.task_counter) return fail(ctx, "stream2d: counter reset failed");
     a.map = ctx->map + ctx->pad + ctx->halo;
     a.tab = ctx->tab;
     a.tables = ctx->d_tables;
-    const bool peer = a.band_rows > 0;
 #define FDS_STREAM_CASE(K_)                                                                  \
     case K_:                                                                                 \
-        if (ctx->thermal)                                                                    \
-            return peer ? launch_stream2d<K_, true, true>(ctx, a)                            \
-                        : launch_stream2d<K_, true, false>(ctx, a);                          \
-        return peer ? launch_stream2d<K_, false, true>(ctx, a)                               \
-                    : launch_stream2d<K_, false, false>(ctx, a);
+        return ctx->thermal ? launch_stream2d<K_, true>(ctx, a) : launch_stream2d<K_, false>(ctx, a);
     switch (k) {
         FDS_STREAM_CASE(1)
         FDS_STREAM_CASE(2)
@@ -601,6 +595,63 @@ int ensure_ring(fds_ctx *ctx, long long n_steps) {
         ctx->ring.bytes = bytes;
     }
     ctx->ring_half = half;
+    return 0;
+}
+
+// ---- peer-memory halo path ------------------------------------------------------------------------
+bool peers_ready(const fds_ctx *ctx) {
+    if (getenv("FDS_NO_PEER")) return false;
+    if (ctx->rank > 0 && !ctx->peer_open[0]) return false;
+    if (ctx->rank < ctx->world - 1 && !ctx->peer_open[1]) return false;
+    // double2 copies: rows must start on 16-byte boundaries
+    return ctx->d.rows >= ctx->d.halo_rows && ctx->d.nx % 2 == 0;
+}
+
+// Before launch L: the neighbours' rows of launch L-1 must have landed in my halo rows. The first
+// launch of a call is covered by the host-driven exchange at the start of run_steps.
+int peer_wait(fds_ctx *ctx, bool wait) {
+    ++ctx->launch_seq;
+    if (!wait) return 0;
+    const unsigned *lo = ctx->rank > 0 ? ctx->flags + 0 : nullptr;
+    const unsigned *hi = ctx->rank < ctx->world - 1 ? ctx->flags + 1 : nullptr;
+    halo_wait_kernel<<<1, 1, 0, ctx->stream>>>(lo, hi, ctx->launch_seq - 1);
+    FDS_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+// After launch L: my outermost halo_rows rows of buffer `which` go into the neighbours' halo rows of
+// the same buffer, then their flags are released with L.
+int peer_push(fds_ctx *ctx, int which) {
+    const long long nx = ctx->d.nx, h = ctx->d.halo_rows, rows = ctx->d.rows;
+    const long long off = ctx->pad + ctx->halo;
+    const int ncomp = ctx->thermal ? 1 : 3;
+    HaloPushArgs p{};
+    p.count = h * nx;
+    p.launch_id = ctx->launch_seq;
+    p.blocks_done = ctx->flags + 2;
+    int seg = 0;
+    for (int side = 0; side < 2; ++side) {
+        const bool has = side == 0 ? ctx->rank > 0 : ctx->rank < ctx->world - 1;
+        p.flag_out[side] = has ? ctx->peer_flags[side] + (1 - side) : nullptr;
+        if (!has) continue;
+        for (int c = 0; c < ncomp; ++c, ++seg) {
+            double *mine = origin(ctx, which, c);
+            double *theirs = (double *)ctx->peer_base[side][which][c] + off;
+            if (side == 0) {   // my bottom rows -> lower neighbour's upper halo
+                p.src[seg] = mine;
+                p.dst[seg] = theirs + ctx->peer_rows[0] * nx;
+            } else {           // my top rows -> upper neighbour's lower halo
+                p.src[seg] = mine + (rows - h) * nx;
+                p.dst[seg] = theirs - h * nx;
+            }
+        }
+    }
+    p.n_segments = seg;
+    if (seg == 0) return 0;
+    if (p.count % 2) return fail(ctx, "peer_push: odd halo size");
+    const int blocks = (int)std::min<long long>(32, (p.count / 2 + 255) / 256);
+    halo_push_kernel<<<dim3((unsigned)blocks, (unsigned)seg), 256, 0, ctx->stream>>>(p);
+    FDS_CUDA(ctx, cudaGetLastError());
     return 0;
 }
 
@@ -698,33 +749,12 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 if (multi) k = std::min<int>(k, ctx->d.halo_rows);
                 // thermal fluxes are derived data: stored only by the launch that ends the call
                 a.write_vector = (s + k == n_steps);
-                const bool peer = multi && (ctx->rank == 0 || ctx->peer_open[0]) &&
-                                  (ctx->rank == ctx->world - 1 || ctx->peer_open[1]) &&
-                                  rows >= 3ll * ctx->d.halo_rows && !getenv("FDS_NO_PEER");
-                if (peer) {
-                    // one launch: band rows go to the neighbours' halos over NVLink from inside the
-                    // kernel, flags in peer memory order the launches of adjacent slabs
-                    const long long nx = ctx->d.nx;
+                if (multi && peers_ready(ctx)) {
+                    // one launch for the whole slab; halo rows travel over NVLink peer memory
+                    if (peer_wait(ctx, in_chunk > 0 || chunk > 0)) return 1;
                     a.row_begin = 0; a.row_end = rows;
-                    a.band_rows = ctx->d.halo_rows;
-                    a.launch_id = ++ctx->launch_seq;
-                    a.wait_halos = (in_chunk > 0 || chunk > 0) ? 1 : 0;
-                    a.band_done = ctx->flags + 2;
-                    const long long off = ctx->pad + ctx->halo;
-                    for (int side = 0; side < 2; ++side) {
-                        const bool has = side == 0 ? ctx->rank > 0 : ctx->rank < ctx->world - 1;
-                        a.flag_in[side] = has ? ctx->flags + side : nullptr;
-                        a.flag_out[side] = has ? ctx->peer_flags[side] + (1 - side) : nullptr;
-                        for (int c = 0; c < 3; ++c) {
-                            double *base = has ? (double *)ctx->peer_base[side][ctx->cur ^ 1][c] : nullptr;
-                            // pre-offset: my local cell index addresses the neighbour's halo row
-                            a.peer_out[side][c] =
-                                !has ? nullptr
-                                     : side == 0 ? base + off + ctx->peer_rows[0] * nx
-                                                 : base + off - rows * nx;
-                        }
-                    }
                     if (dispatch_stream2d(ctx, a, k)) return 1;
+                    if (peer_push(ctx, ctx->cur ^ 1)) return 1;
                     ctx->last_launches += 1;
                 } else if (multi) {
                     // the k outermost rows of either side travel while the interior is computed
@@ -762,7 +792,13 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 // thermal fluxes are derived data: store them only with the last step of the call
                 a.write_vector = (s == n_steps - 1);
                 const long long rows = ctx->d.rows;
-                if (ctx->comm && ctx->world > 1) {
+                if (ctx->comm && ctx->world > 1 && peers_ready(ctx)) {
+                    if (peer_wait(ctx, in_chunk > 0 || chunk > 0)) return 1;
+                    a.row_begin = 0; a.row_end = rows;
+                    if (dispatch_step2d(ctx, a, t)) return 1;
+                    if (peer_push(ctx, ctx->cur ^ 1)) return 1;
+                    ctx->last_launches += 1;
+                } else if (ctx->comm && ctx->world > 1) {
                     // edge bands first, so that their rows can travel while the interior computes
                     const long long band = std::min<long long>(ctx->d.halo_rows, rows);
                     a.row_begin = 0; a.row_end = band;

@@ -149,4 +149,58 @@ __device__ __noinline__ void write_probes(const ProbeTable t, const RowIndex ri,
     for (; k < hi && __ldg(t.cells + k) == cell; ++k) record[__ldg(t.slots + k)] = v;
 }
 
+// ---- multi-GPU halo rows over NVLink peer memory ----------------------------------------------------
+// After every launch the outermost `halo` rows of a slab are copied straight into the halo rows of the
+// neighbour slabs (their buffers are mapped through CUDA IPC) and a flag in the neighbour's memory is
+// released with the launch number; before the next launch a one-thread kernel waits for the flags the
+// neighbours wrote. No host involvement, no NCCL call in the time loop.
+struct HaloPushArgs {
+    const double *src[6];    // up to 2 sides x 3 components
+    double *dst[6];
+    long long count;         // doubles per segment (multiple of 2)
+    int n_segments;
+    unsigned *flag_out[2];   // neighbours' flags (peer memory), nullptr if there is no neighbour
+    unsigned launch_id;
+    unsigned *blocks_done;   // zero before the launch; reset by the last block
+};
+
+__global__ void halo_push_kernel(HaloPushArgs a) {
+    const int seg = blockIdx.y;
+    const double2 *__restrict__ src = reinterpret_cast<const double2 *>(a.src[seg]);
+    double2 *__restrict__ dst = reinterpret_cast<double2 *>(a.dst[seg]);
+    const long long n2 = a.count / 2;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n2;
+         k += (long long)gridDim.x * blockDim.x)
+        dst[k] = src[k];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y;
+        if (atomicAdd(a.blocks_done, 1u) == total - 1u) {
+            *a.blocks_done = 0u;
+            __threadfence_system();
+            for (int side = 0; side < 2; ++side)
+                if (a.flag_out[side])
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_out[side]),
+                                 "r"(a.launch_id)
+                                 : "memory");
+        }
+    }
+}
+
+__global__ void halo_wait_kernel(const unsigned *flag_lo, const unsigned *flag_hi, unsigned want) {
+    const unsigned *flags[2] = {flag_lo, flag_hi};
+    for (int side = 0; side < 2; ++side) {
+        if (!flags[side]) continue;
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];"
+                         : "=r"(seen)
+                         : "l"(flags[side])
+                         : "memory");
+            if ((int)(seen - want) < 0) __nanosleep(100);
+        } while ((int)(seen - want) < 0);
+    }
+}
+
 }  // namespace fds

@@ -57,20 +57,6 @@ struct Stream2DArgs {
     long long sig_index;   // first step - sig_first_step
     long long ring_row;    // probe record of the first step
     int write_vector;      // thermal: store the flux components of the last step as well
-    // ---- multi-GPU: halo rows over NVLink peer memory, fused into this kernel ------------------
-    // The first 2 * n_strips tasks are the bottom band (rows [row_begin, row_begin + band_rows)) and
-    // the top band (rows [row_end - band_rows, row_end)); everything else is chunked as usual. A band
-    // task first waits until the neighbour slab has delivered the halo rows of this launch (flag_in),
-    // stores its output rows ALSO into the neighbour's halo (peer_out, pre-offset so that the local
-    // cell index addresses it) and, when the last task of a band is done, releases the neighbour's
-    // flag with the launch number. band_rows == 0: single-GPU launch.
-    int band_rows;
-    double *peer_out[2][3];      // [0] lower neighbour (bottom band rows), [1] upper neighbour
-    const unsigned *flag_in[2];  // my flags: written by the lower / upper neighbour
-    unsigned *flag_out[2];       // the neighbours' flags for me (peer memory)
-    unsigned *band_done;         // [2] monotonic counters of finished band tasks
-    unsigned launch_id;          // number of this launch (same on all ranks)
-    int wait_halos;              // 0 for the first launch of a call (halos came by the host exchange)
 };
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) {
@@ -155,9 +141,7 @@ struct RowInfo {
 // THERMAL: Thermal2D (pyfds/thermal.py:92-107) -- same pipeline with the temperature as the only
 // state: the flux components are not read (q = -(A_q_t T) overwrites them, they are not accumulated)
 // and only stored when the host asks for them after the last step of a call.
-// PEER: compiled with the multi-GPU band / peer-memory logic (kept out of the single-GPU kernel to
-// save registers).
-template <int K, bool THERMAL, bool PEER>
+template <int K, bool THERMAL>
 __global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2DArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double tabs[4][kMaxMaterials];   // FDS_TAB_GX, GY, FX, FY
@@ -195,37 +179,10 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2D
         if (lane == 0) task = atomicAdd(a.task_counter, 1);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= a.n_tasks) break;
-        int strip, band = -1;                       // band: 0 bottom, 1 top, -1 interior
-        long long ys, ye;
-        const int n_band_tasks = (PEER && a.band_rows > 0) ? 2 * a.n_strips : 0;
-        if (PEER && task < n_band_tasks) {
-            band = task / a.n_strips;
-            strip = __ldg(a.strip_order + task % a.n_strips);
-            ys = band == 0 ? a.row_begin : a.row_end - a.band_rows;
-            ye = ys + a.band_rows;
-            if (a.wait_halos && a.flag_in[band]) {
-                // the neighbour's band of the previous launch must have landed in my halo rows
-                if (lane == 0) {
-                    const unsigned want = a.launch_id - 1;
-                    unsigned seen;
-                    do {
-                        asm volatile("ld.acquire.sys.global.u32 %0, [%1];"
-                                     : "=r"(seen)
-                                     : "l"(a.flag_in[band])
-                                     : "memory");
-                        if ((int)(seen - want) < 0) __nanosleep(200);
-                    } while ((int)(seen - want) < 0);
-                }
-                __syncwarp();
-            }
-        } else {
-            const int t2 = task - n_band_tasks;
-            strip = __ldg(a.strip_order + t2 / a.n_chunks);
-            const long long lo = a.row_begin + (PEER ? a.band_rows : 0);
-            const long long hi = a.row_end - (PEER ? a.band_rows : 0);
-            ys = lo + (long long)(t2 % a.n_chunks) * a.chunk_rows;
-            ye = min(ys + (long long)a.chunk_rows, hi);
-        }
+        const int strip = __ldg(a.strip_order + task / a.n_chunks);
+        const long long chunk = task % a.n_chunks;
+        const long long ys = a.row_begin + chunk * a.chunk_rows;
+        const long long ye = min(ys + (long long)a.chunk_rows, a.row_end);
         const long long xs = (long long)strip * kStripStride - kStripHalo;   // column of lane 0
         const long long r0 = ys - K, r1 = ye + K;                            // rows streamed in
 
@@ -439,33 +396,8 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2D
                     *reinterpret_cast<double2 *>(a.out[f] + o + 2) =
                         make_double2(cur[f][2], cur[f][3]);
                 }
-                if (PEER && band >= 0 && a.peer_out[band][0]) {
-                    // the same rows, straight into the neighbour slab's halo over NVLink
-#pragma unroll
-                    for (int f = 0; f < (THERMAL ? 1 : 3); ++f) {
-                        *reinterpret_cast<double2 *>(a.peer_out[band][f] + o) =
-                            make_double2(cur[f][0], cur[f][1]);
-                        *reinterpret_cast<double2 *>(a.peer_out[band][f] + o + 2) =
-                            make_double2(cur[f][2], cur[f][3]);
-                    }
-                }
             }
             cell_r += nx;
-        }
-        if (PEER && band >= 0 && a.flag_out[band]) {
-            // all peer stores of this task are visible system-wide before the band counter moves;
-            // the task that completes the band publishes the launch number to the neighbour
-            __threadfence_system();
-            __syncwarp();
-            if (lane == 0) {
-                const unsigned done = atomicAdd(a.band_done + band, 1u) + 1u;
-                if (done % (unsigned)a.n_strips == 0u) {
-                    __threadfence_system();
-                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.flag_out[band]),
-                                 "r"(a.launch_id)
-                                 : "memory");
-                }
-            }
         }
     }
 }

@@ -98,12 +98,12 @@ class SlabRun:
             self._open_peers()
 
     def _open_peers(self):
-        """Maps the neighbour slabs' state buffers (CUDA IPC) so that the streaming kernel can store
-        its band rows straight into their halo rows over NVLink. Best effort: without it (no peer
-        access, other kernels) the halo rows travel by ncclSend/ncclRecv."""
+        """Maps the neighbour slabs' state buffers (CUDA IPC) so that halo rows are copied straight
+        into the neighbours' memory over NVLink by a small kernel after every launch, ordered by flags
+        in peer memory. Best effort: without peer access the rows travel by ncclSend/ncclRecv."""
         import os
         import torch.distributed as dist
-        if os.environ.get('FDS_NO_PEER') or not streaming_eligible(self.field):
+        if os.environ.get('FDS_NO_PEER'):
             return
         handles = [None] * self.world
         dist.all_gather_object(handles, self.engine.peer_export())
