@@ -207,7 +207,7 @@ def main():
         return
 
     import pyfds_b200 as fds
-    from pyfds_b200 import _engine
+    from pyfds_b200 import _engine, parallel
 
     dist = None
     if world > 1:
@@ -224,7 +224,6 @@ def main():
 
     # ---- device-resident run --------------------------------------------------------------------
     if world > 1:
-        from pyfds_b200 import parallel
         run = parallel.SlabRun(field, rank, world, device=local_rank, kernel=args.kernel)
         engine = run.engine
     else:
@@ -260,33 +259,50 @@ def main():
         device_ms = float(t.item())
 
     cells = nx * ny
+    per_gpu_cells = nx * rows
     value = cells * args.steps / (device_ms * 1e-3) / 1e9
     peak, peak_source = measured_peak()
-    per_gpu_cells = nx * rows
     step_launches = launches / (3 if world > 1 else 1)
     launch_ms = device_ms / max(step_launches, 1)
     achieved = BYTES_PER_CELL_UPDATE * per_gpu_cells * steps_per_launch / (launch_ms * 1e-3) / 1e9
 
     # ---- end to end through the public API (host arrays in and out) -----------------------------
     e2e = None
-    if not args.no_e2e and world == 1:
-        api_field = build_field(fds, nx, ny, total_steps + 1)
+    if not args.no_e2e:
+        api_field = build_field(fds, nx, ny, total_steps + 1, wall=not args.no_wall)
         for name in ('pressure', 'velocity_x', 'velocity_y'):
-            getattr(api_field, name).values = 1e-3 * rng.standard_normal(cells)
-        api_field.simulate(args.warmup)          # includes assembly, context creation, first copies
+            values = getattr(api_field, name).values
+            if world == 1:
+                values[:] = 1e-3 * rng.standard_normal(cells)
+            else:   # only the rows this rank owns are ever read
+                values[rank * per_gpu_cells:(rank + 1) * per_gpu_cells] = \
+                    1e-3 * rng.standard_normal(per_gpu_cells)
+        api_field.device_kernel = args.kernel
+        if world == 1:
+            runner = api_field
+        else:
+            # drop the device-resident context first: one communicator / IPC mapping set per rank
+            del run, engine
+            runner = parallel.SlabRun(api_field, rank, world, device=local_rank, kernel=args.kernel)
+        runner.simulate(args.warmup)             # includes assembly, context creation, first copies
         first_call = dict(api_field.__dict__.get('_last_run_profile') or {})
+        if dist is not None:
+            dist.barrier()
         t0 = time.perf_counter()
-        api_field.simulate(args.steps)
+        runner.simulate(args.steps)
+        if dist is not None:
+            dist.barrier()
         seconds = time.perf_counter() - t0
-        state_bytes = 3 * cells * 8
+        state_bytes = 3 * per_gpu_cells * 8
         e2e = {'value': cells * args.steps / seconds / 1e9, 'unit': 'Gcell-updates/s',
-               'h2d_bytes_per_step': state_bytes / args.steps,
-               'd2h_bytes_per_step': (state_bytes + 4 * 8 * args.steps) / args.steps,
+               'h2d_bytes_per_step': world * state_bytes / args.steps,
+               'd2h_bytes_per_step': world * (state_bytes + 4 * 8 * args.steps) / args.steps,
                'seconds': seconds, 'phases': api_field.__dict__.get('_last_run_profile'),
                'first_call_phases': first_call,
-               'what': 'field.simulate({}) from host numpy arrays: upload of p/vx/vy, boundary and '
-                       'probe tables, {} steps, download of p/vx/vy and probe signals'.format(
-                           args.steps, args.steps)}
+               'what': '{}.simulate({}) from host numpy arrays (page-locked on first use): upload of '
+                       'p/vx/vy rows, boundary and probe tables, {} steps, download of p/vx/vy and '
+                       'probe signals'.format('field' if world == 1 else 'SlabRun', args.steps,
+                                              args.steps)}
 
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:

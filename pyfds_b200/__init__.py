@@ -6,7 +6,10 @@ whose ``simulate()`` runs on the CUDA step engine (``libfdsb200.so``, C ABI in `
 """
 
 from . import fields, regions
+from .acoustic_flow import *
 from .acoustics import *
+from .coupled_fields import *
+from .coupling import *
 from .regions import *
 from .thermal import *
 

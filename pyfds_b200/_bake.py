@@ -52,6 +52,31 @@ class MaterialSnapshot:
         return all(len(values) == len(self.params) for _, values in self.entries)
 
 
+class DenseSnapshot:
+    """Material description of a field whose ``material_vector`` was replaced on the instance (the
+    reference's ``MaterialCoupling`` does that, ``pyfds/coupling.py:179-180``): the per-point vectors
+    themselves, frozen at ``assemble_matrices`` time. Distinct value combinations become materials."""
+
+    def __init__(self, field, params):
+        self.params = tuple(params)
+        self.vectors = {p: np.asarray(field.material_vector(p), dtype=np.float64).reshape(-1)
+                        for p in self.params}
+
+
+def _dense_material_ids(snapshot, num_points, cell_lo, cell_hi):
+    lo, hi = max(cell_lo, 0), min(cell_hi, num_points)
+    ids = np.zeros(cell_hi - cell_lo, dtype=np.uint8)
+    stacked = np.stack([snapshot.vectors[p][lo:hi] for p in snapshot.params], axis=1)
+    combos, inverse = np.unique(stacked, axis=0, return_inverse=True)
+    if len(combos) > MAX_MATERIALS:
+        raise NotImplementedError(
+            'The per-point material vectors hold {} distinct parameter combinations; the device '
+            'engine supports {}.'.format(len(combos), MAX_MATERIALS))
+    ids[lo - cell_lo:hi - cell_lo] = (inverse.reshape(-1) + 1).astype(np.uint8)
+    values = {p: np.concatenate(([0.0], combos[:, k])) for k, p in enumerate(snapshot.params)}
+    return ids, values
+
+
 def _local_cells(region, nx, cell_lo, cell_hi):
     """Flat indices of ``region`` that fall into [cell_lo, cell_hi), shifted to start at 0."""
     idx = region.index_array() if isinstance(region, reg.Region) else \
@@ -84,6 +109,8 @@ def material_ids(snapshot, num_points, nx, cell_lo, cell_hi):
     Returns ``(ids uint8[cell_hi - cell_lo], {param: float64[n + 1]})`` with entry 0 of every value
     vector unused (the void material has no physical parameters; its coefficients are all zero).
     """
+    if isinstance(snapshot, DenseSnapshot):
+        return _dense_material_ids(snapshot, num_points, cell_lo, cell_hi)
     lo, hi = max(cell_lo, 0), min(cell_hi, num_points)
     ids = np.zeros(cell_hi - cell_lo, dtype=np.uint8)
     inner = ids[lo - cell_lo:hi - cell_lo]

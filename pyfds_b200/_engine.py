@@ -277,7 +277,7 @@ class _State:
             return
         address = array.ctypes.data
         current = self.pinned.get(index)
-        if current is not None and current[1] == address and current[0] is array:
+        if current is not None and current[1] == address and current[0].nbytes == array.nbytes:
             return
         if current is not None:
             lib.fds_host_unregister(ct.c_void_p(current[1]))

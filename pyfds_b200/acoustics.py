@@ -31,8 +31,12 @@ class _DeviceModel:
         """Freezes what the reference's ``assemble_matrices`` reads (materials per region) for the
         device engine; the scipy ``a_*`` operators are built lazily and only if somebody asks."""
         epoch = (self._baked['epoch'] + 1) if self._baked else 0
-        self._baked = {'snapshot': _bake.MaterialSnapshot(self, self._material_params),
-                       'epoch': epoch, 'lossy': False}
+        if 'material_vector' in vars(self):
+            # material_vector was replaced on the instance (MaterialCoupling): per-point parameters
+            snapshot = _bake.DenseSnapshot(self, self._material_params)
+        else:
+            snapshot = _bake.MaterialSnapshot(self, self._material_params)
+        self._baked = {'snapshot': snapshot, 'epoch': epoch, 'lossy': False}
         self._operators = {}
         self.matrices_assembled = True
 

@@ -14,7 +14,7 @@ and gathers probe records; none of the field data moves through it.
 
 import numpy as np
 
-from . import _engine
+from . import _bake, _engine
 
 #: steps per launch of the streaming kernel = halo rows it needs on a lossless grid
 STREAM_STEPS = 4
@@ -35,8 +35,10 @@ def is_lossy(field):
     """True if any material region has a non-zero absorption coefficient (acoustic models)."""
     if not field.matrices_assembled:
         field.assemble_matrices()
-    return any(values.get('absorption_coef', 0) != 0
-               for _, values in field._baked['snapshot'].entries)
+    snapshot = field._baked['snapshot']
+    if isinstance(snapshot, _bake.DenseSnapshot):
+        return bool(np.any(snapshot.vectors.get('absorption_coef', 0) != 0))
+    return any(values.get('absorption_coef', 0) != 0 for _, values in snapshot.entries)
 
 
 def stencil_reach(field):
@@ -122,15 +124,19 @@ class SlabRun:
         return slice(self.row0 * nx, (self.row0 + self.rows) * nx)
 
     def upload_state(self):
+        state = self.field.__dict__['_engine_state']
         for c, name in enumerate(self.field._device_components):
             values = _engine._host_values(getattr(self.field, name), self.field.num_points)
-            self.engine.upload_state(c, values[self.cells])
+            own = values[self.cells]
+            if values.ctypes.data == np.asarray(getattr(self.field, name).values).ctypes.data:
+                state.pin(self.engine.lib, c, own)       # page-lock the rows this rank owns
+            self.engine.upload_state(c, own)
 
     def download_state(self):
         for c, name in enumerate(self.field._device_components):
             component = getattr(self.field, name)
             values = np.ascontiguousarray(component.values, dtype=np.float64)
-            values[self.cells] = self.engine.download_state(c)
+            self.engine.download_state(c, out=values[self.cells])
             component.values = values
 
     def simulate(self, num_steps, gather_probes=True):
