@@ -115,6 +115,7 @@ def test_thermoacoustic_preset_matches_host_emulation(library):
     device.simulate(60)
 
     host = build()
+    host.assemble_matrices()      # the interaction reads the acoustic field's a_v_p operator
     steppers = [restate.stepper_for(field) for field in host.fields]
     for step in range(60):
         for field, stepper in zip(host.fields, steppers):
