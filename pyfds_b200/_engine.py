@@ -43,6 +43,10 @@ _LIB = None
 
 
 def library_path():
+    # FDS_LIBRARY_PATH: load an alternative build of the same library (kernel tuning experiments)
+    override = os.environ.get('FDS_LIBRARY_PATH')
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), 'libfdsb200.so')
 
 

@@ -29,6 +29,7 @@
 #include "fds_step1d.cuh"
 #include "fds_step2d.cuh"
 #include "fds_stream2d.cuh"
+#include "fds_streamv.cuh"
 
 using namespace fds;
 
@@ -149,6 +150,7 @@ struct fds_ctx {
     unsigned launch_seq = 0;
     bool use_stream2d = false; // streaming multi-step kernel selected
     bool use_tile2d = false;   // shared-memory tile kernel selected (one step per launch)
+    bool use_streamv = false;  // streaming kernel of the viscous / axisymmetric acoustic models
     StepTables *d_tables = nullptr;   // device copy of the tables for the streaming kernel's slow path
     int *task_counters = nullptr;     // pool of zeroed work counters, one per streaming launch
     int next_counter = 0;
@@ -455,11 +457,22 @@ bool stream_supported(const fds_desc &d) {
     return model_ok && d.nx % 4 == 0 && d.nx >= kStripCells;
 }
 
+bool streamv_supported(const fds_desc &d) {
+    const bool model_ok = (d.model == FDS_ACOUSTIC2D && d.lossy) || d.model == FDS_ACOUSTIC3DAXI;
+    return model_ok && d.nx % 4 == 0 && d.nx >= kStripCells;
+}
+
+// steps per launch the streaming kernels support for this model
+int stream_max_steps(const fds_ctx *ctx) {
+    if (ctx->use_streamv) return (ctx->d.model == FDS_ACOUSTIC3DAXI) ? 1 : 2;
+    return kMaxStreamSteps;
+}
+
 int stream_chunk_rows(const fds_ctx *ctx, long long rows, int n_strips, int k) {
     if (ctx->chunk_rows > 0) return ctx->chunk_rows;
     // A task costs about t = (chunk + 2k + ring fill) row times; with dynamic distribution over the
     // 148 SMs x 2 CTAs x 4 warps the makespan is about tasks * t / slots plus half a task of tail.
-    const double slots = 148.0 * 2 * kStreamWarps;
+    const double slots = 148.0 * kStreamCtasPerSm * kStreamWarps;
     long long best = 64;
     double best_cost = -1;
     for (long long h : {32, 48, 64, 96, 128, 192, 256, 384, 512}) {
@@ -482,8 +495,24 @@ int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
     }
     // persistent CTAs (2 per SM) pull tasks from a counter
     const long long want = (a.n_tasks + kStreamWarps - 1) / kStreamWarps;
-    const long long ctas = std::min<long long>(want, 148 * 2);
+    const long long ctas = std::min<long long>(want, 148 * kStreamCtasPerSm);
     kernel<<<(unsigned)ctas, kStreamWarps * 32, smem, ctx->stream>>>(a);
+    FDS_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+template <int K, bool AXI, bool VISC>
+int launch_streamv(fds_ctx *ctx, const StreamVArgs &av) {
+    auto kernel = streamv_kernel<K, AXI, VISC>;
+    const int smem = kStreamWarps * kWarpRingBytes;
+    static bool configured = false;
+    if (!configured) {
+        FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const long long want = (av.base.n_tasks + kStreamWarps - 1) / kStreamWarps;
+    const long long ctas = std::min<long long>(want, 148 * kStreamCtasPerSm);
+    kernel<<<(unsigned)ctas, kStreamWarps * 32, smem, ctx->stream>>>(av);
     FDS_CUDA(ctx, cudaGetLastError());
     return 0;
 }
@@ -492,7 +521,7 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     const long long rows = a.row_end - a.row_begin;
     if (rows <= 0) return 0;
     a.n_strips = (int)((a.nx + kStripStride - 1) / kStripStride);
-    a.chunk_rows = stream_chunk_rows(ctx, rows, a.n_strips, k);
+    a.chunk_rows = stream_chunk_rows(ctx, rows, a.n_strips, ctx->use_streamv ? 2 * k : k);
     a.n_tasks = (int)(a.n_strips * ((rows + a.chunk_rows - 1) / a.chunk_rows));
     if (ctx->n_strips_ordered != a.n_strips) {
         // strips that carry boundary cells (slow path) are handed out first (longest task first)
@@ -521,6 +550,21 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     a.map = ctx->map + ctx->pad + ctx->halo;
     a.tab = ctx->tab;
     a.tables = ctx->d_tables;
+    if (ctx->use_streamv) {
+        StreamVArgs av{};
+        av.base = a;
+        av.ctab = ctx->ctab;
+        av.cvec = ctx->cvec;
+        av.n_mat1 = ctx->d.n_materials + 1;
+        const bool lossy = ctx->d.lossy != 0;
+        if (ctx->d.model == FDS_ACOUSTIC3DAXI && k == 1)
+            return lossy ? launch_streamv<1, true, true>(ctx, av) : launch_streamv<1, true, false>(ctx, av);
+        if (ctx->d.model == FDS_ACOUSTIC2D && lossy && k == 1)
+            return launch_streamv<1, false, true>(ctx, av);
+        if (ctx->d.model == FDS_ACOUSTIC2D && lossy && k == 2)
+            return launch_streamv<2, false, true>(ctx, av);
+        return fail(ctx, "streamv: unsupported model / step count");
+    }
 #define FDS_STREAM_CASE(K_)                                                                  \
     case K_:                                                                                 \
         return ctx->thermal ? launch_stream2d<K_, true>(ctx, a) : launch_stream2d<K_, false>(ctx, a);
@@ -681,7 +725,7 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
     }
 
     StepTables t = make_tables(ctx);
-    if (ctx->use_stream2d)
+    if (ctx->use_stream2d || ctx->use_streamv)
         FDS_CUDA(ctx, cudaMemcpyAsync(ctx->d_tables, &t, sizeof(StepTables), cudaMemcpyHostToDevice,
                                       ctx->stream));
     const long long half = ctx->ring_half;
@@ -734,7 +778,7 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                                                   : "step1d_kernel<acoustic,lossless>";
                 ctx->last_steps_per_launch = p.steps;
                 ctx->last_launches += 1;
-            } else if (ctx->use_stream2d) {
+            } else if (ctx->use_stream2d || ctx->use_streamv) {
                 Stream2DArgs a{};
                 for (int c = 0; c < 3; ++c) {
                     a.in[c] = origin(ctx, ctx->cur, c);
@@ -745,8 +789,10 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 a.ring_row = ring_row;
                 const long long rows = ctx->d.rows;
                 const bool multi = ctx->comm && ctx->world > 1;
-                int k = (int)std::min<long long>(ctx->max_k, chunk_steps - in_chunk);
-                if (multi) k = std::min<int>(k, ctx->d.halo_rows);
+                int k = (int)std::min<long long>(std::min(ctx->max_k, stream_max_steps(ctx)),
+                                                 chunk_steps - in_chunk);
+                // a slab can only advance as many steps as its halo rows cover
+                if (multi) k = std::min<int>(k, ctx->d.halo_rows / (ctx->d.lossy ? 2 : 1));
                 // thermal fluxes are derived data: stored only by the launch that ends the call
                 a.write_vector = (s + k == n_steps);
                 if (multi && peers_ready(ctx)) {
@@ -778,8 +824,14 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 }
                 advanced = k;
                 ctx->last_steps_per_launch = std::max<long long>(ctx->last_steps_per_launch, k);
-                ctx->last_kernel = ctx->thermal ? "stream2d_kernel<thermal2d>"
-                                                : "stream2d_kernel<acoustic2d,lossless>";
+                ctx->last_kernel =
+                    ctx->use_streamv
+                        ? (ctx->d.model == FDS_ACOUSTIC3DAXI
+                               ? (ctx->d.lossy ? "streamv_kernel<acoustic3daxi,lossy>"
+                                               : "streamv_kernel<acoustic3daxi,lossless>")
+                               : "streamv_kernel<acoustic2d,lossy>")
+                        : (ctx->thermal ? "stream2d_kernel<thermal2d>"
+                                        : "stream2d_kernel<acoustic2d,lossless>");
             } else {
                 Step2DArgs a{};
                 for (int c = 0; c < 3; ++c) {
@@ -960,15 +1012,16 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
     ctx->axi = (d.model == FDS_ACOUSTIC3DAXI || d.model == FDS_THERMAL3DAXI);
     ctx->owned = d.rows * d.nx;
     ctx->halo = (long long)d.halo_rows * d.nx;
-    if (d.kernel == 2 && !stream_supported(d)) {
+    if (d.kernel == 2 && !stream_supported(d) && !streamv_supported(d)) {
         delete ctx;
-        return fail(nullptr, "fds_create: the streaming kernel needs lossless Acoustic2D or Thermal2D "
-                             "with nx % 4 == 0 and nx >= 128");
+        return fail(nullptr, "fds_create: the streaming kernels need Acoustic2D, Acoustic3DAxi or "
+                             "Thermal2D with nx % 4 == 0 and nx >= 128");
     }
     if (const char *env = getenv("FDS_TILE_ROWS")) ctx->tile_rows = atoi(env);
     ctx->use_stream2d = (d.kernel == 0 || d.kernel == 2) && stream_supported(d);
-    ctx->use_tile2d = !one_d && !ctx->use_stream2d && (d.kernel == 0 || d.kernel == 3) &&
-                      d.nx % 8 == 0 && d.nx >= kTileW;
+    ctx->use_streamv = (d.kernel == 0 || d.kernel == 2) && streamv_supported(d);
+    ctx->use_tile2d = !one_d && !ctx->use_stream2d && !ctx->use_streamv &&
+                      (d.kernel == 0 || d.kernel == 3) && d.nx % 8 == 0 && d.nx >= kTileW;
     if (d.kernel == 3 && !ctx->use_tile2d) {
         delete ctx;
         return fail(nullptr, "fds_create: the tile kernel needs a 2-D model with nx % 8 == 0, nx >= 128");

@@ -31,7 +31,14 @@ namespace fds {
 constexpr int kStripCells = 128;     // cells a warp streams per row (4 per lane)
 constexpr int kStripHalo = 4;        // halo cells either side = one lane
 constexpr int kStripStride = kStripCells - 2 * kStripHalo;   // 120 owned cells per strip
-constexpr int kRingDepth = 6;        // rows in flight per warp
+#ifndef FDS_STREAM_MIN_CTAS
+#define FDS_STREAM_MIN_CTAS 2
+#endif
+#ifndef FDS_STREAM_RING
+#define FDS_STREAM_RING 6
+#endif
+constexpr int kStreamCtasPerSm = FDS_STREAM_MIN_CTAS;   // resident CTAs per SM (register budget)
+constexpr int kRingDepth = FDS_STREAM_RING;   // rows in flight per warp
 constexpr int kStreamWarps = 4;      // warps per CTA
 constexpr int kMaxStreamSteps = 4;   // K
 constexpr int kMapWindowBytes = kStripCells * 2 + 16;         // 128 map entries + alignment slack
@@ -142,7 +149,8 @@ struct RowInfo {
 // state: the flux components are not read (q = -(A_q_t T) overwrites them, they are not accumulated)
 // and only stored when the host asks for them after the last step of a call.
 template <int K, bool THERMAL>
-__global__ void __launch_bounds__(kStreamWarps * 32, 2) stream2d_kernel(Stream2DArgs a) {
+__global__ void __launch_bounds__(kStreamWarps * 32, kStreamCtasPerSm)
+stream2d_kernel(Stream2DArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double tabs[4][kMaxMaterials];   // FDS_TAB_GX, GY, FX, FY
     __shared__ double cls_alpha[3][kMaxClasses], cls_value[3][kMaxClasses];

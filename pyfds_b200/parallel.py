@@ -46,20 +46,33 @@ def stencil_reach(field):
     return 2 if is_lossy(field) else 1
 
 
-def streaming_eligible(field):
+def streaming_steps(field):
+    """Time steps per launch of the streaming kernels for this field (0: not eligible): 4 for lossless
+    Acoustic2D and Thermal2D, 2 for lossy Acoustic2D, 1 for Acoustic3DAxi."""
     nx = field.x.samples
-    model_ok = (field._device_model == 'acoustic2d' and not is_lossy(field)) or \
-        field._device_model == 'thermal2d'
-    return model_ok and nx % 4 == 0 and nx >= 128
+    if nx % 4 or nx < 128:
+        return 0
+    model = field._device_model
+    if model == 'thermal2d' or (model == 'acoustic2d' and not is_lossy(field)):
+        return STREAM_STEPS
+    if model == 'acoustic2d':
+        return 2
+    if model == 'acoustic3daxi':
+        return 1
+    return 0
+
+
+def streaming_eligible(field):
+    return streaming_steps(field) > 0
 
 
 def halo_rows_for(field, world, kernel=0):
     """Halo rows per side of a slab context: the reach of one step, times the steps per launch when
-    the streaming kernel will run."""
+    a streaming kernel will run."""
     if world <= 1:
         return 0
-    if kernel != 1 and streaming_eligible(field):
-        return STREAM_STEPS * stencil_reach(field)
+    if kernel in (0, 2) and streaming_eligible(field):
+        return streaming_steps(field) * stencil_reach(field)
     return stencil_reach(field)
 
 

@@ -162,7 +162,7 @@ def test_round_trip_properties_at_full_size(library):
 
 # ---- streaming multi-step kernel vs one-step kernel -------------------------------------------------
 
-def _stream_case(nx, ny, steps, seed, kernel):
+def _stream_case(nx, ny, steps, seed, kernel, klass='Acoustic2D', lossy=False):
     """Boundaries, sources and probes placed on strip seams (x = 119, 120, 121, 240), on the halo
     lanes, on the first/last rows and on chunk seams (coordinates clamped to small grids)."""
     def X(k):
@@ -171,13 +171,15 @@ def _stream_case(nx, ny, steps, seed, kernel):
     def Y(k):
         return min(k, ny - 1) * 1e-3
 
-    f = fds.Acoustic2D(t_delta=1e-7, t_samples=steps, x_delta=1e-3, x_samples=nx, y_delta=1e-3,
-                       y_samples=ny, material=fds.AcousticMaterial(1500, 1000))
+    f = getattr(fds, klass)(t_delta=1e-7, t_samples=steps, x_delta=1e-3, x_samples=nx,
+                            y_delta=1e-3, y_samples=ny,
+                            material=fds.AcousticMaterial(1500, 1000,
+                                                          shear_viscosity=1e-3 if lossy else 0))
     f.device_kernel = kernel
     f.add_material_region(f.get_rect_region((X(100), Y(10), X(145) - X(100), Y(40) - Y(10))),
-                          fds.AcousticMaterial(1200, 900))
+                          fds.AcousticMaterial(1200, 900, absorption_coef=7.7 if lossy else None))
     f.add_material_region(f.get_rect_region((X(119), Y(20), X(121) - X(119), Y(60) - Y(20))),
-                          fds.AcousticMaterial(1350, 950))
+                          fds.AcousticMaterial(1350, 950, absorption_coef=300 if lossy else None))
     scenarios._randomise(f, ('pressure', 'velocity_x', 'velocity_y'), seed)
     top = Y(ny)
     f.velocity_x.add_boundary(f.get_line_region((0, 0, 0, top)))
@@ -249,3 +251,28 @@ def test_tile_kernel_equals_one_step_kernel(library, builder, args, monkeypatch)
         name = f.__dict__['_engine_state'].engine.last_launch_info()[2]
         assert ('tile2d' in name) == (kernel == 3), name
     assert_same(results[1], results[0], 'tile vs step {}'.format(args))
+
+
+# ---- streaming kernel of the viscous / axisymmetric models vs one-step kernel ---------------------
+
+@pytest.mark.parametrize('klass,lossy,max_k,chunk', [
+    ('Acoustic2D', True, 2, 0), ('Acoustic2D', True, 1, 11), ('Acoustic2D', True, 2, 6),
+    ('Acoustic3DAxi', False, 1, 0), ('Acoustic3DAxi', True, 1, 0), ('Acoustic3DAxi', True, 1, 9)])
+def test_viscous_streaming_kernel_equals_one_step_kernel(library, klass, lossy, max_k, chunk,
+                                                         monkeypatch):
+    monkeypatch.setenv('FDS_MAX_K', str(max_k))
+    monkeypatch.setenv('FDS_CHUNK_ROWS', str(chunk))
+    results = []
+    for kernel in (1, 2):
+        f = _stream_case(376, 83, 15, seed=61, kernel=kernel, klass=klass, lossy=lossy)
+        f.simulate(7)
+        f.simulate(8)
+        results.append(scenarios.collect(f))
+        name = f.__dict__['_engine_state'].engine.last_launch_info()[2]
+        assert ('streamv' in name) == (kernel == 2), name
+    assert_same(results[1], results[0], 'streamv vs step {} lossy={}'.format(klass, lossy))
+
+
+def test_viscous_streaming_kernel_vs_oracle(library):
+    f = _stream_case(256, 70, 12, seed=62, kernel=2, klass='Acoustic3DAxi', lossy=True)
+    _vs_oracle(f, 12, 'streamv axi lossy 256x70')
