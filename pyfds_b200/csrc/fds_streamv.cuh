@@ -8,7 +8,7 @@
 //   rows q-2, q-1)            ->  new p of row q-2 (needs new vx of row q-2, new vy of rows q-2, q-1)
 //
 // and the dependency cone grows 1 cell to the left and 2 to the right per step, which the 4-cell strip
-// halo covers for K <= 2. Per stage 8 row fragments stay in registers (p after boundaries, old vx, vy
+// halo covers for K <= 2 (only K = 1 is instantiated: a second stage spills registers and is slower). Per stage 8 row fragments stay in registers (p after boundaries, old vx, vy
 // of two rows; new vx, vy of one row). Axisymmetric coefficients depend on the column: for the
 // warp-uniform material path the per-column values of this lane's cells (and its two neighbours) are
 // kept in registers and reloaded only when the material changes; K = 1 there (register budget).

@@ -48,16 +48,14 @@ def stencil_reach(field):
 
 def streaming_steps(field):
     """Time steps per launch of the streaming kernels for this field (0: not eligible): 4 for lossless
-    Acoustic2D and Thermal2D, 2 for lossy Acoustic2D, 1 for Acoustic3DAxi."""
+    Acoustic2D and Thermal2D, 1 for lossy Acoustic2D and Acoustic3DAxi."""
     nx = field.x.samples
     if nx % 4 or nx < 128:
         return 0
     model = field._device_model
     if model == 'thermal2d' or (model == 'acoustic2d' and not is_lossy(field)):
         return STREAM_STEPS
-    if model == 'acoustic2d':
-        return 2
-    if model == 'acoustic3daxi':
+    if model in ('acoustic2d', 'acoustic3daxi'):
         return 1
     return 0
 
