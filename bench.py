@@ -262,7 +262,9 @@ def main():
     per_gpu_cells = nx * rows
     value = cells * args.steps / (device_ms * 1e-3) / 1e9
     peak, peak_source = measured_peak()
-    step_launches = launches / (3 if world > 1 else 1)
+    # time steps advance steps_per_launch at a time (a slab without peer access launches its edge
+    # bands and its interior separately: `launches` counts those, not this)
+    step_launches = -(-args.steps // max(steps_per_launch, 1))
     launch_ms = device_ms / max(step_launches, 1)
     achieved = BYTES_PER_CELL_UPDATE * per_gpu_cells * steps_per_launch / (launch_ms * 1e-3) / 1e9
 

@@ -113,8 +113,17 @@ struct fds_ctx {
     DevArray ccells[3], cclass[3];
     long long n_ccells[3] = {0, 0, 0};
     double cls_alpha[3][kMaxClasses] = {}, cls_value[3][kMaxClasses] = {};
-    DevArray strip_order;
-    int n_strips_ordered = 0;
+    // task tables of the streaming kernels, one per (row range, steps per launch) seen so far, and
+    // the census they are balanced with: rows per strip that cannot take the branch-free body
+    struct StreamPlan {
+        long long row_begin = 0, row_end = 0;
+        int k = 0, n_tasks = 0;
+        void *tasks = nullptr;
+    };
+    std::vector<StreamPlan> plans;
+    std::vector<int> strip_nonplain;   // [strip][block of kCensusBlockRows rows]
+    int census_blocks = 0;
+    bool census_valid = false;
     DevArray flagged;         // cells whose flag bits are currently set
     long long n_flagged = 0;
     bool flags_dirty = false;
@@ -262,8 +271,11 @@ int upload_row_ptr(fds_ctx *ctx, DevArray &dst, const long long *cells, int64_t 
 }
 
 // Rebuilds the per-cell flag bits from the boundary and probe tables.
+void invalidate_plans(fds_ctx *ctx);
+
 int refresh_flags(fds_ctx *ctx) {
     if (!ctx->flags_dirty) return 0;
+    invalidate_plans(ctx);   // the strip census reads the flag and class bits
     const unsigned all_bits = kFlagBound | kFlagProbe | kClassMask;
     if (ctx->n_flagged)
         if (launch_flags(ctx, (const long long *)ctx->flagged.ptr, nullptr, 0, ctx->n_flagged, 0,
@@ -454,7 +466,7 @@ const char *step2d_name(const fds_ctx *ctx) {
 
 bool stream_supported(const fds_desc &d) {
     const bool model_ok = (d.model == FDS_ACOUSTIC2D && !d.lossy) || d.model == FDS_THERMAL2D;
-    return model_ok && d.nx % 4 == 0 && d.nx >= kStripCells;
+    return model_ok && d.nx % 4 == 0 && d.nx >= 128;
 }
 
 bool streamv_supported(const fds_desc &d) {
@@ -470,34 +482,230 @@ int stream_max_steps(const fds_ctx *ctx) {
     return kMaxStreamSteps;
 }
 
-int stream_chunk_rows(const fds_ctx *ctx, long long rows, int n_strips, int k) {
-    if (ctx->chunk_rows > 0) return ctx->chunk_rows;
-    // A task costs about t = (chunk + 2k + ring fill) row times; with dynamic distribution over the
-    // 148 SMs x 2 CTAs x 4 warps the makespan is about tasks * t / slots plus half a task of tail.
-    const double slots = 148.0 * kStreamCtasPerSm * kStreamWarps;
-    long long best = 64;
-    double best_cost = -1;
-    for (long long h : {32, 48, 64, 96, 128, 192, 256, 384, 512}) {
-        const double tasks = (double)n_strips * (double)((rows + h - 1) / h);
-        const double t = (double)std::min(h, rows) + 2 * k + 4;
-        const double cost = std::max(tasks, slots) * t / slots + 0.5 * t;
-        if (best_cost < 0 || cost < best_cost) { best = h; best_cost = cost; }
+// Rows of every strip that cannot take the branch-free body of the streaming kernels: flagged for
+// a table lookup or a probe, constant operations on more than one component (or on any, where the
+// row is not of one material), or map words that differ from the row before (the criterion of RowTag::steady and of the pair
+// vote in fds_stream2d.cuh): one warp per (strip, row).
+constexpr int kCensusBlockRows = 32;   // the census counts per strip and block of rows
+
+template <int C>   // cells per lane: 2 (fds_stream2d.cuh) or 4 (fds_streamv.cuh)
+__global__ void strip_census_kernel(const map_t *map, long long nx, long long rows, int n_strips,
+                                    int stride, int halo, int n_blocks, int *nonplain) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long item = warp; item < rows * n_strips; item += n_warps) {
+        const int strip = (int)(item % n_strips);
+        const long long row = item / n_strips;
+        const long long x0 = (long long)strip * stride - halo + C * lane;
+        unsigned long long raw = 0, prev = 0, unit = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            raw |= (unsigned long long)map[row * nx + x0 + c] << (16 * c);
+            prev |= (unsigned long long)map[(row - 1) * nx + x0 + c] << (16 * c);
+            unit |= 1ull << (16 * c);
+        }
+        const unsigned long long first = __shfl_sync(0xffffffffu, raw, 0) & kIdMask;
+        const bool relevant = x0 < nx + halo;
+        if (!relevant) raw = prev = first * unit;
+        unsigned comps = 0;   // components with constant operations in this row
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (__any_sync(0xffffffffu, (raw & ((7ull * unit) << class_shift(c))) != 0))
+                comps |= 1u << c;
+        const bool uniform = __all_sync(0xffffffffu, (raw & (kIdMask * unit)) == first * unit);
+        const bool ok = (raw & ((kFlagBound | kFlagProbe) * unit)) == 0 && (row == 0 || raw == prev);
+        const bool classes_ok = uniform ? (comps & (comps - 1u)) == 0u : comps == 0u;
+        if ((!__all_sync(0xffffffffu, ok) || !classes_ok) && lane == 0)
+            atomicAdd(nonplain + (long long)strip * n_blocks + row / kCensusBlockRows, 1);
     }
-    return (int)best;
+}
+
+int strip_census(fds_ctx *ctx, int n_strips) {
+    const int n_blocks = (int)((ctx->d.rows + kCensusBlockRows - 1) / kCensusBlockRows);
+    const size_t n = (size_t)n_strips * (size_t)n_blocks;
+    int *d_counts = nullptr;
+    if (dev_alloc(ctx, (void **)&d_counts, sizeof(int) * n, true)) return 1;
+    const map_t *map = ctx->map + ctx->pad + ctx->halo;
+    if (ctx->use_streamv)
+        strip_census_kernel<4><<<148 * 4, 256, 0, ctx->stream>>>(
+            map, ctx->d.nx, ctx->d.rows, n_strips, kStripStride, kStripHalo, n_blocks, d_counts);
+    else
+        strip_census_kernel<kS2LaneCells><<<148 * 4, 256, 0, ctx->stream>>>(
+            map, ctx->d.nx, ctx->d.rows, n_strips, kS2StripStride, kS2StripHalo, n_blocks, d_counts);
+    FDS_CUDA(ctx, cudaGetLastError());
+    ctx->strip_nonplain.assign(n, 0);
+    FDS_CUDA(ctx, cudaMemcpyAsync(ctx->strip_nonplain.data(), d_counts, sizeof(int) * n,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_counts);
+    ctx->device_bytes -= (long long)(sizeof(int) * n);
+    ctx->census_blocks = n_blocks;
+    ctx->census_valid = true;
+    return 0;
+}
+
+void invalidate_plans(fds_ctx *ctx) {
+    if (!ctx->plans.empty()) {
+        cudaStreamSynchronize(ctx->stream);
+        for (auto &p : ctx->plans)
+            if (p.tasks) cudaFree(p.tasks);
+        ctx->plans.clear();
+    }
+    ctx->census_valid = false;
+}
+
+// Task table of one streaming launch: every strip is cut into chunks of rows so that all tasks cost
+// about the same and fill a whole number of rounds over the 148 SMs x CTAs x warps.
+//   cost of a task = its rows + overhead, a row that takes the general row iteration counting
+//   general_weight times (census: rows that are not steady, each of which sends about k + 3 rows
+//   through the general iteration); overhead = rows streamed in addition to the owned ones
+//   (pipeline fill, ring fill).
+// For R = 1, 2, ... rounds the smallest cost C is found for which the tasks fit R * slots; the R with
+// the smallest makespan R * C wins. Strips without general rows are cut evenly, the others where the
+// accumulated cost crosses the multiples of their share. Tasks of the latter are handed out first,
+// the rest chunk-major (dynamic distribution absorbs what the model misses).
+int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int k, int lag_rows) {
+    const long long rows = plan.row_end - plan.row_begin;
+    const double slots = 148.0 * (ctx->use_streamv ? kStreamCtasPerSm : kS2CtasPerSm) * kStreamWarps;
+    const double overhead = 2.0 * lag_rows + 4.0;
+    // measured on B200 (4096^2, bench.py): 4 -> 326, 8 -> 317, 14 -> 320 Gcell-updates/s. The viscous /
+    // axisymmetric kernel has its own fast-path test and no branch-free body: all rows count alike.
+    double general_weight = ctx->use_streamv ? 1.0 : 5.0;
+    if (const char *env = getenv("FDS_GENERAL_WEIGHT")) general_weight = atof(env);
+    const int nb = ctx->census_blocks;
+    auto row_cost = [&](int s, long long row) {
+        const int count = ctx->strip_nonplain[(size_t)s * nb + (size_t)(row / kCensusBlockRows)];
+        const double general =
+            std::min<double>(kCensusBlockRows, (double)count * (k + 3)) / kCensusBlockRows;
+        return 1.0 + (general_weight - 1.0) * general;
+    };
+    std::vector<double> strip_cost((size_t)n_strips, (double)rows);
+    std::vector<char> has_general((size_t)n_strips, 0);
+    for (int s = 0; s < n_strips; ++s) {
+        for (long long b = plan.row_begin / kCensusBlockRows;
+             b <= (plan.row_end - 1) / kCensusBlockRows; ++b)
+            if (ctx->strip_nonplain[(size_t)s * nb + (size_t)b] && general_weight != 1.0)
+                has_general[(size_t)s] = 1;
+        if (!has_general[(size_t)s]) continue;
+        double total = 0;
+        for (long long row = plan.row_begin; row < plan.row_end; ++row) total += row_cost(s, row);
+        strip_cost[(size_t)s] = total;
+    }
+    const long long min_rows = std::min<long long>(rows, 8);
+    std::vector<long long> count((size_t)n_strips, 1), best_count;
+    auto tasks_for = [&](double cost) {
+        double n = 0;
+        const double room = std::max(cost - overhead, 1.0);
+        for (int s = 0; s < n_strips; ++s) {
+            long long c = (long long)std::ceil(strip_cost[(size_t)s] / room);
+            c = std::max<long long>(1, std::min(c, std::max<long long>(rows / min_rows, 1)));
+            count[(size_t)s] = c;
+            n += (double)c;
+        }
+        return n;
+    };
+    if (ctx->chunk_rows > 0) {
+        const long long h = std::min<long long>(ctx->chunk_rows, rows);
+        best_count.assign((size_t)n_strips, (rows + h - 1) / h);
+    } else {
+        double best_makespan = -1;
+        for (int rounds = 1; rounds <= 8; ++rounds) {
+            double lo = overhead + (double)min_rows, hi = general_weight * (double)rows + overhead;
+            if (tasks_for(lo) <= rounds * slots) hi = lo;
+            for (int it = 0; it < 50 && hi - lo > 0.01; ++it) {
+                const double mid = 0.5 * (lo + hi);
+                if (tasks_for(mid) <= rounds * slots) hi = mid; else lo = mid;
+            }
+            const double n = tasks_for(hi);
+            // fewer tasks than slots: one round of whatever the tallest task costs
+            const double makespan = (n <= slots ? 1 : rounds) * hi;
+            if (best_makespan < 0 || makespan < best_makespan * 0.995) {
+                best_makespan = makespan;
+                best_count = count;
+            }
+            if (n <= slots) break;
+        }
+    }
+    struct Item { int strip; long long ys, ye; double cost; };
+    std::vector<Item> items;
+    // strips with general rows: cut where the accumulated cost crosses the multiples of the share
+    for (int s = 0; s < n_strips; ++s) {
+        if (!has_general[(size_t)s] || ctx->chunk_rows > 0) continue;
+        const long long n = best_count[(size_t)s];
+        const double share = strip_cost[(size_t)s] / (double)n;
+        double acc = 0, chunk_cost = 0;
+        long long ys = plan.row_begin, cuts = 1;
+        for (long long row = plan.row_begin; row < plan.row_end; ++row) {
+            const double c = row_cost(s, row);
+            acc += c;
+            chunk_cost += c;
+            if (row + 1 == plan.row_end || (acc >= share * (double)cuts && cuts < n)) {
+                items.push_back({s, ys, row + 1, chunk_cost + overhead});
+                ys = row + 1;
+                chunk_cost = 0;
+                ++cuts;
+            }
+        }
+    }
+    std::stable_sort(items.begin(), items.end(),
+                     [](const Item &x, const Item &y) { return x.cost > y.cost; });
+    // the other strips: even chunks in chunk-major order -- tasks that are handed out together (the
+    // warps of a CTA, neighbouring CTAs) stream neighbouring strips of the same rows, i.e. adjacent
+    // memory: DRAM pages and the halo columns shared by two strips are reused while they are hot
+    long long max_count = 0;
+    for (int s = 0; s < n_strips; ++s) max_count = std::max(max_count, best_count[(size_t)s]);
+    for (long long c = 0; c < max_count; ++c) {
+        for (int s = 0; s < n_strips; ++s) {
+            const long long n = best_count[(size_t)s];
+            if (c >= n) continue;
+            if (ctx->chunk_rows > 0) {   // forced height (tests): fixed chunks, a short last one
+                const long long h = std::min<long long>(ctx->chunk_rows, rows);
+                const long long ys = plan.row_begin + c * h;
+                items.push_back({s, ys, std::min(ys + h, plan.row_end), 0.0});
+                continue;
+            }
+            if (has_general[(size_t)s]) continue;
+            const long long base = rows / n, extra = rows % n;   // even split into n chunks
+            const long long ys = plan.row_begin + c * base + std::min(c, extra);
+            const long long h = base + (c < extra ? 1 : 0);
+            items.push_back({s, ys, ys + h, (double)h + overhead});
+        }
+    }
+    std::vector<int4> tasks(items.size());
+    for (size_t i = 0; i < items.size(); ++i)
+        tasks[i] = make_int4(items[i].strip, (int)items[i].ys, (int)items[i].ye, 0);
+    void *dev = nullptr;
+    if (dev_alloc(ctx, &dev, tasks.size() * sizeof(int4), false)) return 1;
+    FDS_CUDA(ctx, cudaMemcpyAsync(dev, tasks.data(), tasks.size() * sizeof(int4),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `tasks` is pageable host memory
+    plan.tasks = dev;
+    plan.n_tasks = (int)tasks.size();
+    plan.k = k;
+    if (getenv("FDS_DEBUG_PLAN")) {
+        long long hmin = rows, hmax = 0;
+        for (auto &it : items) { hmin = std::min(hmin, it.ye - it.ys); hmax = std::max(hmax, it.ye - it.ys); }
+        int general = 0;
+        for (int s = 0; s < n_strips; ++s) general += has_general[(size_t)s];
+        fprintf(stderr, "[fds plan] rows %lld strips %d (%d with general rows) k %d: %d tasks, heights %lld..%lld\n",
+                rows, n_strips, general, k, plan.n_tasks, hmin, hmax);
+    }
+    return 0;
 }
 
 template <int K, bool THERMAL>
 int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
     auto kernel = stream2d_kernel<K, THERMAL>;
-    const int smem = kStreamWarps * kWarpRingBytes;
+    const int smem = kStreamWarps * kS2WarpRingBytes;
     static bool configured = false;
     if (!configured) {
         FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    // persistent CTAs (2 per SM) pull tasks from a counter
+    // persistent CTAs (4 per SM) pull tasks from a counter
     const long long want = (a.n_tasks + kStreamWarps - 1) / kStreamWarps;
-    const long long ctas = std::min<long long>(want, 148 * kStreamCtasPerSm);
+    const long long ctas = std::min<long long>(want, 148 * kS2CtasPerSm);
     kernel<<<(unsigned)ctas, kStreamWarps * 32, smem, ctx->stream>>>(a);
     FDS_CUDA(ctx, cudaGetLastError());
     return 0;
@@ -522,31 +730,24 @@ int launch_streamv(fds_ctx *ctx, const StreamVArgs &av) {
 int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     const long long rows = a.row_end - a.row_begin;
     if (rows <= 0) return 0;
-    a.n_strips = (int)((a.nx + kStripStride - 1) / kStripStride);
-    a.chunk_rows = stream_chunk_rows(ctx, rows, a.n_strips, ctx->use_streamv ? 2 * k : k);
-    a.n_tasks = (int)(a.n_strips * ((rows + a.chunk_rows - 1) / a.chunk_rows));
-    if (ctx->n_strips_ordered != a.n_strips) {
-        // strips that carry boundary cells (slow path) are handed out first (longest task first)
-        std::vector<long long> weight((size_t)a.n_strips, 0);
-        for (int c = 0; c < 3; ++c) {
-            for (long long cell : ctx->host_bcells[c]) {      // table lookups: expensive
-                const long long col = ((cell % a.nx) + a.nx) % a.nx;
-                weight[(size_t)std::min<long long>(col / kStripStride, a.n_strips - 1)] += 8;
-            }
-            for (long long cell : ctx->host_ccells[c]) {      // inline classes: cheap
-                const long long col = ((cell % a.nx) + a.nx) % a.nx;
-                weight[(size_t)std::min<long long>(col / kStripStride, a.n_strips - 1)] += 1;
-            }
-        }
-        std::vector<int> order((size_t)a.n_strips);
-        for (int k = 0; k < a.n_strips; ++k) order[(size_t)k] = k;
-        std::stable_sort(order.begin(), order.end(),
-                         [&](int x, int y) { return weight[(size_t)x] > weight[(size_t)y]; });
-        if (dev_upload(ctx, ctx->strip_order, order.data(), order.size() * sizeof(int))) return 1;
-        ctx->n_strips_ordered = a.n_strips;
+    const int stride = ctx->use_streamv ? kStripStride : kS2StripStride;
+    a.n_strips = (int)((a.nx + stride - 1) / stride);
+    if (!ctx->census_valid && strip_census(ctx, a.n_strips)) return 1;
+    fds_ctx::StreamPlan *plan = nullptr;
+    for (auto &p : ctx->plans)
+        if (p.row_begin == a.row_begin && p.row_end == a.row_end && p.k == k) plan = &p;
+    if (!plan) {
+        fds_ctx::StreamPlan fresh;
+        fresh.row_begin = a.row_begin;
+        fresh.row_end = a.row_end;
+        // rows a task streams in before its first owned row comes out: k, or 2k with the
+        // three-row window of the viscous kernel
+        if (build_stream_plan(ctx, fresh, a.n_strips, k, ctx->use_streamv ? 2 * k : k)) return 1;
+        ctx->plans.push_back(fresh);
+        plan = &ctx->plans.back();
     }
-    a.strip_order = (const int *)ctx->strip_order.ptr;
-    a.n_chunks = (int)((rows + a.chunk_rows - 1) / a.chunk_rows);
+    a.tasks = (const int4 *)plan->tasks;
+    a.n_tasks = plan->n_tasks;
     a.task_counter = next_counter(ctx);
     if (!a.task_counter) return fail(ctx, "stream2d: counter reset failed");
     a.map = ctx->map + ctx->pad + ctx->halo;
@@ -1115,7 +1316,7 @@ void fds_destroy(fds_ctx *ctx) {
             if (a->ptr) cudaFree(a->ptr);
     }
     if (ctx->flagged.ptr) cudaFree(ctx->flagged.ptr);
-    if (ctx->strip_order.ptr) cudaFree(ctx->strip_order.ptr);
+    invalidate_plans(ctx);
     if (ctx->signals.ptr) cudaFree(ctx->signals.ptr);
     if (ctx->ring.ptr) cudaFree(ctx->ring.ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -1267,7 +1468,7 @@ int fds_upload_boundaries(fds_ctx *ctx, int32_t component, const int64_t *cells,
     if (dev_upload(ctx, ctx->cclass[c], class_ids.data(), nc * 4)) return 1;
     ctx->host_bcells[c] = slow_cells;
     ctx->host_ccells[c] = class_cells;
-    ctx->n_strips_ordered = 0;
+    invalidate_plans(ctx);
     ctx->n_bcells[c] = (long long)ns;
     ctx->n_ccells[c] = (long long)nc;
     ctx->flags_dirty = true;

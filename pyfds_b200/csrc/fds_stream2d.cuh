@@ -24,6 +24,8 @@
 // bitwise identical to it and to the reference (tests/test_gpu_parity.py).
 #pragma once
 
+#include <type_traits>
+
 #include "fds_common.cuh"
 
 namespace fds {
@@ -53,13 +55,11 @@ struct Stream2DArgs {
     const double *tab;     // coefficient tables [FDS_TAB_COUNT][kMaxMaterials]
     const StepTables *tables;   // device copy, read on the slow path (boundaries, probes) only
     int *task_counter;     // dynamic task distribution (zero before the launch)
-    const int *strip_order;   // strips sorted by expected cost, most expensive first
+    const int4 *tasks;     // (strip, first row, end row, -) per task, most expensive first
     long long nx;          // row length, multiple of 4
     long long row_begin;   // rows [row_begin, row_end) are produced
     long long row_end;
-    int chunk_rows;        // rows per task
     int n_strips;
-    int n_chunks;
     int n_tasks;
     long long sig_index;   // first step - sig_first_step
     long long ring_row;    // probe record of the first step
@@ -139,18 +139,172 @@ __device__ __noinline__ void stream_slow_cells(const StepTables *__restrict__ tp
 // Row metadata that travels through the pipeline with the row.
 struct RowInfo {
     unsigned long long ids;   // the 4 map entries of this lane's cells
-    int uniform;       // material id shared by all 128 cells of the row, or -1
+    int uniform;       // material id shared by all cells of the row that matter, or -1
     bool flagged;      // some cell of the row (any lane) needs the slow path (table lookup, probe)
     unsigned classed;  // bit c set: some cell of the row (any lane) carries an inline constant
                        // boundary operation on component c
 };
 
+// =====================================================================================================
+// stream2d_kernel: lossless Acoustic2D / Thermal2D, K steps per launch
+// =====================================================================================================
+// Geometry of this kernel: a lane holds kS2LaneCells = 2 consecutive cells, so a warp streams a strip
+// of 64 cells (two halo lanes = 4 cells either side, 56 owned). Two cells per lane keep the K = 4
+// pipeline state at 48 registers and the whole kernel under 128, i.e. FOUR resident CTAs (16 warps)
+// per SM: the FP64 pipe is fed by four warps per scheduler instead of two (measured: the 4-cell
+// variant ran at 35 % FP64 pipe utilisation, bound by issue stalls of its two warps).
+constexpr int kS2LaneCells = 2;
+constexpr int kS2StripCells = 32 * kS2LaneCells;                   // 64
+constexpr int kS2StripHalo = 4;                                    // cells; K <= 4
+constexpr int kS2HaloLanes = kS2StripHalo / kS2LaneCells;          // 2
+constexpr int kS2StripStride = kS2StripCells - 2 * kS2StripHalo;   // 56 owned cells per strip
+constexpr int kS2CtasPerSm = 4;
+constexpr int kS2MapWindowBytes = kS2StripCells * 2 + 16;
+constexpr int kS2FieldBytes = kS2StripCells * 8;                   // 512
+constexpr int kS2SlotBytes = 3 * kS2FieldBytes + kS2MapWindowBytes + 16;
+constexpr int kS2ScratchBytes = 32 * 2 * kS2LaneCells * 8;         // slow path: 2 components per lane
+constexpr int kS2WarpRingBytes = kRingDepth * kS2SlotBytes + kS2ScratchBytes + 64;   // + mbarriers
+static_assert(kS2SlotBytes % 16 == 0, "bulk copies need 16-byte aligned slots");
+static_assert(kS2LaneCells == 2, "the 32-bit lane map word and the double2 row accesses assume 2");
+
+// Row metadata, packed (the kernel keeps K + 3 of them in registers).
+struct RowTag {
+    unsigned ids;    // the 2 map entries of this lane's cells
+    unsigned bits;   // 0-4 material of the row's first cell, 5 row is not of one material,
+                     // 6 flagged, 7-9 classed (bit 7 + c: component c)
+    __device__ int uniform() const { return (bits & 32u) ? -1 : (int)(bits & 31u); }
+    __device__ bool flagged() const { return (bits & 64u) != 0; }
+    __device__ unsigned classed() const { return bits >> 7; }
+    // plain: one material, no boundary operation, no probe
+    __device__ bool plain() const { return bits < 32u; }
+    // steady: no table lookup, no probe, and either constant operations on at most ONE component of
+    // a row of one material, or several materials without any operation -- such rows take the
+    // branch-free body as long as every lane sees the same map word row after row (a wall, a constant
+    // source or a material interface along y; plain rows are the special case without any of it)
+    __device__ bool steady() const {
+        const unsigned cls = bits >> 7;
+        return (bits & 64u) == 0u && ((bits & 32u) ? cls == 0u : (cls & (cls - 1u)) == 0u);
+    }
+};
+
+// Metadata of the row in ring slot `src` (once per row, reused by all K stages). Lanes whose cells lie
+// beyond the dependency cone of the owned cells (`relevant` false: past the row end plus the strip
+// halo) do not vote: what they compute is never used.
+__device__ __forceinline__ RowTag s2_row_meta(const unsigned char *src, int map_off, int lane,
+                                              bool relevant) {
+    const unsigned raw = *reinterpret_cast<const unsigned *>(src + 3 * kS2FieldBytes + 2 * map_off +
+                                                             4 * lane);
+    const unsigned first = __shfl_sync(0xffffffffu, raw, 0) & kIdMask;
+    // irrelevant lanes take the row's first material and no flags
+    const unsigned idw = relevant ? raw : first * 0x00010001u;
+    RowTag m;
+    const bool uni = __all_sync(0xffffffffu, (idw & 0x001f001fu) == first * 0x00010001u);
+    m.ids = idw;
+    m.bits = first | (uni ? 0u : 32u);
+    if (__any_sync(0xffffffffu, (idw & 0xffe0ffe0u) != 0)) {
+        if (__any_sync(0xffffffffu, (idw & 0x00600060u) != 0)) m.bits |= 64u;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const unsigned mask = 0x00070007u << class_shift(c);
+            if (__any_sync(0xffffffffu, (idw & mask) != 0)) m.bits |= 128u << c;
+        }
+    }
+    return m;
+}
+
+// Slow path of this kernel (see stream_slow_cells): 2 cells per lane, 32-bit map word.
+__device__ __noinline__ void s2_slow_cells(const StepTables *__restrict__ tp, int first_comp,
+                                           int n_comp, long long sig, long long record_row,
+                                           long long cell0, unsigned ids, bool owned,
+                                           double *scratch) {
+    for (int k = 0; k < n_comp; ++k) {
+        const int comp = first_comp + k;
+        for (int c = 0; c < kS2LaneCells; ++c) {
+            const unsigned f = ids >> (16 * c);
+            if (!(f & (kFlagBound | kFlagProbe))) continue;
+            double v = scratch[kS2LaneCells * k + c];
+            if (f & kFlagBound) {
+                v = apply_bounds(tp->bound[comp], tp->rows, tp->signals, tp->sig_steps, sig,
+                                 cell0 + c, v);
+                scratch[kS2LaneCells * k + c] = v;
+            }
+            if ((f & kFlagProbe) && owned)
+                write_probes(tp->probe[comp], tp->rows, tp->ring + record_row * tp->n_slots,
+                             cell0 + c, v);
+        }
+    }
+}
+
+// One stage of the time pipeline on a STEADY row pair (rows q-1 and q of one material, no table
+// lookup, no probe): straight-line arithmetic, no branch. `cur` = row q at level s on entry and
+// row q-1 at level s+1 on exit; P/U/V = p (after boundaries), new vx, new vy of row q-1 (read),
+// Pn/Un/Vn = the same of row q (written: the state of the next row iteration).
+// CC >= 0: component CC carries constant operations v = alpha * v + value on some cells of the
+// strip; ca/cv hold them for this lane's cells, cells without one get alpha = 1, value = -0.0, which
+// returns v bit for bit (1 * v is exact and v + (-0.0) = v for every v, signed zeros included).
+// gx[c] = x-gradient coefficient of cell c-1 (gx[0]: the left-hand lane's last cell), gy[c], fy[c] =
+// y coefficients of cell c, fx[c] = x-divergence coefficient of cell c (fx[C]: the right-hand lane's
+// first cell): the same for rows q-1 and q, because steady rows repeat their map words.
+template <bool THERMAL, int CC>
+__device__ __forceinline__ void steady_stage(double (&cur)[3][kS2LaneCells],
+                                             const double (&P)[kS2LaneCells],
+                                             const double (&U)[kS2LaneCells],
+                                             const double (&V)[kS2LaneCells],
+                                             double (&Pn)[kS2LaneCells], double (&Un)[kS2LaneCells],
+                                             double (&Vn)[kS2LaneCells],
+                                             const double (&gx)[kS2LaneCells + 1],
+                                             const double (&gy)[kS2LaneCells],
+                                             const double (&fx)[kS2LaneCells + 1],
+                                             const double (&fy)[kS2LaneCells],
+                                             const double (&ca)[kS2LaneCells],
+                                             const double (&cv)[kS2LaneCells]) {
+    constexpr int C = kS2LaneCells;
+    if (CC == 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) cur[0][c] = add(mul(ca[c], cur[0][c]), cv[c]);
+    }
+    const double p_left = shfl_up1(cur[0][C - 1]);
+    double np[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const double pl = c ? cur[0][c - 1] : p_left;
+        const double dx_ = diff2(gx[c], pl, gx[c + 1], cur[0][c]);
+        const double dy_ = diff2(gy[c], P[c], gy[c], cur[0][c]);
+        Un[c] = THERMAL ? -dx_ : sub(cur[1][c], dx_);
+        Vn[c] = THERMAL ? -dy_ : sub(cur[2][c], dy_);
+        if (CC == 1) Un[c] = add(mul(ca[c], Un[c]), cv[c]);
+        if (CC == 2) Vn[c] = add(mul(ca[c], Vn[c]), cv[c]);
+    }
+    const double u_right = shfl_down1(U[0]);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const double ur = c < C - 1 ? U[c + 1] : u_right;
+        const double divx = diff2(fx[c], U[c], fx[c + 1], ur);
+        const double divy = diff2(fy[c], V[c], fy[c], Vn[c]);
+        np[c] = sub(P[c], add(divx, divy));
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        Pn[c] = cur[0][c];
+        cur[0][c] = np[c];
+        cur[1][c] = U[c];
+        cur[2][c] = V[c];
+    }
+}
+
 // THERMAL: Thermal2D (pyfds/thermal.py:92-107) -- same pipeline with the temperature as the only
 // state: the flux components are not read (q = -(A_q_t T) overwrites them, they are not accumulated)
 // and only stored when the host asks for them after the last step of a call.
+//
+// Row metadata is fetched two rows ahead of the arithmetic. While the next two rows and the K+1 rows
+// before them are PLAIN (one material, no boundary operation, no probe -- almost everywhere) rows
+// are consumed in pairs by a branch-free body of 2 x K stages in which the pipeline state alternates
+// between two register sets, so that no register is moved between row iterations; any other row
+// takes the general row iteration.
 template <int K, bool THERMAL>
-__global__ void __launch_bounds__(kStreamWarps * 32, kStreamCtasPerSm)
+__global__ void __launch_bounds__(kStreamWarps * 32, kS2CtasPerSm)
 stream2d_kernel(Stream2DArgs a) {
+    constexpr int C = kS2LaneCells;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double tabs[4][kMaxMaterials];   // FDS_TAB_GX, GY, FX, FY
     __shared__ double cls_alpha[3][kMaxClasses], cls_value[3][kMaxClasses];
@@ -164,189 +318,341 @@ stream2d_kernel(Stream2DArgs a) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nx = a.nx;
-    unsigned char *ring = smem_raw + warp * kWarpRingBytes;
-    double *scratch = reinterpret_cast<double *>(ring + kRingDepth * kSlotBytes) + lane * 8;
-    unsigned long long *bars =
-        reinterpret_cast<unsigned long long *>(ring + kRingDepth * kSlotBytes + kScratchBytes);
-
-    // shared-memory read pattern: two conflict-free 16-byte loads per field (lanes 4-7 of every
-    // quarter-warp take the upper half first)
-    const int swap = (lane >> 2) & 1;
-    const int off_a = lane * 32 + swap * 16, off_b = lane * 32 + (swap ^ 1) * 16;
-    unsigned phase_bits = 0;   // parity of every ring slot (the barriers live across tasks)
+    unsigned char *ring = smem_raw + warp * kS2WarpRingBytes;
+    double *scratch =
+        reinterpret_cast<double *>(ring + kRingDepth * kS2SlotBytes) + lane * 2 * C;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(
+        ring + kRingDepth * kS2SlotBytes + kS2ScratchBytes);
+    // rows travel in pairs: ring slots 2j and 2j+1 share mbarrier j (one wait, one refill per pair)
+    static_assert(kRingDepth % 2 == 0, "the ring holds whole row pairs");
+    unsigned phase_bits = 0;   // parity of every pair barrier (the barriers live across tasks)
 
     if (lane == 0) {
-        for (int d = 0; d < kRingDepth; ++d) mbar_init(&bars[d], 1);
+        for (int d = 0; d < kRingDepth / 2; ++d) mbar_init(&bars[d], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
 
     for (;;) {
-        // ---- next task: (strip, chunk of rows), handed out dynamically ---------------------------
+        // ---- next task: (strip, rows), handed out dynamically, most expensive first --------------
         int task = 0;
         if (lane == 0) task = atomicAdd(a.task_counter, 1);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= a.n_tasks) break;
-        const int strip = __ldg(a.strip_order + task / a.n_chunks);
-        const long long chunk = task % a.n_chunks;
-        const long long ys = a.row_begin + chunk * a.chunk_rows;
-        const long long ye = min(ys + (long long)a.chunk_rows, a.row_end);
-        const long long xs = (long long)strip * kStripStride - kStripHalo;   // column of lane 0
-        const long long r0 = ys - K, r1 = ye + K;                            // rows streamed in
+        const int4 tk = __ldg(a.tasks + task);
+        const int ys = tk.y, ye = tk.z;
+        const long long xs = (long long)tk.x * kS2StripStride - kS2StripHalo;   // column of lane 0
+        const int r0 = ys - K, r1 = ye + K;                                     // rows streamed in
 
-        auto issue = [&](long long r, int slot) {
-            const long long base = r * nx + xs;         // flat cell index of the strip start
-            const long long base8 = base & ~7LL;        // map entries: 16-byte aligned window
-            unsigned char *dst = ring + slot * kSlotBytes;
-            mbar_expect_tx(&bars[slot], (THERMAL ? 1 : 3) * kStripCells * 8 + kMapWindowBytes);
-            bulk_load(dst, a.in[0] + base, kStripCells * 8, &bars[slot]);
-            if (!THERMAL) {
-                bulk_load(dst + kStripCells * 8, a.in[1] + base, kStripCells * 8, &bars[slot]);
-                bulk_load(dst + 2 * kStripCells * 8, a.in[2] + base, kStripCells * 8, &bars[slot]);
+        // rows r, r+1 (r - r0 even) into ring slots `slot`, `slot` + 1 (slot even), one barrier
+        auto issue_pair = [&](int r, int slot) {
+            const int n_rows = r + 1 < r1 ? 2 : 1;
+            void *bar = &bars[slot >> 1];
+            mbar_expect_tx(bar, n_rows * ((THERMAL ? 1 : 3) * kS2FieldBytes + kS2MapWindowBytes));
+            long long base = (long long)r * nx + xs;   // flat cell index of the strip start
+            unsigned char *dst = ring + slot * kS2SlotBytes;
+            for (int h = 0; h < n_rows; ++h) {
+                bulk_load(dst, a.in[0] + base, kS2FieldBytes, bar);
+                if (!THERMAL) {
+                    bulk_load(dst + kS2FieldBytes, a.in[1] + base, kS2FieldBytes, bar);
+                    bulk_load(dst + 2 * kS2FieldBytes, a.in[2] + base, kS2FieldBytes, bar);
+                }
+                // map entries: 16-byte aligned window
+                bulk_load(dst + 3 * kS2FieldBytes, a.map + (base & ~7LL), kS2MapWindowBytes, bar);
+                base += nx;
+                dst += kS2SlotBytes;
             }
-            bulk_load(dst + 3 * kStripCells * 8, a.map + base8, kMapWindowBytes, &bars[slot]);
         };
         if (lane == 0)
-            for (int d = 0; d < kRingDepth && r0 + d < r1; ++d) issue(r0 + d, d);
+            for (int d = 0; d < kRingDepth && r0 + d < r1; d += 2) issue_pair(r0 + d, d);
 
         // pipeline state: per stage the previous row's p (after boundaries), new vx, new vy
-        double pb[K][4], un[K][4], vn[K][4];
-        RowInfo info[K + 1];
+        double pb[K][C], un[K][C], vn[K][C];
+        RowTag info[K + 1];
 #pragma unroll
         for (int s = 0; s < K; ++s)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) pb[s][c] = un[s][c] = vn[s][c] = 0.0;
+            for (int c = 0; c < C; ++c) pb[s][c] = un[s][c] = vn[s][c] = 0.0;
 #pragma unroll
-        for (int s = 0; s <= K; ++s) info[s] = RowInfo{0ull, 0, false, 0u};
+        for (int s = 0; s <= K; ++s) info[s] = RowTag{0u, 0u};
+        int run = 0;
 
-        // owned cells of this lane: the 120 inner cells of the strip that lie inside the row
-        const long long x0 = xs + 4 * lane;
-        const bool lane_owned = lane >= 1 && lane <= 30 && x0 < nx;
-        long long cell_r = r0 * nx + x0;    // flat index of this lane's first cell in row r
+        // owned cells of this lane: the 56 inner cells of the strip that lie inside the row
+        const long long x0 = xs + C * lane;
+        const bool lane_owned = lane >= kS2HaloLanes && lane < 32 - kS2HaloLanes && x0 < nx;
+        const bool lane_relevant = x0 < nx + kS2StripHalo;
+        long long cell_r = (long long)r0 * nx + x0;   // flat index of this lane's first cell in row r
         const int map_step = (int)(nx & 7LL);
-        int map_off = (int)((r0 * nx + xs) & 7LL);   // (r * nx + xs) & 7: entry offset in the window
+        int map_off = (int)(((long long)r0 * nx + xs) & 7LL);   // entry offset in the map window
 
-        int slot = 0;
-        for (long long r = r0; r < r1; ++r) {
-            mbar_wait(&bars[slot], (phase_bits >> slot) & 1u);
-            phase_bits ^= 1u << slot;
-            const unsigned char *src = ring + slot * kSlotBytes;
-            double cur[3][4];
+        // a lane's 2 cells are one 16-byte word: rows are read and written with 128-bit accesses,
+        // lane after lane, free of bank conflicts
+        auto load_row = [&](double (&cur)[3][C], const unsigned char *src) {
 #pragma unroll
             for (int f = 0; f < 3; ++f) {
                 if (THERMAL && f > 0) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) cur[f][c] = 0.0;
+                    cur[f][0] = cur[f][1] = 0.0;
                     continue;
                 }
-                const double2 va =
-                    *reinterpret_cast<const double2 *>(src + f * kStripCells * 8 + off_a);
-                const double2 vb =
-                    *reinterpret_cast<const double2 *>(src + f * kStripCells * 8 + off_b);
-                cur[f][0] = swap ? vb.x : va.x;
-                cur[f][1] = swap ? vb.y : va.y;
-                cur[f][2] = swap ? va.x : vb.x;
-                cur[f][3] = swap ? va.y : vb.y;
+                const double2 v =
+                    *reinterpret_cast<const double2 *>(src + f * kS2FieldBytes + lane * 16);
+                cur[f][0] = v.x;
+                cur[f][1] = v.y;
             }
-            const unsigned long long idw = *reinterpret_cast<const unsigned long long *>(
-                src + 3 * kStripCells * 8 + 2 * map_off + 8 * lane);
-            map_off = (map_off + map_step) & 7;
-            __syncwarp();
-            if (lane == 0 && r + kRingDepth < r1) issue(r + kRingDepth, slot);
-            if (++slot == kRingDepth) slot = 0;
+        };
+        // row `orow` at level K, held in `cur`; `o` = flat index of this lane's first cell in it
+        auto store_row = [&](const double (&cur)[3][C], int orow, long long o) {
+            if (lane_owned && orow >= ys && orow < ye) {
+#pragma unroll
+                for (int f = 0; f < 3; ++f) {
+                    if (THERMAL && f > 0 && !a.write_vector) continue;
+                    *reinterpret_cast<double2 *>(a.out[f] + o) = make_double2(cur[f][0], cur[f][1]);
+                }
+            }
+        };
 
-            // metadata of the new row (once per row, reused by all K stages)
+        // metadata is fetched two rows ahead of the arithmetic: m0 = row r, m1 = row r+1
+        int fetch_row = r0, fetch_slot = 0;
+        int arrived = r0;       // rows below this one have landed in the ring (always whole pairs)
+        auto await = [&](int row, int slot) {
+            if (row >= arrived) {
+                mbar_wait(&bars[slot >> 1], (phase_bits >> (slot >> 1)) & 1u);
+                phase_bits ^= 1u << (slot >> 1);
+                arrived += 2;
+            }
+        };
+        auto fetch = [&]() {
+            RowTag m = RowTag{0u, 32u};   // past the last row: never plain
+            if (fetch_row < r1) {
+                await(fetch_row, fetch_slot);
+                m = s2_row_meta(ring + fetch_slot * kS2SlotBytes, map_off, lane, lane_relevant);
+                map_off = (map_off + map_step) & 7;
+                if (++fetch_slot == kRingDepth) fetch_slot = 0;
+                ++fetch_row;
+            }
+            return m;
+        };
+        RowTag m0 = fetch(), m1 = fetch();
+        // What the pipeline computes from the rows above r0 (zero state) never reaches an owned row
+        // (the dependency cone of rows >= ys at level K ends at row r0 at level 0), so those rows
+        // may as well count as rows like the first one: a task whose first rows are steady starts in
+        // the branch-free body straight away.
+        if (m0.steady()) {
 #pragma unroll
-            for (int s = K; s > 0; --s) info[s] = info[s - 1];
+            for (int s = 0; s <= K; ++s) info[s] = m0;
+            run = K + 1;
+        }
+
+        int slot = 0;
+        int r = r0;
+        // ---- steady pairs: rows r-K-1 .. r+1 carry the same map words (one material, no table
+        // lookup, no probe, constant operations on component CC only, or none: CC = -1) -------------
+        // (slot even: rows r, r+1 are one ring pair; here fetch_row = r + 2)
+        auto steady_pairs = [&](auto cc_tag, auto uni_tag) {
+            constexpr int CC = decltype(cc_tag)::value;
+            constexpr bool UNI = decltype(uni_tag)::value;   // one material: warp-uniform coefficients
+            const unsigned my_ids = info[0].ids;
+            double gx[C + 1], gy[C], fx[C + 1], fy[C];
             {
-                const unsigned long long first = __shfl_sync(0xffffffffu, idw, 0) & kIdMask;
-                const bool uni = __all_sync(0xffffffffu, (idw & 0x001f001f001f001full) ==
-                                                             first * 0x0001000100010001ull);
-                info[0].ids = idw;
-                info[0].uniform = uni ? (int)first : -1;
-                info[0].flagged = __any_sync(0xffffffffu, (idw & 0x0060006000600060ull) != 0);
-                info[0].classed = 0u;
-                if (__any_sync(0xffffffffu, (idw & 0xff80ff80ff80ff80ull) != 0)) {
+                const unsigned left = __shfl_up_sync(0xffffffffu, my_ids, 1);
+                const unsigned right = __shfl_down_sync(0xffffffffu, my_ids, 1);
+                const unsigned material = info[0].bits & kIdMask;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const unsigned long long m = 0x0007000700070007ull << class_shift(c);
-                        if (__any_sync(0xffffffffu, (idw & m) != 0)) info[0].classed |= 1u << c;
+                for (int c = 0; c <= C; ++c) {
+                    // cell c-1 (c = 0: last cell of the left-hand lane) and cell c (c = C: first cell
+                    // of the right-hand lane)
+                    const unsigned below = c ? my_ids >> (16 * (c - 1)) : left >> (16 * (C - 1));
+                    const unsigned here = c < C ? my_ids >> (16 * c) : right;
+                    gx[c] = tabs[FDS_TAB_GX][UNI ? material : (below & kIdMask)];
+                    fx[c] = tabs[FDS_TAB_FX][UNI ? material : (here & kIdMask)];
+                    if (c < C) {
+                        gy[c] = tabs[FDS_TAB_GY][UNI ? material : (here & kIdMask)];
+                        fy[c] = tabs[FDS_TAB_FY][UNI ? material : (here & kIdMask)];
                     }
                 }
             }
+            double ca[C], cv[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const unsigned k =
+                    CC < 0 ? 0u : (my_ids >> (16 * c + class_shift(CC < 0 ? 0 : CC))) & 7u;
+                ca[c] = k ? cls_alpha[CC < 0 ? 0 : CC][k] : 1.0;
+                cv[c] = k ? cls_value[CC < 0 ? 0 : CC][k] : -0.0;
+            }
+            for (;;) {
+                double cur[3][C], pb1[K][C], un1[K][C], vn1[K][C];
+                load_row(cur, ring + slot * kS2SlotBytes);
+#pragma unroll
+                for (int s = 0; s < K; ++s)
+                    steady_stage<THERMAL, CC>(cur, pb[s], un[s], vn[s], pb1[s], un1[s], vn1[s], gx,
+                                              gy, fx, fy, ca, cv);
+                store_row(cur, r - K, cell_r - K * nx);
+
+                load_row(cur, ring + (slot + 1) * kS2SlotBytes);
+                __syncwarp();
+                if (lane == 0 && r + kRingDepth < r1) issue_pair(r + kRingDepth, slot);
+#pragma unroll
+                for (int s = 0; s < K; ++s)
+                    steady_stage<THERMAL, CC>(cur, pb1[s], un1[s], vn1[s], pb[s], un[s], vn[s], gx,
+                                              gy, fx, fy, ca, cv);
+                store_row(cur, r + 1 - K, cell_r + nx - K * nx);
+                // the window info[0..K] stays what it was: steady rows with these map words
+                cell_r += 2 * nx;
+                r += 2;
+                slot = slot + 2 == kRingDepth ? 0 : slot + 2;
+                // In here the lookahead is implied: rows r, r+1 have landed and been examined
+                // (fetch_row = r + 2); the three cursors are only brought up to date on the way out.
+                fetch_row = r;
+                fetch_slot = slot;
+                arrived = r;
+                if (r + 1 < r1) {
+                    // next pair: one vote instead of the full metadata
+                    mbar_wait(&bars[slot >> 1], (phase_bits >> (slot >> 1)) & 1u);
+                    phase_bits ^= 1u << (slot >> 1);
+                    arrived = r + 2;
+                    const unsigned char *src = ring + slot * kS2SlotBytes + 3 * kS2FieldBytes;
+                    const int map_off1 = (map_off + map_step) & 7;
+                    const unsigned raw0 =
+                        *reinterpret_cast<const unsigned *>(src + 2 * map_off + 4 * lane);
+                    const unsigned raw1 = *reinterpret_cast<const unsigned *>(
+                        src + kS2SlotBytes + 2 * map_off1 + 4 * lane);
+                    if (__all_sync(0xffffffffu,
+                                   !lane_relevant || (raw0 == my_ids && raw1 == my_ids))) {
+                        map_off = (map_off1 + map_step) & 7;
+                        continue;
+                    }
+                }
+                m0 = fetch();
+                m1 = fetch();
+                break;
+            }
+        };
+
+        while (r < r1) {
+            if (run > K && !(slot & 1) && m0.bits == info[0].bits && m1.bits == m0.bits &&
+                (m0.plain() ||
+                 __all_sync(0xffffffffu, m0.ids == info[0].ids && m1.ids == info[0].ids))) {
+                using std::integral_constant;
+                if (m0.bits & 32u)
+                    steady_pairs(integral_constant<int, -1>{}, integral_constant<bool, false>{});
+                else
+                    switch (m0.classed()) {
+                        case 0u:
+                            steady_pairs(integral_constant<int, -1>{}, integral_constant<bool, true>{});
+                            break;
+                        case 1u:
+                            steady_pairs(integral_constant<int, 0>{}, integral_constant<bool, true>{});
+                            break;
+                        case 2u:
+                            steady_pairs(integral_constant<int, 1>{}, integral_constant<bool, true>{});
+                            break;
+                        default:
+                            steady_pairs(integral_constant<int, 2>{}, integral_constant<bool, true>{});
+                            break;
+                    }
+                continue;
+            }
+
+            // ---- general row iteration -----------------------------------------------------------
+            double cur[3][C];
+            load_row(cur, ring + slot * kS2SlotBytes);
+            __syncwarp();
+            // the pair of ring slots is free once its second row has been read
+            if (lane == 0 && (slot & 1) && r - 1 + kRingDepth < r1)
+                issue_pair(r - 1 + kRingDepth, slot - 1);
 
 #pragma unroll
+            for (int s = K; s > 0; --s) info[s] = info[s - 1];
+            info[0] = m0;
+            // run = rows in a row, the last one being info[0], that are steady with the same map words
+            if (!info[0].steady())
+                run = 0;
+            else if (run > 0 && info[0].bits == info[1].bits &&
+                     (info[0].plain() || __all_sync(0xffffffffu, info[0].ids == info[1].ids)))
+                ++run;
+            else
+                run = 1;
+
+            // The K stages run as a ROLLED loop over one copy of the stage code (this path is rare: code
+            // size and register pressure matter more than the moves): stage s works on pb[0], un[0],
+            // vn[0] and on info[0], info[1]; after each stage the state and the tags rotate by one
+            // place. K rotations put the K state entries back where they belong, the K + 1 tags need
+            // one more after the loop.
+#pragma unroll 1
             for (int s = 0; s < K; ++s) {
                 // stage s: cur = row q = r - s at level s  ->  cur = row q-1 at level s+1
-                const RowInfo &ri = info[s], &rp = info[s + 1];
+                const RowTag ri = info[0], rp = info[1];
+                const int ri_uniform = ri.uniform();
+                const int q = r - s;
 
                 // 1. boundaries and probes of p (row q)
-                if (ri.classed & 1u) {
+                if (ri.classed() & 1u) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        cur[0][c] = apply_class(cls_alpha, cls_value, 0,
-                                                (unsigned)(ri.ids >> (16 * c)), cur[0][c]);
+                    for (int c = 0; c < C; ++c)
+                        cur[0][c] = apply_class(cls_alpha, cls_value, 0, ri.ids >> (16 * c),
+                                                cur[0][c]);
                 }
-                if (ri.flagged) {
-                    const long long q = r - s;
+                if (ri.flagged()) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) scratch[c] = cur[0][c];
-                    stream_slow_cells(a.tables, 0, 1, a.sig_index + s, a.ring_row + s,
-                                      cell_r - s * nx, ri.ids,
-                                      lane_owned && q >= ys && q < ye, scratch);
+                    for (int c = 0; c < C; ++c) scratch[c] = cur[0][c];
+                    s2_slow_cells(a.tables, 0, 1, a.sig_index + s, a.ring_row + s, cell_r - s * nx,
+                                  ri.ids, lane_owned && q >= ys && q < ye, scratch);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) cur[0][c] = scratch[c];
+                    for (int c = 0; c < C; ++c) cur[0][c] = scratch[c];
                 }
 
                 // 2. new vx, vy of row q (backward differences of p), their boundaries and probes;
                 // 3. new p of row q-1 (forward differences of the new vx, vy).
                 // `coef` yields the material coefficient of a cell: gx(c) for row q, cell c-1 (c = 0
                 // is the left-hand lane's last cell); gyc/fyc(c) row q; gyp/fxp/fyp(c) row q-1
-                // (fxp(4) is the right-hand lane's first cell).
-                double nu[4], nv[4], np[4];
+                // (fxp(C) is the right-hand lane's first cell).
+                double nu[C], nv[C], np[C];
                 auto math = [&](const auto &coef) {
-                    const double p_left = shfl_up1(cur[0][3]);
+                    const double p_left = shfl_up1(cur[0][C - 1]);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
+                    for (int c = 0; c < C; ++c) {
                         const double pl = c ? cur[0][c - 1] : p_left;
                         const double dx_ = diff2(coef.gx(c), pl, coef.gx(c + 1), cur[0][c]);
-                        const double dy_ = diff2(coef.gyp(c), pb[s][c], coef.gyc(c), cur[0][c]);
+                        const double dy_ = diff2(coef.gyp(c), pb[0][c], coef.gyc(c), cur[0][c]);
                         nu[c] = THERMAL ? -dx_ : sub(cur[1][c], dx_);
                         nv[c] = THERMAL ? -dy_ : sub(cur[2][c], dy_);
                     }
-                    if (ri.classed & 2u) {
+                    if (ri.classed() & 2u) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            nu[c] = apply_class(cls_alpha, cls_value, 1,
-                                                (unsigned)(ri.ids >> (16 * c)), nu[c]);
+                        for (int c = 0; c < C; ++c)
+                            nu[c] = apply_class(cls_alpha, cls_value, 1, ri.ids >> (16 * c), nu[c]);
                     }
-                    if (ri.classed & 4u) {
+                    if (ri.classed() & 4u) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            nv[c] = apply_class(cls_alpha, cls_value, 2,
-                                                (unsigned)(ri.ids >> (16 * c)), nv[c]);
+                        for (int c = 0; c < C; ++c)
+                            nv[c] = apply_class(cls_alpha, cls_value, 2, ri.ids >> (16 * c), nv[c]);
                     }
-                    if (ri.flagged) {
-                        const long long q = r - s;
+                    if (ri.flagged()) {
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) { scratch[c] = nu[c]; scratch[4 + c] = nv[c]; }
-                        stream_slow_cells(a.tables, 1, 2, a.sig_index + s, a.ring_row + s,
-                                          cell_r - s * nx, ri.ids,
-                                          lane_owned && q >= ys && q < ye, scratch);
+                        for (int c = 0; c < C; ++c) {
+                            scratch[c] = nu[c];
+                            scratch[C + c] = nv[c];
+                        }
+                        s2_slow_cells(a.tables, 1, 2, a.sig_index + s, a.ring_row + s,
+                                      cell_r - s * nx, ri.ids, lane_owned && q >= ys && q < ye,
+                                      scratch);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) { nu[c] = scratch[c]; nv[c] = scratch[4 + c]; }
+                        for (int c = 0; c < C; ++c) {
+                            nu[c] = scratch[c];
+                            nv[c] = scratch[C + c];
+                        }
                     }
-                    const double u_right = shfl_down1(un[s][0]);
+                    const double u_right = shfl_down1(un[0][0]);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const double ur = c < 3 ? un[s][c + 1] : u_right;
-                        const double divx = diff2(coef.fxp(c), un[s][c], coef.fxp(c + 1), ur);
-                        const double divy = diff2(coef.fyp(c), vn[s][c], coef.fyc(c), nv[c]);
-                        np[c] = sub(pb[s][c], add(divx, divy));
+                    for (int c = 0; c < C; ++c) {
+                        const double ur = c < C - 1 ? un[0][c + 1] : u_right;
+                        const double divx = diff2(coef.fxp(c), un[0][c], coef.fxp(c + 1), ur);
+                        const double divy = diff2(coef.fyp(c), vn[0][c], coef.fyc(c), nv[c]);
+                        np[c] = sub(pb[0][c], add(divx, divy));
                     }
                 };
-                if (ri.uniform >= 0 && ri.uniform == rp.uniform) {
-                    // all 256 cells of rows q-1 and q share one material: 4 coefficients in registers
+                if (ri_uniform >= 0 && ri_uniform == rp.uniform()) {
+                    // all cells of rows q-1 and q share one material: 4 coefficients in registers
                     struct {
                         double g0, g1, f0, f1;
                         __device__ double gx(int) const { return g0; }
@@ -355,22 +661,23 @@ stream2d_kernel(Stream2DArgs a) {
                         __device__ double fxp(int) const { return f0; }
                         __device__ double fyp(int) const { return f1; }
                         __device__ double fyc(int) const { return f1; }
-                    } coef{tabs[FDS_TAB_GX][ri.uniform], tabs[FDS_TAB_GY][ri.uniform],
-                           tabs[FDS_TAB_FX][ri.uniform], tabs[FDS_TAB_FY][ri.uniform]};
+                    } coef{tabs[FDS_TAB_GX][ri_uniform], tabs[FDS_TAB_GY][ri_uniform],
+                           tabs[FDS_TAB_FX][ri_uniform], tabs[FDS_TAB_FY][ri_uniform]};
                     math(coef);
                 } else {
                     struct {
                         const double (*tabs)[kMaxMaterials];
-                        unsigned long long cur_ids, prev_ids, left, right;
+                        unsigned cur_ids, prev_ids, left, right;
                         __device__ int mc(int c) const { return (int)(cur_ids >> (16 * c)) & kIdMask; }
                         __device__ int mp(int c) const { return (int)(prev_ids >> (16 * c)) & kIdMask; }
                         __device__ double gx(int c) const {
-                            return tabs[FDS_TAB_GX][c ? mc(c - 1) : (int)((left >> 48) & kIdMask)];
+                            return tabs[FDS_TAB_GX][c ? mc(c - 1)
+                                                      : (int)((left >> (16 * (C - 1))) & kIdMask)];
                         }
                         __device__ double gyc(int c) const { return tabs[FDS_TAB_GY][mc(c)]; }
                         __device__ double gyp(int c) const { return tabs[FDS_TAB_GY][mp(c)]; }
                         __device__ double fxp(int c) const {
-                            return tabs[FDS_TAB_FX][c < 4 ? mp(c) : (int)(right & kIdMask)];
+                            return tabs[FDS_TAB_FX][c < C ? mp(c) : (int)(right & kIdMask)];
                         }
                         __device__ double fyp(int c) const { return tabs[FDS_TAB_FY][mp(c)]; }
                         __device__ double fyc(int c) const { return tabs[FDS_TAB_FY][mc(c)]; }
@@ -380,32 +687,44 @@ stream2d_kernel(Stream2DArgs a) {
                     math(coef);
                 }
 
-                // 4. hand row q-1 (level s+1) to the next stage, keep row q for the next iteration
+                // 4. hand row q-1 (level s+1) to the next stage, keep row q for the next iteration,
+                //    rotate: stage s+1 finds its state at index 0
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < C; ++c) {
                     const double keep_p = cur[0][c];
                     cur[0][c] = np[c];
-                    cur[1][c] = un[s][c];
-                    cur[2][c] = vn[s][c];
-                    pb[s][c] = keep_p;
-                    un[s][c] = nu[c];
-                    vn[s][c] = nv[c];
+                    cur[1][c] = un[0][c];
+                    cur[2][c] = vn[0][c];
+#pragma unroll
+                    for (int j = 0; j + 1 < K; ++j) {
+                        pb[j][c] = pb[j + 1][c];
+                        un[j][c] = un[j + 1][c];
+                        vn[j][c] = vn[j + 1][c];
+                    }
+                    pb[K - 1][c] = keep_p;
+                    un[K - 1][c] = nu[c];
+                    vn[K - 1][c] = nv[c];
                 }
+                {
+                    const RowTag first = info[0];
+#pragma unroll
+                    for (int j = 0; j < K; ++j) info[j] = info[j + 1];
+                    info[K] = first;
+                }
+            }
+            {
+                const RowTag first = info[0];
+#pragma unroll
+                for (int j = 0; j < K; ++j) info[j] = info[j + 1];
+                info[K] = first;
             }
 
-            // row r-K at level K
-            const long long orow = r - K;
-            if (lane_owned && orow >= ys && orow < ye) {
-                const long long o = cell_r - K * nx;
-#pragma unroll
-                for (int f = 0; f < 3; ++f) {
-                    if (THERMAL && f > 0 && !a.write_vector) continue;
-                    *reinterpret_cast<double2 *>(a.out[f] + o) = make_double2(cur[f][0], cur[f][1]);
-                    *reinterpret_cast<double2 *>(a.out[f] + o + 2) =
-                        make_double2(cur[f][2], cur[f][3]);
-                }
-            }
+            store_row(cur, r - K, cell_r - K * nx);   // row r-K at level K
             cell_r += nx;
+            ++r;
+            if (++slot == kRingDepth) slot = 0;
+            m0 = m1;
+            m1 = fetch();
         }
     }
 }

@@ -65,11 +65,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) streamv_kernel(StreamVAr
         if (lane == 0) task = atomicAdd(a.task_counter, 1);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= a.n_tasks) break;
-        const int strip = __ldg(a.strip_order + task / a.n_chunks);
-        const long long chunk = task % a.n_chunks;
-        const long long ys = a.row_begin + chunk * a.chunk_rows;
-        const long long ye = min(ys + (long long)a.chunk_rows, a.row_end);
-        const long long xs = (long long)strip * kStripStride - kStripHalo;
+        const int4 tk = __ldg(a.tasks + task);
+        const long long ys = tk.y, ye = tk.z;
+        const long long xs = (long long)tk.x * kStripStride - kStripHalo;
         const long long r0 = ys - kLag, r1 = ye + kLag;
 
         auto issue = [&](long long r, int slot) {
