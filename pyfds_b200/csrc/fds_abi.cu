@@ -561,8 +561,8 @@ void invalidate_plans(fds_ctx *ctx) {
 //   general_weight times (census: rows that are not steady, each of which sends about k + 3 rows
 //   through the general iteration); overhead = rows streamed in addition to the owned ones
 //   (pipeline fill, ring fill).
-// For R = 1, 2, ... rounds the smallest cost C is found for which the tasks fit R * slots; the R with
-// the smallest makespan R * C wins. Strips without general rows are cut evenly, the others where the
+// The number of rounds R follows from a target task height; the smallest cost C is then found for
+// which the tasks fit R * slots. Strips without general rows are cut evenly, the others where the
 // accumulated cost crosses the multiples of their share. Tasks of the latter are handed out first,
 // the rest chunk-major (dynamic distribution absorbs what the model misses).
 int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int k, int lag_rows) {
@@ -609,23 +609,23 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
         const long long h = std::min<long long>(ctx->chunk_rows, rows);
         best_count.assign((size_t)n_strips, (rows + h - 1) / h);
     } else {
-        double best_makespan = -1;
-        for (int rounds = 1; rounds <= 8; ++rounds) {
-            double lo = overhead + (double)min_rows, hi = general_weight * (double)rows + overhead;
-            if (tasks_for(lo) <= rounds * slots) hi = lo;
-            for (int it = 0; it < 50 && hi - lo > 0.01; ++it) {
-                const double mid = 0.5 * (lo + hi);
-                if (tasks_for(mid) <= rounds * slots) hi = mid; else lo = mid;
-            }
-            const double n = tasks_for(hi);
-            // fewer tasks than slots: one round of whatever the tallest task costs
-            const double makespan = (n <= slots ? 1 : rounds) * hi;
-            if (best_makespan < 0 || makespan < best_makespan * 0.995) {
-                best_makespan = makespan;
-                best_count = count;
-            }
-            if (n <= slots) break;
+        // Rounds: SMs do not run at one speed (measured 16384^2 on B200: 1 round of 2048-row tasks 299,
+        // 4 rounds 361, 16 rounds of 128-row tasks 401 Gcell-updates/s -- a quarter of the time was
+        // the tail of the slowest SMs), so tasks stay about kTargetRows tall and the dynamic
+        // distribution evens the SMs out; shorter tasks pay more for the rows streamed twice.
+        double target_rows = ctx->use_streamv ? 64.0 : 128.0;
+        if (const char *env = getenv("FDS_TARGET_ROWS")) target_rows = std::max(8.0, atof(env));
+        double total_cost = 0;
+        for (int s = 0; s < n_strips; ++s) total_cost += strip_cost[(size_t)s];
+        const int rounds = (int)std::max(1.0, std::floor(total_cost / slots / target_rows + 0.5));
+        double lo = overhead + (double)min_rows, hi = general_weight * (double)rows + overhead;
+        if (tasks_for(lo) <= rounds * slots) hi = lo;
+        for (int it = 0; it < 50 && hi - lo > 0.01; ++it) {
+            const double mid = 0.5 * (lo + hi);
+            if (tasks_for(mid) <= rounds * slots) hi = mid; else lo = mid;
         }
+        tasks_for(hi);
+        best_count = count;
     }
     struct Item { int strip; long long ys, ye; double cost; };
     std::vector<Item> items;
@@ -655,8 +655,14 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
     // memory: DRAM pages and the halo columns shared by two strips are reused while they are hot
     long long max_count = 0;
     for (int s = 0; s < n_strips; ++s) max_count = std::max(max_count, best_count[(size_t)s]);
-    for (long long c = 0; c < max_count; ++c) {
-        for (int s = 0; s < n_strips; ++s) {
+    // (strip-major, FDS_TASK_ORDER=s, measured 3-4 % slower on every configuration)
+    bool strip_major = false;
+    if (const char *env = getenv("FDS_TASK_ORDER")) strip_major = env[0] == 's';
+    const long long outer = strip_major ? n_strips : max_count, inner = strip_major ? max_count : n_strips;
+    for (long long o = 0; o < outer; ++o) {
+        for (long long i = 0; i < inner; ++i) {
+            const int s = (int)(strip_major ? o : i);
+            const long long c = strip_major ? i : o;
             const long long n = best_count[(size_t)s];
             if (c >= n) continue;
             if (ctx->chunk_rows > 0) {   // forced height (tests): fixed chunks, a short last one
