@@ -65,31 +65,42 @@ class ClockSampler:
 
     def __init__(self, device):
         self.device = device
-        self.lines = []
+        self.lines = []          # (arrival time, csv line)
         self.proc = None
 
-    def start(self):
+    def start(self, wait=8.0):
+        """Launches nvidia-smi in loop mode and returns once its first sample has arrived (start-up
+        takes longer than a short timed region, the more GPUs the longer)."""
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.device), '--query-gpu=' + self.QUERY,
-                 '--format=csv,noheader,nounits', '-lms', '100'],
+                 '--format=csv,noheader,nounits', '-lms', '25'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+            return
+        deadline = time.perf_counter() + wait
+        while not self.lines and time.perf_counter() < deadline:
+            time.sleep(0.01)
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Clocks and throttle reasons of the samples that arrived in [t0, t1] (a sample describes
+        the instant it was taken, just before its arrival); all samples if none fell inside."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
+        rows = list(self.lines)
+        inside = [line for at, line in rows if t0 is not None and t0 <= at <= t1 + 0.03]
+        chosen = inside or [line for _, line in rows]
         sm, sm_max, reasons = [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for line in self.lines:
+        for line in chosen:
             parts = [p.strip() for p in line.split(',')]
             if len(parts) < 9:
                 continue
@@ -103,7 +114,8 @@ class ClockSampler:
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None,
                 'sm_max_mhz': max(sm_max) if sm_max else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+                'reasons': sorted(reasons), 'samples': len(sm),
+                'samples_in_timed_region': len(inside)}
 
 
 def measured_peak():
@@ -187,8 +199,8 @@ def run_reference(args, rank, world):
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument('--gpus', type=int, default=1)
-    parser.add_argument('--steps', type=int, default=200)
-    parser.add_argument('--warmup', type=int, default=20)
+    parser.add_argument('--steps', type=int, default=2000)
+    parser.add_argument('--warmup', type=int, default=100)
     parser.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     parser.add_argument('--size', type=int, default=4096, help='grid is size x size per GPU')
     parser.add_argument('--kernel', type=int, default=0, help='0 auto, 1 one-step, 2 streaming')
@@ -239,16 +251,18 @@ def main():
         if dist is not None:
             dist.barrier()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     engine.step_async(0, args.warmup)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     t0 = time.perf_counter()
     engine.step_async(args.warmup, args.steps)
     engine.sync()
-    wall = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    wall = t1 - t0
     device_ms = engine.last_step_ms()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
     barrier()
     launches, steps_per_launch, kernel = engine.last_launch_info()
 

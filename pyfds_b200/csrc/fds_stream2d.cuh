@@ -406,7 +406,10 @@ stream2d_kernel(Stream2DArgs a) {
 #pragma unroll
                 for (int f = 0; f < 3; ++f) {
                     if (THERMAL && f > 0 && !a.write_vector) continue;
-                    *reinterpret_cast<double2 *>(a.out[f] + o) = make_double2(cur[f][0], cur[f][1]);
+                    // streaming store: the rows are not read again by this launch and should not
+                    // evict what little the L1 holds (spilled loop counters); measured +2 %
+                    __stcs(reinterpret_cast<double2 *>(a.out[f] + o),
+                           make_double2(cur[f][0], cur[f][1]));
                 }
             }
         };
