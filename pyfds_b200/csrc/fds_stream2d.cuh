@@ -1,24 +1,35 @@
-// Streaming multi-step kernel for the lossless Acoustic2D leapfrog (pyfds/acoustics.py:111-128):
-// K time steps per launch with ONE read and ONE write of the state (temporal blocking).
+// Streaming multi-step kernel for the lossless Acoustic2D leapfrog (pyfds/acoustics.py:111-128) and
+// for Thermal2D (pyfds/thermal.py:92-107): K time steps per launch with ONE read and ONE write of the
+// state (temporal blocking).
 //
 // Work decomposition -- every warp is autonomous, there is no block-level synchronisation in the loop:
-//   * a warp owns an x-strip of 120 cells and a chunk of rows; it streams the strip (128 cells wide:
+//   * a warp owns an x-strip of 56 cells and a chunk of rows; it streams the strip (64 cells wide:
 //     4 halo cells either side) row by row through a K-stage time pipeline held in REGISTERS.
 //     Stage t receives row q at time level t and emits row q-1 at level t+1, so after K stages the
 //     warp stores row r-K at level K while row r is being read. Per stage only three row-fragments
-//     stay live (p after boundaries, new vx, new vy of the previous row): 24 registers per lane.
-//   * each lane holds 4 consecutive cells; the x-neighbours that live in the adjacent lane travel by
-//     warp shuffle (p to the right-hand lane for the backward difference, new vx to the left-hand
-//     lane for the forward difference). The outermost lanes compute garbage that never reaches the
-//     120 owned cells: the dependency cone grows one cell per step and K <= 4.
-//   * rows are fetched by the bulk-copy engine (TMA, cp.async.bulk + mbarrier) into a per-warp ring of
-//     shared-memory slots, kRingDepth rows ahead of the arithmetic, so DRAM latency is hidden without
-//     spending registers on loads in flight. Strips are addressed by flat cell index, which gives the
-//     reference's row wrap (pyfds/fields.py:290-297) and the zero padding at the grid ends for free.
-//   * material coefficients come from a 4 x 64 table in shared memory; rows whose 128 cells share one
-//     material (almost all) take a warp-uniform fast path with the four coefficients in registers.
-//   * boundary operations, sources and probes are applied inside the stages at the right time level
-//     (per-cell flag bits in the material map byte, slow path only where a flag is set).
+//     stay live (p after boundaries, new vx, new vy of the previous row): 12 registers per lane.
+//   * each lane holds 2 consecutive cells (one 16-byte word); the x-neighbours that live in the
+//     adjacent lane travel by warp shuffle (p to the right-hand lane for the backward difference, new
+//     vx to the left-hand lane for the forward difference). The two outermost lanes either side
+//     compute garbage that never reaches the 56 owned cells: the dependency cone grows one cell per
+//     step and K <= 4. Two cells per lane keep the kernel at 128 registers, i.e. four CTAs = 16 warps
+//     per SM (a 4-cell variant with 2 CTAs per SM ran the FP64 pipe at 35 %, this one at 52 %).
+//   * rows are fetched in pairs by the bulk-copy engine (TMA, cp.async.bulk + mbarrier) into a
+//     per-warp ring of shared-memory slots, two pairs ahead of the arithmetic, so DRAM latency is
+//     hidden without spending registers on loads in flight. Strips are addressed by flat cell index,
+//     which gives the reference's row wrap (pyfds/fields.py:290-297) and the zero padding at the grid
+//     ends for free.
+//   * STEADY rows -- the lane's map word repeats row after row, nothing needs a table lookup -- run
+//     through a branch-free body that consumes two rows per iteration with the pipeline state
+//     alternating between two register sets (no register moves between iterations). Five
+//     instantiations: one material (coefficients warp-uniform) with constant boundary operations on
+//     no component or on exactly one (applied to all cells as v = alpha*v + value, the identity
+//     being alpha = 1, value = -0.0), and several materials without operations (per-lane
+//     coefficients). Everything else -- rows around a change of the map, sources with signals,
+//     probes -- takes the general row iteration: one rolled copy of the stage code with per-cell
+//     coefficient lookups, inline classes and the table slow path.
+//   * tasks (strip, rows) come from a host-built table balanced with a device census of the rows that
+//     are not steady (fds_abi.cu: build_stream_plan) and are handed out dynamically.
 //
 // Arithmetic is the same sequence of __dmul_rn/__dadd_rn as the one-step kernel, so results are
 // bitwise identical to it and to the reference (tests/test_gpu_parity.py).
@@ -30,6 +41,7 @@
 
 namespace fds {
 
+// ---- shared with fds_streamv.cuh (viscous / axisymmetric kernel: 4 cells per lane, 128-cell strips)
 constexpr int kStripCells = 128;     // cells a warp streams per row (4 per lane)
 constexpr int kStripHalo = 4;        // halo cells either side = one lane
 constexpr int kStripStride = kStripCells - 2 * kStripHalo;   // 120 owned cells per strip

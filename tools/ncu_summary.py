@@ -26,6 +26,9 @@ WANT = [
     'sm__cycles_elapsed.avg', 'smsp__cycles_active.avg',
     'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
     'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio',
+    'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio',
+    'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
     'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
     'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
     'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
