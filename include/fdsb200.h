@@ -189,6 +189,12 @@ int fds_last_launch_info(fds_ctx *ctx, int64_t *launches, int64_t *steps_per_lau
                          const char **kernel_name);
 /* Bytes of device memory held by the context. */
 int64_t fds_device_bytes(const fds_ctx *ctx);
+/* Diagnostics of the streaming kernel, accumulated since fds_create when the environment variable
+ * FDS_STREAM_STATS is set (all zero otherwise): out[0..4] entries into the branch-free row-pair body
+ * by variant (no boundary operation, constant operations on component 0 / 1 / 2, several materials),
+ * out[5] rows that took the general row iteration, out[6] rows streamed in total. Test support: no
+ * reference counterpart. */
+int fds_stream_stats(fds_ctx *ctx, int64_t out[8]);
 
 #ifdef __cplusplus
 }

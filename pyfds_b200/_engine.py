@@ -92,6 +92,7 @@ def load_library():
         'fds_last_launch_info': (ct.c_int, [p, ct.POINTER(i64), ct.POINTER(i64),
                                             ct.POINTER(ct.c_char_p)]),
         'fds_device_bytes': (i64, [p]),
+        'fds_stream_stats': (ct.c_int, [p, ct.POINTER(i64)]),
     }
     for name, (restype, argtypes) in sigs.items():
         fn = getattr(lib, name)
@@ -225,6 +226,13 @@ class Engine:
 
     def device_bytes(self):
         return self.lib.fds_device_bytes(self.handle)
+
+    def stream_stats(self):
+        """Counters of the streaming kernel (all zero unless FDS_STREAM_STATS was set at creation):
+        entries into the branch-free body by variant [0..4], general rows [5], rows streamed [6]."""
+        out = (ct.c_int64 * 8)()
+        self._check(self.lib.fds_stream_stats(self.handle, out))
+        return list(out)
 
     def peer_export(self):
         buf = (ct.c_uint8 * (7 * 64))()

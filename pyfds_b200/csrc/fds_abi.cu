@@ -161,6 +161,7 @@ struct fds_ctx {
     bool use_tile2d = false;   // shared-memory tile kernel selected (one step per launch)
     bool use_streamv = false;  // streaming kernel of the viscous / axisymmetric acoustic models
     StepTables *d_tables = nullptr;   // device copy of the tables for the streaming kernel's slow path
+    unsigned long long *stream_stats = nullptr;   // FDS_STREAM_STATS: counters of the streaming kernel
     int *task_counters = nullptr;     // pool of zeroed work counters, one per streaming launch
     int next_counter = 0;
     int chunk_rows = 0;       // rows per streaming task (0 = heuristic)
@@ -700,9 +701,9 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
     return 0;
 }
 
-template <int K, bool THERMAL>
-int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
-    auto kernel = stream2d_kernel<K, THERMAL>;
+template <int K, bool THERMAL, bool STATS>
+int launch_stream2d_as(fds_ctx *ctx, const Stream2DArgs &a) {
+    auto kernel = stream2d_kernel<K, THERMAL, STATS>;
     const int smem = kStreamWarps * kS2WarpRingBytes;
     static bool configured = false;
     if (!configured) {
@@ -715,6 +716,12 @@ int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
     kernel<<<(unsigned)ctas, kStreamWarps * 32, smem, ctx->stream>>>(a);
     FDS_CUDA(ctx, cudaGetLastError());
     return 0;
+}
+
+template <int K, bool THERMAL>
+int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
+    return a.stats ? launch_stream2d_as<K, THERMAL, true>(ctx, a)
+                   : launch_stream2d_as<K, THERMAL, false>(ctx, a);
 }
 
 template <int K, bool AXI, bool VISC>
@@ -754,6 +761,7 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     }
     a.tasks = (const int4 *)plan->tasks;
     a.n_tasks = plan->n_tasks;
+    a.stats = ctx->stream_stats;
     a.task_counter = next_counter(ctx);
     if (!a.task_counter) return fail(ctx, "stream2d: counter reset failed");
     a.map = ctx->map + ctx->pad + ctx->halo;
@@ -1281,6 +1289,8 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
     FDS_TRY(dev_alloc(ctx, (void **)&ctx->flags, 4 * sizeof(unsigned), true));
     FDS_TRY(dev_alloc(ctx, (void **)&ctx->d_tables, sizeof(StepTables), true));
     FDS_TRY(dev_alloc(ctx, (void **)&ctx->task_counters, sizeof(int) * kCounterPool, true));
+    if (getenv("FDS_STREAM_STATS"))
+        FDS_TRY(dev_alloc(ctx, (void **)&ctx->stream_stats, sizeof(unsigned long long) * 8, true));
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         ctx->err = "device initialisation failed";
         return bail(0);
@@ -1314,6 +1324,7 @@ void fds_destroy(fds_ctx *ctx) {
     if (ctx->flags) cudaFree(ctx->flags);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
     if (ctx->task_counters) cudaFree(ctx->task_counters);
+    if (ctx->stream_stats) cudaFree(ctx->stream_stats);
     for (int c = 0; c < 3; ++c) {
         DevArray *arrays[] = {&ctx->bcells[c], &ctx->boffsets[c], &ctx->balpha[c], &ctx->bvalue[c],
                               &ctx->bsignal[c], &ctx->pcells[c], &ctx->pslots[c],
@@ -1698,5 +1709,15 @@ int fds_last_launch_info(fds_ctx *ctx, int64_t *launches, int64_t *steps_per_lau
 }
 
 int64_t fds_device_bytes(const fds_ctx *ctx) { return ctx ? ctx->device_bytes : 0; }
+
+int fds_stream_stats(fds_ctx *ctx, int64_t out[8]) {
+    if (!ctx) return fail(ctx, "fds_stream_stats: null context");
+    for (int k = 0; k < 8; ++k) out[k] = 0;
+    if (!ctx->stream_stats) return 0;
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FDS_CUDA(ctx, cudaMemcpy(out, ctx->stream_stats, sizeof(int64_t) * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
 
 }  // extern "C"

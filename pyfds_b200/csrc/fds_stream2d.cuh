@@ -76,6 +76,10 @@ struct Stream2DArgs {
     long long sig_index;   // first step - sig_first_step
     long long ring_row;    // probe record of the first step
     int write_vector;      // thermal: store the flux components of the last step as well
+    // optional counters (nullptr unless FDS_STREAM_STATS is set): [0..4] entries into the branch-free
+    // body by variant (no operation, operations on component 0 / 1 / 2, several materials),
+    // [5] rows through the general row iteration, [6] rows streamed in total
+    unsigned long long *stats;
 };
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) {
@@ -313,7 +317,9 @@ __device__ __forceinline__ void steady_stage(double (&cur)[3][kS2LaneCells],
 // are consumed in pairs by a branch-free body of 2 x K stages in which the pipeline state alternates
 // between two register sets, so that no register is moved between row iterations; any other row
 // takes the general row iteration.
-template <int K, bool THERMAL>
+// STATS: count in a.stats what the rows went through (tests only: a separate instantiation, so that
+// the counters cannot disturb the register allocation of the production kernel).
+template <int K, bool THERMAL, bool STATS = false>
 __global__ void __launch_bounds__(kStreamWarps * 32, kS2CtasPerSm)
 stream2d_kernel(Stream2DArgs a) {
     constexpr int C = kS2LaneCells;
@@ -377,6 +383,7 @@ stream2d_kernel(Stream2DArgs a) {
         };
         if (lane == 0)
             for (int d = 0; d < kRingDepth && r0 + d < r1; d += 2) issue_pair(r0 + d, d);
+        if (STATS && lane == 0) atomicAdd(a.stats + 6, (unsigned long long)(r1 - r0));
 
         // pipeline state: per stage the previous row's p (after boundaries), new vx, new vy
         double pb[K][C], un[K][C], vn[K][C];
@@ -466,6 +473,7 @@ stream2d_kernel(Stream2DArgs a) {
         auto steady_pairs = [&](auto cc_tag, auto uni_tag) {
             constexpr int CC = decltype(cc_tag)::value;
             constexpr bool UNI = decltype(uni_tag)::value;   // one material: warp-uniform coefficients
+            if (STATS && lane == 0) atomicAdd(a.stats + (UNI ? CC + 1 : 4), 1ull);
             const unsigned my_ids = info[0].ids;
             double gx[C + 1], gy[C], fx[C + 1], fy[C];
             {
@@ -569,6 +577,7 @@ stream2d_kernel(Stream2DArgs a) {
             }
 
             // ---- general row iteration -----------------------------------------------------------
+            if (STATS && lane == 0) atomicAdd(a.stats + 5, 1ull);
             double cur[3][C];
             load_row(cur, ring + slot * kS2SlotBytes);
             __syncwarp();

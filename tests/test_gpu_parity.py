@@ -230,6 +230,125 @@ def test_streaming_kernel_step_counts_and_chunking(library, max_k, chunk, monkey
     assert_same(scenarios.collect(f), scenarios.collect(g), 'K={} chunk={}'.format(max_k, chunk))
 
 
+# ---- the branch-free (steady-row) variants of the streaming kernel and the rows between them --------
+
+def _steady_case(pattern, nx, ny, steps, seed, kernel):
+    """Maps laid out for the kernel's geometry (56 owned cells per strip, seams at x = 56, 112, ...):
+    long stretches of rows with the same map word per lane -- walls, constant sources and material
+    interfaces ALONG y -- separated by a few rows that break them."""
+    mm = 1e-3
+    f = fds.Acoustic2D(t_delta=1e-7, t_samples=steps, x_delta=mm, x_samples=nx, y_delta=mm,
+                       y_samples=ny, material=fds.AcousticMaterial(1500, 1000))
+    f.device_kernel = kernel
+    scenarios._randomise(f, ('pressure', 'velocity_x', 'velocity_y'), seed)
+    top = (ny - 1) * mm
+    second, third = fds.AcousticMaterial(1200, 900), fds.AcousticMaterial(1350, 950)
+
+    def column(x, y0=0, y1=None):
+        return f.get_line_region((x * mm, y0 * mm, x * mm, top if y1 is None else y1 * mm))
+
+    if pattern == 'plain':
+        pass
+    elif pattern == 'vx_walls':          # component 1: rigid wall at x = 0, constant source on a seam
+        f.velocity_x.add_boundary(column(0))
+        f.velocity_x.add_boundary(column(56), value=1e-6, additive=True)
+        f.velocity_x.add_boundary(column(nx - 1), value=-2e-6)
+    elif pattern == 'p_columns':         # component 0: pressure-release columns, one on a halo lane
+        f.pressure.add_boundary(column(55))
+        f.pressure.add_boundary(column(113), value=3e-4)
+        f.pressure.add_boundary(column(170), value=1e-5, additive=True)
+    elif pattern == 'vy_columns':        # component 2
+        f.velocity_y.add_boundary(column(111), value=2e-6, additive=True)
+        f.velocity_y.add_boundary(column(5))
+    elif pattern == 'interfaces_y':      # several materials, interfaces inside a strip and on seams
+        f.add_material_region(f.get_rect_region((50 * mm, 0, 80 * mm, top)), second)
+        f.add_material_region(f.get_rect_region((112 * mm, 0, 3 * mm, top)), third)
+    elif pattern == 'interface_and_wall':    # operations AND several materials in one strip: general
+        f.add_material_region(f.get_rect_region((20 * mm, 0, 60 * mm, top)), second)
+        f.velocity_x.add_boundary(column(0))
+        f.pressure.add_boundary(column(130), value=1e-4)
+    elif pattern == 'two_components':    # operations on two components of one strip: general
+        f.velocity_x.add_boundary(column(0))
+        f.pressure.add_boundary(column(3))
+        f.velocity_y.add_boundary(column(60), value=1e-6, additive=True)
+        f.velocity_x.add_boundary(column(62))
+    elif pattern == 'partial_height':    # everything starts and ends somewhere: transitions
+        f.velocity_x.add_boundary(column(0, 9, ny - 14))
+        f.pressure.add_boundary(column(100, 20, 61))
+        f.add_material_region(f.get_rect_region((40 * mm, 17 * mm, 90 * mm, 40 * mm)), second)
+        f.add_material_region(f.get_rect_region((150 * mm, 30 * mm, 30 * mm, 31 * mm)), third)
+        f.velocity_y.add_boundary(f.get_line_region((0, 45 * mm, (nx - 1) * mm, 45 * mm)))
+    else:
+        raise ValueError(pattern)
+    # what every case has: a source with a signal and probes -- single rows of the general path
+    f.pressure.add_boundary(f.get_point_region(((nx // 2) * mm, (ny // 2) * mm)),
+                            value=scenarios._pulse(steps, 6, 4), additive=True)
+    f.pressure.add_output(f.get_point_region((57 * mm, (ny // 3) * mm)))
+    f.velocity_x.add_output(f.get_point_region((1 * mm, (ny - 2) * mm)))
+    f.velocity_y.add_output(f.get_point_region(((nx - 1) * mm, 1 * mm)))
+    return f
+
+
+STEADY_PATTERNS = ['plain', 'vx_walls', 'p_columns', 'vy_columns', 'interfaces_y',
+                   'interface_and_wall', 'two_components', 'partial_height']
+
+
+@pytest.mark.parametrize('pattern', STEADY_PATTERNS)
+@pytest.mark.parametrize('chunk', [0, 23])
+def test_streaming_kernel_steady_variants_equal_one_step_kernel(library, pattern, chunk,
+                                                                monkeypatch):
+    """All five branch-free instantiations, the general rows between them, even and odd numbers of
+    rows per task: bit for bit what the one-step kernel computes."""
+    monkeypatch.setenv('FDS_CHUNK_ROWS', str(chunk))
+    monkeypatch.setenv('FDS_STREAM_STATS', '1')
+    results = []
+    for kernel in (1, 2):
+        f = _steady_case(pattern, 256, 118, 13, seed=71, kernel=kernel)
+        f.simulate(9)         # launches of 4 + 4 + 1 steps
+        f.simulate(4)
+        results.append(scenarios.collect(f))
+        engine = f.__dict__['_engine_state'].engine
+        name = engine.last_launch_info()[2]
+        assert ('stream2d' in name) == (kernel == 2), name
+        if kernel == 2:
+            stats = engine.stream_stats()
+    assert_same(results[1], results[0], 'steady {} chunk={}'.format(pattern, chunk))
+    # the case must really have gone through the variant it is named after
+    plain, comp0, comp1, comp2, materials, general, rows = stats[:7]
+    assert plain > 0 and rows > 0, stats
+    expected = {'vx_walls': comp1, 'p_columns': comp0, 'vy_columns': comp2, 'interfaces_y': materials,
+                'partial_height': comp1 + comp0 + materials}
+    if pattern in expected:
+        assert expected[pattern] > 0, (pattern, stats)
+    if pattern in ('plain', 'vx_walls', 'p_columns', 'vy_columns', 'interfaces_y') and chunk == 0:
+        assert general < 0.25 * rows, (pattern, stats)     # only the rows around source and probes
+    if pattern in ('interface_and_wall', 'two_components'):
+        assert general > 0, (pattern, stats)
+
+
+@pytest.mark.parametrize('pattern', ['vx_walls', 'interfaces_y', 'partial_height'])
+def test_streaming_kernel_steady_variants_vs_oracle(library, pattern):
+    f = _steady_case(pattern, 192, 97, 11, seed=72, kernel=2)
+    _vs_oracle(f, 11, 'steady {} vs oracle'.format(pattern))
+
+
+@pytest.mark.parametrize('chunk', [0, 17])
+def test_streaming_kernel_thermal_equals_one_step_kernel(library, chunk, monkeypatch):
+    """Thermal2D on the streaming kernel: Dirichlet temperature columns (component 0 operations),
+    zero-flux rows, an anisotropic material block."""
+    monkeypatch.setenv('FDS_CHUNK_ROWS', str(chunk))
+    results = []
+    for kernel in (1, 2):
+        f, steps = scenarios._thermal2d(fds, 'Thermal2D', 256, 101, 14, seed=73)
+        f.device_kernel = kernel
+        f.simulate(6)
+        f.simulate(8)
+        results.append(scenarios.collect(f))
+        name = f.__dict__['_engine_state'].engine.last_launch_info()[2]
+        assert ('stream2d' in name) == (kernel == 2), name
+    assert_same(results[1], results[0], 'thermal stream vs step chunk={}'.format(chunk))
+
+
 # ---- shared-memory tile kernel vs one-step kernel --------------------------------------------------
 
 @pytest.mark.parametrize('builder,args', [
