@@ -570,9 +570,10 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
     const long long rows = plan.row_end - plan.row_begin;
     const double slots = 148.0 * (ctx->use_streamv ? kStreamCtasPerSm : kS2CtasPerSm) * kStreamWarps;
     const double overhead = 2.0 * lag_rows + 4.0;
-    // measured on B200 (4096^2, bench.py): 4 -> 326, 8 -> 317, 14 -> 320 Gcell-updates/s. The viscous /
-    // axisymmetric kernel has its own fast-path test and no branch-free body: all rows count alike.
-    double general_weight = ctx->use_streamv ? 1.0 : 5.0;
+    // measured on B200 (4096^2, bench.py, 3 CTAs/SM): 1.5 and 2.5 -> 346, 4 -> 341 Gcell-updates/s. The
+    // viscous / axisymmetric kernel has its own fast-path test and no branch-free body: all rows
+    // count alike.
+    double general_weight = ctx->use_streamv ? 1.0 : 2.5;
     if (const char *env = getenv("FDS_GENERAL_WEIGHT")) general_weight = atof(env);
     const int nb = ctx->census_blocks;
     auto row_cost = [&](int s, long long row) {

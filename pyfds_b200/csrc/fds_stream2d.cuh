@@ -174,12 +174,19 @@ constexpr int kS2StripCells = 32 * kS2LaneCells;                   // 64
 constexpr int kS2StripHalo = 4;                                    // cells; K <= 4
 constexpr int kS2HaloLanes = kS2StripHalo / kS2LaneCells;          // 2
 constexpr int kS2StripStride = kS2StripCells - 2 * kS2StripHalo;   // 56 owned cells per strip
-constexpr int kS2CtasPerSm = 4;
+#ifndef FDS_S2_CTAS
+#define FDS_S2_CTAS 3
+#endif
+#ifndef FDS_S2_RING
+#define FDS_S2_RING 6
+#endif
+constexpr int kS2CtasPerSm = FDS_S2_CTAS;   // 3 CTAs x 4 warps at 168 registers: no spills
+constexpr int kS2RingDepth = FDS_S2_RING;   // rows in flight per warp (whole pairs)
 constexpr int kS2MapWindowBytes = kS2StripCells * 2 + 16;
 constexpr int kS2FieldBytes = kS2StripCells * 8;                   // 512
 constexpr int kS2SlotBytes = 3 * kS2FieldBytes + kS2MapWindowBytes + 16;
 constexpr int kS2ScratchBytes = 32 * 2 * kS2LaneCells * 8;         // slow path: 2 components per lane
-constexpr int kS2WarpRingBytes = kRingDepth * kS2SlotBytes + kS2ScratchBytes + 64;   // + mbarriers
+constexpr int kS2WarpRingBytes = kS2RingDepth * kS2SlotBytes + kS2ScratchBytes + 64;   // + mbarriers
 static_assert(kS2SlotBytes % 16 == 0, "bulk copies need 16-byte aligned slots");
 static_assert(kS2LaneCells == 2, "the 32-bit lane map word and the double2 row accesses assume 2");
 
@@ -338,15 +345,15 @@ stream2d_kernel(Stream2DArgs a) {
     const long long nx = a.nx;
     unsigned char *ring = smem_raw + warp * kS2WarpRingBytes;
     double *scratch =
-        reinterpret_cast<double *>(ring + kRingDepth * kS2SlotBytes) + lane * 2 * C;
+        reinterpret_cast<double *>(ring + kS2RingDepth * kS2SlotBytes) + lane * 2 * C;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(
-        ring + kRingDepth * kS2SlotBytes + kS2ScratchBytes);
+        ring + kS2RingDepth * kS2SlotBytes + kS2ScratchBytes);
     // rows travel in pairs: ring slots 2j and 2j+1 share mbarrier j (one wait, one refill per pair)
-    static_assert(kRingDepth % 2 == 0, "the ring holds whole row pairs");
+    static_assert(kS2RingDepth % 2 == 0, "the ring holds whole row pairs");
     unsigned phase_bits = 0;   // parity of every pair barrier (the barriers live across tasks)
 
     if (lane == 0) {
-        for (int d = 0; d < kRingDepth / 2; ++d) mbar_init(&bars[d], 1);
+        for (int d = 0; d < kS2RingDepth / 2; ++d) mbar_init(&bars[d], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -382,7 +389,7 @@ stream2d_kernel(Stream2DArgs a) {
             }
         };
         if (lane == 0)
-            for (int d = 0; d < kRingDepth && r0 + d < r1; d += 2) issue_pair(r0 + d, d);
+            for (int d = 0; d < kS2RingDepth && r0 + d < r1; d += 2) issue_pair(r0 + d, d);
         if (STATS && lane == 0) atomicAdd(a.stats + 6, (unsigned long long)(r1 - r0));
 
         // pipeline state: per stage the previous row's p (after boundaries), new vx, new vy
@@ -449,7 +456,7 @@ stream2d_kernel(Stream2DArgs a) {
                 await(fetch_row, fetch_slot);
                 m = s2_row_meta(ring + fetch_slot * kS2SlotBytes, map_off, lane, lane_relevant);
                 map_off = (map_off + map_step) & 7;
-                if (++fetch_slot == kRingDepth) fetch_slot = 0;
+                if (++fetch_slot == kS2RingDepth) fetch_slot = 0;
                 ++fetch_row;
             }
             return m;
@@ -513,7 +520,7 @@ stream2d_kernel(Stream2DArgs a) {
 
                 load_row(cur, ring + (slot + 1) * kS2SlotBytes);
                 __syncwarp();
-                if (lane == 0 && r + kRingDepth < r1) issue_pair(r + kRingDepth, slot);
+                if (lane == 0 && r + kS2RingDepth < r1) issue_pair(r + kS2RingDepth, slot);
 #pragma unroll
                 for (int s = 0; s < K; ++s)
                     steady_stage<THERMAL, CC>(cur, pb1[s], un1[s], vn1[s], pb[s], un[s], vn[s], gx,
@@ -522,7 +529,7 @@ stream2d_kernel(Stream2DArgs a) {
                 // the window info[0..K] stays what it was: steady rows with these map words
                 cell_r += 2 * nx;
                 r += 2;
-                slot = slot + 2 == kRingDepth ? 0 : slot + 2;
+                slot = slot + 2 == kS2RingDepth ? 0 : slot + 2;
                 // In here the lookahead is implied: rows r, r+1 have landed and been examined
                 // (fetch_row = r + 2); the three cursors are only brought up to date on the way out.
                 fetch_row = r;
@@ -582,8 +589,8 @@ stream2d_kernel(Stream2DArgs a) {
             load_row(cur, ring + slot * kS2SlotBytes);
             __syncwarp();
             // the pair of ring slots is free once its second row has been read
-            if (lane == 0 && (slot & 1) && r - 1 + kRingDepth < r1)
-                issue_pair(r - 1 + kRingDepth, slot - 1);
+            if (lane == 0 && (slot & 1) && r - 1 + kS2RingDepth < r1)
+                issue_pair(r - 1 + kS2RingDepth, slot - 1);
 
 #pragma unroll
             for (int s = K; s > 0; --s) info[s] = info[s - 1];
@@ -746,7 +753,7 @@ stream2d_kernel(Stream2DArgs a) {
             store_row(cur, r - K, cell_r - K * nx);   // row r-K at level K
             cell_r += nx;
             ++r;
-            if (++slot == kRingDepth) slot = 0;
+            if (++slot == kS2RingDepth) slot = 0;
             m0 = m1;
             m1 = fetch();
         }
