@@ -163,6 +163,31 @@ int fds_step(fds_ctx *ctx, int64_t first_step, int64_t n_steps, double *probes_o
 int fds_step_async(fds_ctx *ctx, int64_t first_step, int64_t n_steps);
 int fds_sync(fds_ctx *ctx);
 
+/* --- the step after the hot path: medium flow ------------------------------- */
+
+/* `AcousticFlow2D.apply_flow` (pyfds/acoustic_flow.py:49-57) on the device: after leapfrog step s every
+ * owned row n with s % periods[n] == 0 is moved one cell towards +x (row[1:] = row[:-1], row[0] = 0) in
+ * all three components. periods[n] = |flow_t_deltas[row0 + n]| (pyfds/acoustic_flow.py:34); 0 and 1
+ * both mean "after every step" (numpy evaluates s % 0 to 0). n = rows. The step kernels keep advancing
+ * several steps per launch and end a launch where a row has to move. periods == NULL or n == 0 switches
+ * the flow off. Acoustic2D only. */
+int fds_set_flow(fds_ctx *ctx, const int64_t *periods, int64_t n);
+/* Number of row-shift passes the last fds_step / fds_step_async call launched. */
+int fds_last_flow_shifts(fds_ctx *ctx, int64_t *shifts);
+
+/* --- the output side: field snapshots --------------------------------------- */
+
+/* What `Animator._sim_function` puts on its queue after every `steps_per_frame` steps
+ * (pyfds/gfx.py:72-86: `getattr(field, observed_component).values`), without moving the whole state
+ * to the host: every stride_x-th sample of every stride_y-th owned row of one component, taken from
+ * the state as it is after the steps enqueued so far, is gathered into frame slot 0 or 1 on the device
+ * and copied to page-locked host memory on a second stream while the caller's next steps run.
+ * Frame size: ceil(nx / stride_x) * ceil(rows / stride_y) doubles, row-major. */
+int fds_snapshot_async(fds_ctx *ctx, int32_t component, int32_t stride_x, int32_t stride_y,
+                       int32_t slot);
+/* Waits for the snapshot in `slot` and copies its n doubles to `frame`. */
+int fds_snapshot_wait(fds_ctx *ctx, int32_t slot, double *frame, int64_t n);
+
 /* --- multi-GPU: y-slab halo exchange over NCCL (no reference equivalent) ------- */
 
 /* Writes a 128-byte NCCL unique id (rank 0 calls this, the host side broadcasts it). */

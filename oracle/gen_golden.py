@@ -6,6 +6,7 @@ are committed. ``import pyfds`` pulls in matplotlib through ``pyfds/gfx.py`` whi
 so empty stand-in modules are registered first -- nothing on the time-stepping path uses them.
 
     python oracle/gen_golden.py            # all scenarios + region index maps
+    python oracle/gen_golden.py NAME ...   # only the named scenarios
 """
 
 import os
@@ -38,7 +39,10 @@ def main():
     import scipy
     versions = 'numpy {} scipy {}'.format(np.__version__, scipy.__version__)
 
+    only = sys.argv[1:]
     for name, builder in scenarios.SCENARIOS.items():
+        if only and name not in only:
+            continue
         field, steps = builder(pyfds)
         # segmented run: the second call must resume at field.step (pyfds/fields.py:87-93)
         first = steps // 3
@@ -50,6 +54,8 @@ def main():
         print('{:28s} steps {:4d}  {}'.format(
             name, steps, {k: v.shape for k, v in data.items() if k.startswith('values')}))
 
+    if only:
+        return
     regions = {k: np.asarray(r.indices, dtype=np.int64)
                for k, r in scenarios.region_cases(pyfds).items()}
     np.savez_compressed(os.path.join(GOLDEN, 'regions.npz'), **regions)

@@ -258,6 +258,27 @@ class Acoustic2D(_Stepper):
         p.values -= (self.dot(self.a_p_vx, vx.values) + self.dot(self.a_p_vy, vy.values))
 
 
+class AcousticFlow2D(Acoustic2D):
+    """``pyfds/acoustic_flow.py:44-57``: the Acoustic2D step, then every row n with
+    ``step % flow_t_deltas[n] == 0`` moves one cell towards +x in all three components."""
+
+    def assemble(self, field):
+        super().assemble(field)
+        self.flow_t_deltas = [int(f) for f in field.flow_t_deltas]
+
+    def sim_step(self):
+        super().sim_step()
+        # Python's % on ints has the sign conventions of the reference's `self.step % f` for f != 0;
+        # NumPy evaluates `step % 0` to 0 (pyfds/acoustic_flow.py:54 with an np.int64 period)
+        moving = [n for n, f in enumerate(self.flow_t_deltas) if f == 0 or self.step % f == 0]
+        if not moving:
+            return
+        for name in self.components:
+            grid = self.comp[name].values.reshape(self.ny, self.nx)
+            grid[moving, 1:] = grid[moving, :-1]
+            grid[moving, 0] = 0
+
+
 class Acoustic3DAxi(_Stepper):
     """``pyfds/acoustics.py:166-225``."""
     components = ('pressure', 'velocity_x', 'velocity_y')
@@ -355,7 +376,8 @@ class Thermal3DAxi(Thermal2D):
 
 
 STEPPERS = {
-    'Acoustic1D': Acoustic1D, 'Acoustic2D': Acoustic2D, 'Acoustic3DAxi': Acoustic3DAxi,
+    'Acoustic1D': Acoustic1D, 'Acoustic2D': Acoustic2D, 'AcousticFlow2D': AcousticFlow2D,
+    'Acoustic3DAxi': Acoustic3DAxi,
     'Thermal1D': Thermal1D, 'Thermal2D': Thermal2D, 'Thermal3DAxi': Thermal3DAxi,
 }
 

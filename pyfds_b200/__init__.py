@@ -11,6 +11,7 @@ from .acoustics import *
 from .coupled_fields import *
 from .coupling import *
 from .regions import *
+from .snapshots import *
 from .thermal import *
 
 __version__ = '0.1.0'

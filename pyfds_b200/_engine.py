@@ -84,6 +84,10 @@ def load_library():
         'fds_step': (ct.c_int, [p, i64, i64, p]),
         'fds_step_async': (ct.c_int, [p, i64, i64]),
         'fds_sync': (ct.c_int, [p]),
+        'fds_set_flow': (ct.c_int, [p, p, i64]),
+        'fds_last_flow_shifts': (ct.c_int, [p, ct.POINTER(i64)]),
+        'fds_snapshot_async': (ct.c_int, [p, i32, i32, i32, i32]),
+        'fds_snapshot_wait': (ct.c_int, [p, i32, p, i64]),
         'fds_comm_unique_id': (ct.c_int, [p]),
         'fds_comm_init': (ct.c_int, [p, p, i32, i32]),
         'fds_peer_export': (ct.c_int, [p, p]),
@@ -223,6 +227,31 @@ class Engine:
         self._check(self.lib.fds_last_launch_info(self.handle, ct.byref(launches), ct.byref(spl),
                                                   ct.byref(name)))
         return launches.value, spl.value, (name.value or b'').decode()
+
+    def set_flow(self, periods):
+        """Per-row shift periods of a flowing medium (``None`` switches the flow off)."""
+        if periods is None:
+            self._check(self.lib.fds_set_flow(self.handle, None, 0))
+            return
+        periods = _c(periods, np.int64)
+        self._check(self.lib.fds_set_flow(self.handle, _ptr(periods), periods.size))
+
+    def last_flow_shifts(self):
+        shifts = ct.c_int64()
+        self._check(self.lib.fds_last_flow_shifts(self.handle, ct.byref(shifts)))
+        return shifts.value
+
+    def frame_shape(self, stride_x, stride_y):
+        return (-(-self.rows // stride_y), -(-self.nx // stride_x))
+
+    def snapshot_async(self, component, stride_x, stride_y, slot):
+        """Enqueues a decimated snapshot of one component behind the steps enqueued so far."""
+        self._check(self.lib.fds_snapshot_async(self.handle, component, stride_x, stride_y, slot))
+
+    def snapshot_wait(self, slot, shape):
+        frame = np.empty(shape, dtype=np.float64)
+        self._check(self.lib.fds_snapshot_wait(self.handle, slot, _ptr(frame), frame.size))
+        return frame
 
     def device_bytes(self):
         return self.lib.fds_device_bytes(self.handle)
@@ -366,6 +395,8 @@ def upload_run_tables(field, engine, first_step, n_steps):
     signal window for the step range, and the probe points. Returns ``(n_slots, layout)`` where layout
     lists ``(output, first_slot, n_points)``."""
     nx = engine.nx
+    periods = field._device_flow()
+    engine.set_flow(None if periods is None else periods[engine.row0:engine.row0 + engine.rows])
     signals = []
     for c, component in enumerate(_components(field)):
         table = _bake.boundary_table(component.boundaries, first_step, n_steps, engine.cell_lo,
@@ -412,6 +443,43 @@ def _host_values(component, num_points):
     return values
 
 
+def upload_values(field, engine):
+    """Host ``values`` of every component -> device. Arrays the field keeps reusing are page-locked
+    on first use (the reference updates ``values`` in place, so the registration is reused call after
+    call). Returns the seconds spent page-locking and copying."""
+    import time
+    clock = time.perf_counter
+    t0 = clock()
+    state = field.__dict__['_engine_state']
+    host = []
+    for c, component in enumerate(_components(field)):
+        values = _host_values(component, field.num_points)
+        own = component.values
+        if isinstance(own, np.ndarray) and own.ctypes.data == values.ctypes.data and \
+                own.nbytes == values.nbytes:
+            state.pin(engine.lib, c, own)
+        host.append(values)
+    t1 = clock()
+    for c, values in enumerate(host):
+        engine.upload_state(c, values)
+    return t1 - t0, clock() - t1
+
+
+def download_values(field, engine, only=None):
+    """Device -> host ``values`` (in place where the component holds a suitable array, so that
+    page-locked arrays keep being reused). ``only``: component numbers to fetch (default all)."""
+    for c, component in enumerate(_components(field)):
+        if only is not None and c not in only:
+            continue
+        target = component.values
+        if isinstance(target, np.ndarray) and target.dtype == np.float64 and \
+                target.flags.c_contiguous and target.flags.writeable and \
+                target.shape == (field.num_points,):
+            engine.download_state(c, out=target)
+        else:
+            component.values = engine.download_state(c)
+
+
 def run(field, n_steps, progress_logger=None, advance=True):
     """``n_steps`` x ``sim_step`` on the device: upload values, step, download values and probes.
     Wall-clock seconds of the phases are left in ``field.__dict__['_last_run_profile']``."""
@@ -422,20 +490,7 @@ def run(field, n_steps, progress_logger=None, advance=True):
     first_step = field.step
     n_slots, layout = upload_run_tables(field, engine, first_step, n_steps)
     t1 = clock()
-
-    components = _components(field)
-    state = field.__dict__['_engine_state']
-    host = []
-    for c, component in enumerate(components):
-        values = _host_values(component, field.num_points)
-        own = component.values
-        if isinstance(own, np.ndarray) and own.ctypes.data == values.ctypes.data and \
-                own.nbytes == values.nbytes:
-            state.pin(engine.lib, c, own)
-        host.append(values)
-    t1b = clock()
-    for c, values in enumerate(host):
-        engine.upload_state(c, values)
+    lock_s, upload_s = upload_values(field, engine)
     t2 = clock()
 
     chunk = n_steps
@@ -455,17 +510,10 @@ def run(field, n_steps, progress_logger=None, advance=True):
         done += count
     t3 = clock()
 
-    for c, component in enumerate(components):
-        target = component.values
-        if isinstance(target, np.ndarray) and target.dtype == np.float64 and \
-                target.flags.c_contiguous and target.flags.writeable and \
-                target.shape == (field.num_points,):
-            engine.download_state(c, out=target)
-        else:
-            component.values = engine.download_state(c)
+    download_values(field, engine)
     t4 = clock()
     field.__dict__['_last_run_profile'] = {
-        'prepare_and_tables_s': t1 - t0, 'page_lock_s': t1b - t1, 'upload_state_s': t2 - t1b,
+        'prepare_and_tables_s': t1 - t0, 'page_lock_s': lock_s, 'upload_state_s': upload_s,
         'step_s': t3 - t2,
         'download_state_s': t4 - t3}
     if advance:

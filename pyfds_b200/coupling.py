@@ -1,11 +1,20 @@
 """Coupled fields: lock-step simulation of several fields and interactions between them.
 
-Mirror of the reference interface ``pyfds/coupling.py``. These classes are host-side orchestration
-around arbitrary Python transfer functions, so they drive the device engine through the per-step seam:
-``SynchronizedFields.sim_step`` calls every field's ``sim_step()`` (one device step each, host
-``values`` coherent before and after) and then applies the interactions on the host arrays, exactly as
-the reference does (``pyfds/coupling.py:81-87``). Correct, but one host round trip per step -- meant for
-the small coupled problems the reference ships (1-D thermo-acoustics), not for the large-grid hot path.
+Mirror of the reference interface ``pyfds/coupling.py``. The interactions are arbitrary Python
+transfer functions of one component's ``values``, so they stay on the host; what changes is how much
+travels for them:
+
+* ``SynchronizedFields.sim_step`` is the reference statement (``pyfds/coupling.py:81-87``): every
+  field's ``sim_step()`` (one device step each, host ``values`` coherent before and after), then the
+  interactions on the host arrays.
+* ``SynchronizedFields.simulate`` runs a *device session* when every field is on the device path and
+  every interaction is a plain ``BoundaryCoupling``: the state of all fields stays in HBM for the whole
+  call, boundary / probe tables are uploaded once, and per step only the components an interaction
+  actually touches cross the bus -- the source when the interaction reads it (every step if it
+  accumulates, else every ``stepping``-th), the target when it is written. Anything else
+  (``MaterialCoupling``, subclasses with their own ``sim_step``/``apply``) falls back to the per-step
+  loop. Set ``device_session = False`` on the instance if a transfer function looks at components
+  other than the source it is given.
 """
 
 import logging as lo
@@ -78,6 +87,89 @@ class SynchronizedFields(fld.Field):
             field.sim_step()
         for interaction in self.interactions:
             interaction.apply(self.step)
+
+    # ---- device session -------------------------------------------------------------------------
+
+    #: allow ``simulate`` to keep the fields' state on the device between steps (module docstring)
+    device_session = True
+
+    def _session_plan(self):
+        """``[(interaction, source key, target key)]`` with keys ``(field number, component number)``
+        if the device session applies, else ``None``."""
+        if not self.device_session or type(self).sim_step is not SynchronizedFields.sim_step:
+            return None
+        owners = {}
+        for f, field in enumerate(self.fields):
+            if not field._uses_device():
+                return None
+            for c, name in enumerate(field._device_components):
+                owners[id(getattr(field, name))] = (f, c)
+        plan = []
+        for interaction in self.interactions:
+            if type(interaction) is not BoundaryCoupling:
+                return None
+            source = owners.get(id(interaction.source_component))
+            target = owners.get(id(interaction.target_component))
+            if source is None or target is None:
+                return None
+            plan.append((interaction, source, target))
+        return plan
+
+    def _simulate_on_device(self, num_steps, progress_logger=None):
+        """``num_steps`` x ``sim_step`` with the state of all fields resident on the device; returns
+        ``False`` (and does nothing) if the session does not apply."""
+        plan = self._session_plan()
+        if plan is None:
+            return False
+        from . import _engine
+        first_step = self.step
+        engines, tables, components = [], [], []
+        for field in self.fields:
+            if not field.matrices_assembled:
+                field.assemble_matrices()
+            engine = _engine.prepare(field)
+            engines.append(engine)
+            tables.append(_engine.upload_run_tables(field, engine, first_step, num_steps))
+            components.append(_engine._components(field))
+            _engine.upload_values(field, engine)
+        # host copy of (field, component) equals the device copy
+        fresh = {(f, c): True for f in range(len(self.fields))
+                 for c in range(len(components[f]))}
+
+        def to_host(key):
+            if not fresh[key]:
+                f, c = key
+                _engine.download_values(self.fields[f], engines[f], only=(c,))
+                fresh[key] = True
+
+        try:
+            for step in range(first_step, first_step + num_steps):
+                for f, engine in enumerate(engines):
+                    n_slots, layout = tables[f]
+                    records = engine.step(step, 1, n_slots)
+                    if n_slots:
+                        _engine._append_signals(layout, records)
+                    for c in range(len(components[f])):
+                        fresh[(f, c)] = False
+                for interaction, source, target in plan:
+                    writes = step % interaction.stepping == 0
+                    if writes or interaction.accumulate is True:
+                        to_host(source)
+                    if writes and interaction.additive is True:
+                        to_host(target)
+                    interaction.apply(step)
+                    if writes:
+                        f, c = target
+                        engines[f].upload_state(c, _engine._host_values(components[f][c],
+                                                                        self.fields[f].num_points))
+                        fresh[target] = True
+                if progress_logger:
+                    progress_logger.log(step)
+                self.step = step + 1
+        finally:
+            for key in fresh:
+                to_host(key)
+        return True
 
 
 class BoundaryCoupling():

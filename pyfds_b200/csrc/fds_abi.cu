@@ -30,6 +30,7 @@
 #include "fds_step2d.cuh"
 #include "fds_stream2d.cuh"
 #include "fds_streamv.cuh"
+#include "fds_aux.cuh"
 
 using namespace fds;
 
@@ -167,6 +168,20 @@ struct fds_ctx {
     int chunk_rows = 0;       // rows per streaming task (0 = heuristic)
     int tile_rows = 0;        // owned rows per tile of the tile kernel (0 = default)
     int max_k = kMaxStreamSteps;
+
+    // medium flow (AcousticFlow2D): |flow_t_deltas| of every owned row and their distinct values
+    DevArray flow_periods;
+    std::vector<long long> flow_unique;
+    bool flow = false;
+    long long flow_shifts = 0;        // flow_shift_kernel launches of the last call
+
+    // field snapshots: two frame slots, each a device buffer and a pinned host buffer
+    double *frame_dev[2] = {nullptr, nullptr};
+    size_t frame_dev_cap[2] = {0, 0};
+    void *frame_host[2] = {nullptr, nullptr};
+    size_t frame_host_cap[2] = {0, 0};
+    long long frame_n[2] = {0, 0};
+    cudaEvent_t ev_frame_ready[2] = {nullptr, nullptr}, ev_frame_done[2] = {nullptr, nullptr};
 
     std::string err;
 };
@@ -917,6 +932,37 @@ int peer_push(fds_ctx *ctx, int which) {
 
 int exchange_halos(fds_ctx *ctx, int which);
 
+// ---- medium flow ------------------------------------------------------------------------------------
+// True if some row moves after leapfrog step `step` (pyfds/acoustic_flow.py:54: step % period == 0).
+bool flow_due(const fds_ctx *ctx, long long step) {
+    for (long long period : ctx->flow_unique)
+        if (period <= 1 || step % period == 0) return true;
+    return false;
+}
+
+// Steps that may run back to back starting at `step` before a row has to move: the launch may include
+// the step after which the shift is due, but none beyond it.
+long long flow_run_length(const fds_ctx *ctx, long long step, long long limit) {
+    for (long long j = 0; j < limit; ++j)
+        if (flow_due(ctx, step + j)) return j + 1;
+    return limit;
+}
+
+// Moves the rows that are due after `step` in buffer `which` (owned rows; halo rows are refreshed by
+// the exchange that follows).
+int launch_flow(fds_ctx *ctx, int which, long long step) {
+    FlowArgs a{};
+    for (int c = 0; c < 3; ++c) a.state[c] = origin(ctx, which, c);
+    a.periods = (const long long *)ctx->flow_periods.ptr;
+    a.nx = ctx->d.nx;
+    a.rows = ctx->d.rows;
+    a.step = step;
+    flow_shift_kernel<<<dim3((unsigned)ctx->d.rows, 3), kFlowThreads, 0, ctx->stream>>>(a);
+    FDS_CUDA(ctx, cudaGetLastError());
+    ctx->flow_shifts += 1;
+    return 0;
+}
+
 // The time loop. `drain` = copy probe records to pinned host memory behind the computation.
 int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain) {
     if (n_steps <= 0) return 0;
@@ -948,6 +994,7 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
     const long long sig0 = first_step - ctx->sig_first;
     ctx->last_launches = 0;
     ctx->last_steps_per_launch = 1;
+    ctx->flow_shifts = 0;
 
     if (ctx->comm && ctx->world > 1 && ctx->dims == 2) {
         // the neighbours' rows of the current state (fresh upload, or a previous call's last step)
@@ -1009,6 +1056,10 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                                                  chunk_steps - in_chunk);
                 // a slab can only advance as many steps as its halo rows cover
                 if (multi) k = std::min<int>(k, ctx->d.halo_rows / (ctx->d.lossy ? 2 : 1));
+                // rows of a flowing medium move between two steps: end the launch there
+                if (ctx->flow) k = (int)flow_run_length(ctx, first_step + s, k);
+                const long long last = first_step + s + k - 1;
+                const bool shift = ctx->flow && flow_due(ctx, last);
                 // thermal fluxes are derived data: stored only by the launch that ends the call
                 a.write_vector = (s + k == n_steps);
                 if (multi && peers_ready(ctx)) {
@@ -1016,7 +1067,19 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                     if (peer_wait(ctx, in_chunk > 0 || chunk > 0)) return 1;
                     a.row_begin = 0; a.row_end = rows;
                     if (dispatch_stream2d(ctx, a, k)) return 1;
+                    if (shift && launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
                     if (peer_push(ctx, ctx->cur ^ 1)) return 1;
+                    ctx->last_launches += 1;
+                } else if (multi && shift) {
+                    // the edge rows move before they travel: no overlap for this launch
+                    a.row_begin = 0; a.row_end = rows;
+                    if (dispatch_stream2d(ctx, a, k)) return 1;
+                    if (launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
+                    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
+                    FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
+                    if (exchange_halos(ctx, ctx->cur ^ 1)) return 1;
+                    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+                    FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
                     ctx->last_launches += 1;
                 } else if (multi) {
                     // the k outermost rows of either side travel while the interior is computed
@@ -1036,6 +1099,7 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 } else {
                     a.row_begin = 0; a.row_end = rows;
                     if (dispatch_stream2d(ctx, a, k)) return 1;
+                    if (shift && launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
                     ctx->last_launches += 1;
                 }
                 advanced = k;
@@ -1060,11 +1124,24 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 // thermal fluxes are derived data: store them only with the last step of the call
                 a.write_vector = (s == n_steps - 1);
                 const long long rows = ctx->d.rows;
+                const long long last = first_step + s;
+                const bool shift = ctx->flow && flow_due(ctx, last);
                 if (ctx->comm && ctx->world > 1 && peers_ready(ctx)) {
                     if (peer_wait(ctx, in_chunk > 0 || chunk > 0)) return 1;
                     a.row_begin = 0; a.row_end = rows;
                     if (dispatch_step2d(ctx, a, t)) return 1;
+                    if (shift && launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
                     if (peer_push(ctx, ctx->cur ^ 1)) return 1;
+                    ctx->last_launches += 1;
+                } else if (ctx->comm && ctx->world > 1 && shift) {
+                    a.row_begin = 0; a.row_end = rows;
+                    if (dispatch_step2d(ctx, a, t)) return 1;
+                    if (launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
+                    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
+                    FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
+                    if (exchange_halos(ctx, ctx->cur ^ 1)) return 1;
+                    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+                    FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
                     ctx->last_launches += 1;
                 } else if (ctx->comm && ctx->world > 1) {
                     // edge bands first, so that their rows can travel while the interior computes
@@ -1084,6 +1161,7 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 } else {
                     a.row_begin = 0; a.row_end = rows;
                     if (dispatch_step2d(ctx, a, t)) return 1;
+                    if (shift && launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
                     ctx->last_launches += 1;
                 }
                 ctx->last_kernel = step2d_name(ctx);
@@ -1338,6 +1416,13 @@ void fds_destroy(fds_ctx *ctx) {
     if (ctx->signals.ptr) cudaFree(ctx->signals.ptr);
     if (ctx->ring.ptr) cudaFree(ctx->ring.ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->flow_periods.ptr) cudaFree(ctx->flow_periods.ptr);
+    for (int slot = 0; slot < 2; ++slot) {
+        if (ctx->frame_dev[slot]) cudaFree(ctx->frame_dev[slot]);
+        if (ctx->frame_host[slot]) cudaFreeHost(ctx->frame_host[slot]);
+        if (ctx->ev_frame_ready[slot]) cudaEventDestroy(ctx->ev_frame_ready[slot]);
+        if (ctx->ev_frame_done[slot]) cudaEventDestroy(ctx->ev_frame_done[slot]);
+    }
 
     cudaEvent_t events[] = {ctx->ev_half[0], ctx->ev_half[1], ctx->ev_drained[0], ctx->ev_drained[1],
                             ctx->ev_t0, ctx->ev_t1, ctx->ev_edge, ctx->ev_comm};
@@ -1622,6 +1707,107 @@ int fds_sync(fds_ctx *ctx) {
     FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     FDS_CUDA(ctx, cudaStreamSynchronize(ctx->drain));
     FDS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    return 0;
+}
+
+int fds_set_flow(fds_ctx *ctx, const int64_t *periods, int64_t n) {
+    if (!ctx) return fail(ctx, "fds_set_flow: null context");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    if (!periods || n == 0) {
+        ctx->flow = false;
+        ctx->flow_unique.clear();
+        return 0;
+    }
+    if (ctx->d.model != FDS_ACOUSTIC2D)
+        return fail(ctx, "fds_set_flow: medium flow is defined for Acoustic2D only");
+    if (n != ctx->d.rows) return fail(ctx, "fds_set_flow: expected one period per owned row");
+    std::vector<long long> unique;
+    for (int64_t k = 0; k < n; ++k) {
+        if (periods[k] < 0) return fail(ctx, "fds_set_flow: periods must not be negative");
+        bool seen = false;
+        for (long long u : unique) seen = seen || u == periods[k];
+        if (!seen) unique.push_back(periods[k]);
+        if (unique.size() > 4096)
+            return fail(ctx, "fds_set_flow: more than 4096 distinct shift periods");
+    }
+    static_assert(sizeof(long long) == sizeof(int64_t), "period width");
+    if (dev_upload(ctx, ctx->flow_periods, periods, (size_t)n * 8)) return 1;
+    ctx->flow_unique.swap(unique);
+    ctx->flow = true;
+    return 0;
+}
+
+int fds_last_flow_shifts(fds_ctx *ctx, int64_t *shifts) {
+    if (!ctx || !shifts) return fail(ctx, "fds_last_flow_shifts: null argument");
+    *shifts = ctx->flow_shifts;
+    return 0;
+}
+
+int fds_snapshot_async(fds_ctx *ctx, int32_t component, int32_t stride_x, int32_t stride_y,
+                       int32_t slot) {
+    if (!ctx) return fail(ctx, "fds_snapshot_async: null context");
+    if (component < 0 || component >= ctx->ncomp)
+        return fail(ctx, "fds_snapshot_async: bad component");
+    if (stride_x < 1 || stride_y < 1) return fail(ctx, "fds_snapshot_async: strides must be >= 1");
+    if (slot < 0 || slot > 1) return fail(ctx, "fds_snapshot_async: slot must be 0 or 1");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    const long long fx = (ctx->d.nx + stride_x - 1) / stride_x;
+    const long long fy = (ctx->d.rows + stride_y - 1) / stride_y;
+    const size_t bytes = (size_t)(fx * fy) * 8;
+    if (!ctx->ev_frame_ready[slot]) {
+        FDS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_frame_ready[slot], cudaEventDisableTiming));
+        FDS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_frame_done[slot], cudaEventDisableTiming));
+    }
+    // the slot may still be on its way to the host from an earlier snapshot
+    FDS_CUDA(ctx, cudaEventSynchronize(ctx->ev_frame_done[slot]));
+    if (ctx->frame_dev_cap[slot] < bytes) {
+        if (ctx->frame_dev[slot]) {
+            cudaFree(ctx->frame_dev[slot]);
+            ctx->device_bytes -= (long long)ctx->frame_dev_cap[slot];
+        }
+        ctx->frame_dev[slot] = nullptr;
+        ctx->frame_dev_cap[slot] = 0;
+        if (dev_alloc(ctx, (void **)&ctx->frame_dev[slot], bytes, false)) return 1;
+        ctx->frame_dev_cap[slot] = bytes;
+    }
+    if (ctx->frame_host_cap[slot] < bytes) {
+        if (ctx->frame_host[slot]) cudaFreeHost(ctx->frame_host[slot]);
+        ctx->frame_host[slot] = nullptr;
+        ctx->frame_host_cap[slot] = 0;
+        FDS_CUDA(ctx, cudaHostAlloc(&ctx->frame_host[slot], bytes, cudaHostAllocPortable));
+        ctx->frame_host_cap[slot] = bytes;
+    }
+    SnapshotArgs a{};
+    a.state = origin(ctx, ctx->cur, component);
+    a.frame = ctx->frame_dev[slot];
+    a.nx = ctx->d.nx;
+    a.fx = fx;
+    a.fy = fy;
+    a.stride_x = stride_x;
+    a.stride_y = stride_y;
+    const long long blocks = std::min<long long>((fx * fy + 255) / 256, 148 * 16);
+    snapshot_kernel<<<(unsigned)std::max<long long>(blocks, 1), 256, 0, ctx->stream>>>(a);
+    FDS_CUDA(ctx, cudaGetLastError());
+    // the copy to the host runs on the drain stream, behind whatever the caller enqueues next
+    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_frame_ready[slot], ctx->stream));
+    FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->drain, ctx->ev_frame_ready[slot], 0));
+    FDS_CUDA(ctx, cudaMemcpyAsync(ctx->frame_host[slot], ctx->frame_dev[slot], bytes,
+                                  cudaMemcpyDeviceToHost, ctx->drain));
+    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_frame_done[slot], ctx->drain));
+    ctx->frame_n[slot] = fx * fy;
+    return 0;
+}
+
+int fds_snapshot_wait(fds_ctx *ctx, int32_t slot, double *frame, int64_t n) {
+    if (!ctx || !frame) return fail(ctx, "fds_snapshot_wait: null argument");
+    if (slot < 0 || slot > 1 || !ctx->ev_frame_done[slot] || ctx->frame_n[slot] == 0)
+        return fail(ctx, "fds_snapshot_wait: no snapshot pending in this slot");
+    if (n != ctx->frame_n[slot])
+        return fail(ctx, "fds_snapshot_wait: frame size differs from the snapshot taken");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    FDS_CUDA(ctx, cudaEventSynchronize(ctx->ev_frame_done[slot]));
+    memcpy(frame, ctx->frame_host[slot], (size_t)n * 8);
+    ctx->frame_n[slot] = 0;
     return 0;
 }
 

@@ -85,6 +85,16 @@ class Field:
         return self._device_model is not None and \
             getattr(type(self).sim_step, '_on_device', False)
 
+    def _simulate_on_device(self, num_steps, progress_logger=None):
+        """Hook for composite fields (``SynchronizedFields``) that can run a whole ``simulate`` call
+        with device-resident state although they are not a device model themselves."""
+        return False
+
+    def _device_flow(self):
+        """Per-row shift periods if the medium flows and the device applies the shift (only
+        ``AcousticFlow2D``), else ``None``."""
+        return None
+
     def simulate(self, num_steps=None):
         """Run ``num_steps`` steps (``self.t.samples`` if falsy, as ``pyfds/fields.py:74-75``)."""
 
@@ -103,6 +113,8 @@ class Field:
         if self._uses_device():
             from . import _engine
             _engine.run(self, int(num_steps), progress_logger)
+        elif self._simulate_on_device(int(num_steps), progress_logger):
+            pass                            # coupled fields with their state resident on the device
         else:
             start_step = self.step
             while self.step < start_step + num_steps:

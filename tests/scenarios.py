@@ -157,6 +157,48 @@ def acoustic3daxi_lossless(fds):
     return fld, steps
 
 
+def _flow_for_periods(periods, ny):
+    """Flow velocities (m/s) whose ``flow_t_deltas`` (pyfds/acoustic_flow.py:34: dx / flow / dt cut to
+    an integer) are the given periods, repeated over the rows; with dx = 1e-3 and dt = 1e-7."""
+    wanted = np.array([periods[n % len(periods)] for n in range(ny)], dtype=float)
+    return 1e4 / (wanted + np.sign(wanted) * 0.5)
+
+
+def _acoustic_flow2d(fds, nx, ny, steps, seed, periods):
+    """``AcousticFlow2D`` (pyfds/acoustic_flow.py): the config-2 layout in a medium whose rows move at
+    different speeds, one row against the x direction (the shift itself ignores the sign)."""
+    import warnings
+    main = fds.AcousticMaterial(1500, 1000)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')      # "Flow velocity may be to high" for the period-1 rows
+        fld = fds.AcousticFlow2D(_flow_for_periods(periods, ny), t_delta=1e-7, t_samples=steps,
+                                 x_delta=1e-3, x_samples=nx, y_delta=1e-3, y_samples=ny,
+                                 material=main)
+    assert [int(f) for f in fld.flow_t_deltas[:len(periods)]] == list(periods)
+    qx, qy = nx // 4, ny // 4
+    fld.add_material_region(fld.get_rect_region((qx * 1e-3, qy * 1e-3, qx * 1e-3, qy * 1e-3)),
+                            fds.AcousticMaterial(1200, 900))
+    _randomise(fld, ('pressure', 'velocity_x', 'velocity_y'), seed=seed)
+    fld.pressure.add_boundary(fld.get_point_region(((nx // 2) * 1e-3, (ny // 2) * 1e-3)),
+                              value=_pulse(steps, 40, 15), additive=True)
+    fld.velocity_x.add_boundary(fld.get_line_region((0, 0, 0, (ny - 1) * 1e-3)))
+    for m in range(1, 5):
+        fld.pressure.add_output(fld.get_point_region(((m * nx // 5) * 1e-3, (m * ny // 5) * 1e-3)))
+    fld.velocity_x.add_output(fld.get_point_region((0, 3e-3)))
+    return fld, steps
+
+
+def acoustic_flow2d(fds):
+    """Small grid (one-step kernel); rows moving after every step, every 2nd ... 33rd step."""
+    return _acoustic_flow2d(fds, 48, 40, 90, seed=12, periods=(3, 7, 1, 33, -5, 1000, 2, 11))
+
+
+def acoustic_flow2d_wide(fds):
+    """Streaming kernel: launches of 4 steps that have to end where a row moves (steps 8, 10, 12, 16,
+    20 ... -> launches of 4, 4, 2, 2, 4 ... steps)."""
+    return _acoustic_flow2d(fds, 400, 75, 60, seed=13, periods=(8, 12, -20, 1000, 10))
+
+
 def _thermal2d(fds, klass, nx, ny, steps, seed):
     """Config 4 of BASELINE.json scaled down: two materials (one anisotropic), Dirichlet temperature
     on x=0 / x=max, adiabatic (zero flux) y=0 / y=max, probes on temperature and flux."""
@@ -216,6 +258,8 @@ SCENARIOS = {
     'thermal2d': thermal2d,
     'thermal3daxi': thermal3daxi,
     'thermal1d': thermal1d,
+    'acoustic_flow2d': acoustic_flow2d,
+    'acoustic_flow2d_wide': acoustic_flow2d_wide,
 }
 
 

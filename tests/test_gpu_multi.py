@@ -59,7 +59,8 @@ def _worker(rank, world, port, name, kernel, queue):
 
 @pytest.mark.parametrize('name,kernel', [
     ('big_lossless', 0), ('big_lossless', 1), ('big_lossy', 0), ('acoustic2d_wide', 0),
-    ('acoustic2d_boundaries', 0), ('thermal2d', 0), ('acoustic3daxi_lossy', 0)])
+    ('acoustic2d_boundaries', 0), ('thermal2d', 0), ('acoustic3daxi_lossy', 0),
+    ('acoustic_flow2d', 0), ('acoustic_flow2d_wide', 0)])
 def test_two_slabs_equal_single_domain(library, name, kernel):
     if _gpu_count() < 2:
         pytest.skip('needs 2 GPUs')
