@@ -27,6 +27,7 @@
 
 #include "fds_common.cuh"
 #include "fds_step1d.cuh"
+#include "fds_line1d.cuh"
 #include "fds_step2d.cuh"
 #include "fds_stream2d.cuh"
 #include "fds_streamv.cuh"
@@ -167,6 +168,7 @@ struct fds_ctx {
     int next_counter = 0;
     int chunk_rows = 0;       // rows per streaming task (0 = heuristic)
     int tile_rows = 0;        // owned rows per tile of the tile kernel (0 = default)
+    int halo_1d = 0;          // halo cells of the tiled 1-D kernel (0 = default)
     int max_k = kMaxStreamSteps;
 
     // medium flow (AcousticFlow2D): |flow_t_deltas| of every owned row and their distinct values
@@ -811,7 +813,7 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
 
 // 1-D tiling: owned cells per CTA, halo and steps per launch.
 struct Plan1D {
-    int tile, halo, steps;
+    int tile, halo, steps, threads, per;
     long long ctas;
     size_t smem;
 };
@@ -819,45 +821,94 @@ struct Plan1D {
 Plan1D plan_1d(const fds_ctx *ctx, long long steps_left) {
     Plan1D p{};
     const long long n = ctx->d.nx;
-    if (n <= 1536) {  // a short line in one CTA: no neighbours, any number of steps per launch
+    if (ctx->d.kernel != 1) {
+        // register-resident warp tiles (fds_line1d.cuh): 256 cells per warp, one warp per CTA
+        p.per = 0;
+        p.threads = 32;
+        if (n + 16 <= kLineWidth) {   // the whole line in one warp: any number of steps per launch
+            p.tile = (int)n;
+            p.halo = 8;
+            p.ctas = 1;
+            p.steps = (int)std::min<long long>(steps_left, 1 << 20);
+        } else {
+            // steps per launch = halo / 2: a wide halo saves launches (a launch costs ~7 us of start-up
+            // and tail) but leaves fewer owned cells per warp; short lines can afford it
+            p.halo = n <= 592 * 64 ? 96 : n <= 1184 * 128 ? 64 : 32;
+            if (ctx->halo_1d > 0) p.halo = std::min(112, (ctx->halo_1d + 7) / 8 * 8);
+            p.tile = kLineWidth - 2 * p.halo;
+            p.ctas = (n + p.tile - 1) / p.tile;
+            p.steps = (int)std::min<long long>(steps_left, p.halo / 2);
+        }
+        p.smem = 0;
+        return p;
+    }
+    if (n + 4 <= k1DThreads) {  // a short line in one CTA: no neighbours, any number of steps per launch
         p.tile = (int)n;
         p.halo = 2;
         p.ctas = 1;
         p.steps = (int)std::min<long long>(steps_left, 1 << 20);
     } else {
-        // several CTAs, 32 steps per launch on 64-cell halos; tiles sized for a few dozen CTAs
-        // (one SM steps ~1 cell per thread and barrier; more SMs beat fewer launches)
-        p.halo = 64;
-        long long tile = (n + 47) / 48;
-        tile = (tile + 31) / 32 * 32;
-        p.tile = (int)std::max<long long>(512, std::min<long long>(tile, 4096 - 2 * p.halo));
+        // several CTAs, halo / 2 steps per launch. A step costs issue slots and latency of one SM (four
+        // phases between block barriers), so tiles are small: one cell per thread, a dozen warps.
+        p.halo = ctx->halo_1d > 0 ? ctx->halo_1d : 64;
+        p.tile = 256;
         if (ctx->tile_rows > 0) p.tile = ctx->tile_rows;      // FDS_TILE_ROWS: experiments
+        p.tile = (int)std::min<long long>(p.tile, (long long)k1DMaxPerThread * k1DThreads - 2 * p.halo);
         p.ctas = (n + p.tile - 1) / p.tile;
         p.steps = (int)std::min<long long>(steps_left, p.halo / 2);
     }
-    p.smem = (size_t)(p.tile + 2 * p.halo) * (16 + sizeof(map_t)) + 16;
+    const int width = p.tile + 2 * p.halo;
+    p.per = width <= k1DThreads ? 1 : k1DMaxPerThread;
+    p.threads = p.per == 1 ? (width + 31) / 32 * 32 : k1DThreads;
+    p.smem = (size_t)width * (16 + sizeof(map_t)) + 16;
     return p;
 }
 
-template <bool THERMAL, bool LOSSY>
-int launch_step1d(fds_ctx *ctx, const Step1DArgs &a, const StepTables &t, const Plan1D &p) {
-    auto kernel = step1d_kernel<THERMAL, LOSSY>;
-    FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)p.smem));
-    kernel<<<(unsigned)p.ctas, k1DThreads, p.smem, ctx->stream>>>(a, t);
+template <bool THERMAL, bool LOSSY, int PER>
+int launch_step1d_as(fds_ctx *ctx, const Step1DArgs &a, const StepTables &t, const Plan1D &p) {
+    auto kernel = step1d_kernel<THERMAL, LOSSY, PER>;
+    static size_t configured = 0;
+    if (configured < p.smem) {
+        FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p.smem));
+        configured = p.smem;
+    }
+    kernel<<<(unsigned)p.ctas, p.threads, p.smem, ctx->stream>>>(a, t);
     FDS_CUDA(ctx, cudaGetLastError());
     return 0;
 }
 
+template <bool THERMAL, bool LOSSY>
+int launch_step1d(fds_ctx *ctx, const Step1DArgs &a, const StepTables &t, const Plan1D &p) {
+    if (p.per == 0) {
+        auto kernel = line1d_kernel<THERMAL, LOSSY>;
+        const int smem = (int)(kLineWarps * sizeof(LineShared));
+        static bool configured = false;
+        if (!configured) {
+            FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               smem));
+            configured = true;
+        }
+        const unsigned ctas = (unsigned)((p.ctas + kLineWarps - 1) / kLineWarps);
+        kernel<<<ctas, 32 * kLineWarps, smem, ctx->stream>>>(a, t, (int)p.ctas);
+        FDS_CUDA(ctx, cudaGetLastError());
+        return 0;
+    }
+    return p.per == 1 ? launch_step1d_as<THERMAL, LOSSY, 1>(ctx, a, t, p)
+                      : launch_step1d_as<THERMAL, LOSSY, k1DMaxPerThread>(ctx, a, t, p);
+}
+
 int ensure_ring(fds_ctx *ctx, long long n_steps) {
     // two halves, each holding `ring_half` step records
-    long long half = 1;
+    // (without probes nothing is recorded: a call is one chunk, so that the step kernels can advance
+    // as many steps per launch as they support)
+    long long half = std::max<long long>(1, n_steps);
     if (ctx->n_slots > 0) {
         const long long budget = (32ll << 20) / (ctx->n_slots * 8);
         half = std::max<long long>(1, std::min<long long>(n_steps, std::max<long long>(budget, 64)));
     }
-    const size_t bytes = (size_t)(2 * half * std::max<long long>(ctx->n_slots, 1)) * 8;
-    if (ctx->ring.bytes < bytes || ctx->ring_half < half) {
+    const size_t bytes = ctx->n_slots > 0 ? (size_t)(2 * half * ctx->n_slots) * 8 : 16;
+    if (ctx->ring.bytes < bytes || (ctx->n_slots > 0 && ctx->ring_half < half)) {
         if (ctx->ring.ptr) {
             FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             cudaFree(ctx->ring.ptr);
@@ -1036,9 +1087,14 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 else rc = launch_step1d<false, false>(ctx, a, t, p);
                 if (rc) return 1;
                 advanced = p.steps;
-                ctx->last_kernel = ctx->thermal ? "step1d_kernel<thermal>"
-                                   : ctx->d.lossy ? "step1d_kernel<acoustic,lossy>"
-                                                  : "step1d_kernel<acoustic,lossless>";
+                if (p.per == 0)
+                    ctx->last_kernel = ctx->thermal ? "line1d_kernel<thermal>"
+                                       : ctx->d.lossy ? "line1d_kernel<acoustic,lossy>"
+                                                      : "line1d_kernel<acoustic,lossless>";
+                else
+                    ctx->last_kernel = ctx->thermal ? "step1d_kernel<thermal>"
+                                       : ctx->d.lossy ? "step1d_kernel<acoustic,lossy>"
+                                                      : "step1d_kernel<acoustic,lossless>";
                 ctx->last_steps_per_launch = p.steps;
                 ctx->last_launches += 1;
             } else if (ctx->use_stream2d || ctx->use_streamv) {
@@ -1322,6 +1378,7 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
     }
     if (const char *env = getenv("FDS_TILE_ROWS")) ctx->tile_rows = atoi(env);
     if (const char *env = getenv("FDS_CHUNK_ROWS")) ctx->chunk_rows = atoi(env);
+    if (const char *env = getenv("FDS_HALO_1D")) ctx->halo_1d = std::max(2, atoi(env) / 2 * 2);
     if (const char *env = getenv("FDS_MAX_K"))
         ctx->max_k = std::max(1, std::min(kMaxStreamSteps, atoi(env)));
     // >= 9 rows + 4096 cells of padding, rounded so that the origin stays 512-byte aligned

@@ -24,11 +24,17 @@ struct Step1DArgs {
     long long ring_row;    // probe record of the first step
 };
 
-constexpr int k1DThreads = 1024;
+constexpr int k1DThreads = 1024;      // upper bound; the launch uses one thread per cell where it can
 constexpr int k1DMaxPerThread = 12;   // (tile + 2*halo) <= 12 * 1024 cells, 18 bytes each
 
-template <bool THERMAL, bool LOSSY>
+// PER = cells per thread (1 or k1DMaxPerThread). A step is a chain of four short phases separated by
+// block barriers, so its cost is instruction issue + latency of one SM, not bandwidth: the plan keeps
+// tiles at a few hundred cells with one cell per thread (PER = 1, blockDim = width rounded up to a
+// warp), which leaves every phase a few dozen instructions per warp; PER = 12 only serves tiles forced
+// larger than a block.
+template <bool THERMAL, bool LOSSY, int PER>
 __global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, StepTables t) {
+    const int nthreads = blockDim.x;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int width = a.tile + 2 * a.halo;
     double *s = reinterpret_cast<double *>(smem_raw);     // scalar component
@@ -39,9 +45,9 @@ __global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, Ste
     const int tid = threadIdx.x;
     const long long origin = (long long)blockIdx.x * a.tile - a.halo;  // global cell of local 0
 
-    for (int k = tid; k < FDS_TAB_COUNT * kMaxMaterials; k += k1DThreads)
+    for (int k = tid; k < FDS_TAB_COUNT * kMaxMaterials; k += nthreads)
         (&tabs[0][0])[k] = t.tab[k];
-    for (int l = tid; l < width; l += k1DThreads) {
+    for (int l = tid; l < width; l += nthreads) {
         const long long g = origin + l;
         s[l] = a.in[0][g];
         u[l] = THERMAL ? 0.0 : a.in[1][g];
@@ -49,13 +55,13 @@ __global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, Ste
     }
     __syncthreads();
 
-    double unew[k1DMaxPerThread];
+    double unew[PER];
     for (int q = 0; q < a.n_steps; ++q) {
         const long long sig = a.sig_index + q;
         double *__restrict__ record = t.ring + (a.ring_row + q) * t.n_slots;
 
         // 1. boundaries and probes of the scalar component
-        for (int l = tid; l < width; l += k1DThreads) {
+        for (int l = tid; l < width; l += nthreads) {
             const unsigned f = id[l];
             if (f & (kFlagBound | kFlagProbe | kClassMask)) {
                 const long long g = origin + l;
@@ -71,8 +77,8 @@ __global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, Ste
 
         // 2. vector component: backward difference of the scalar (+ viscous second difference)
 #pragma unroll
-        for (int r = 0; r < k1DMaxPerThread; ++r) {
-            const int l = tid + r * k1DThreads;
+        for (int r = 0; r < PER; ++r) {
+            const int l = tid + r * nthreads;
             if (l >= 2 && l < width - 2 && (id[l] & kIdMask)) {
                 const int m = id[l] & kIdMask, mm = id[l - 1] & kIdMask;
                 const double d = diff2(tabs[FDS_TAB_GX][mm], s[l - 1], tabs[FDS_TAB_GX][m], s[l]);
@@ -93,8 +99,8 @@ __global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, Ste
 
         // 3. boundaries and probes of the vector component
 #pragma unroll
-        for (int r = 0; r < k1DMaxPerThread; ++r) {
-            const int l = tid + r * k1DThreads;
+        for (int r = 0; r < PER; ++r) {
+            const int l = tid + r * nthreads;
             if (l >= 2 && l < width - 2 && (id[l] & kIdMask)) {
                 const unsigned f = id[l];
                 double v = unew[r];
@@ -113,8 +119,8 @@ __global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, Ste
 
         // 4. scalar component: forward difference of the vector component
 #pragma unroll
-        for (int r = 0; r < k1DMaxPerThread; ++r) {
-            const int l = tid + r * k1DThreads;
+        for (int r = 0; r < PER; ++r) {
+            const int l = tid + r * nthreads;
             if (l >= 2 && l < width - 2 && (id[l] & kIdMask)) {
                 const int m = id[l] & kIdMask, mp = id[l + 1] & kIdMask;
                 s[l] = sub(s[l], diff2(tabs[FDS_TAB_FX][m], u[l], tabs[FDS_TAB_FX][mp], u[l + 1]));
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(k1DThreads, 1) step1d_kernel(Step1DArgs a, Ste
     }
     __syncthreads();
 
-    for (int l = a.halo + tid; l < a.halo + a.tile; l += k1DThreads) {
+    for (int l = a.halo + tid; l < a.halo + a.tile; l += nthreads) {
         const long long g = origin + l;
         if (g < a.n) {
             a.out[0][g] = s[l];

@@ -49,6 +49,41 @@ def test_scenario_matches_reference_golden_bitwise(library, name):
     assert_same(got, {k: gold[k] for k in gold.files if k != 'versions'}, name)
 
 
+@pytest.mark.parametrize('name', ['acoustic1d_lossy', 'acoustic1d_lossless', 'acoustic1d_long',
+                                  'thermal1d'])
+def test_1d_kernels_match_reference_golden_bitwise(library, name):
+    """The default 1-D path is the register-resident warp kernel (fds_line1d.cuh); kernel = 1 selects
+    the shared-memory kernel (fds_step1d.cuh). Both must reproduce the reference."""
+    gold = np.load(os.path.join(GOLDEN, name + '.npz'))
+    expected = {k: gold[k] for k in gold.files if k != 'versions'}
+    for kernel, wanted in ((0, 'line1d_kernel'), (1, 'step1d_kernel')):
+        field, steps = scenarios.SCENARIOS[name](fds)
+        field.device_kernel = kernel
+        first = steps // 3
+        field.simulate(first)
+        field.simulate(steps - first)
+        assert_same(scenarios.collect(field), expected, '{} kernel {}'.format(name, kernel))
+        assert wanted in field.__dict__['_engine_state'].engine.last_launch_info()[2]
+
+
+@pytest.mark.parametrize('name', ['acoustic2d_wide', 'acoustic1d_long', 'thermal2d'])
+def test_field_without_outputs_still_advances_several_steps_per_launch(library, name):
+    """Probe records bound the steps of one chunk; a field without any Output must not fall back to
+    one step per launch (and must still match the run that has outputs)."""
+    field, steps = scenarios.SCENARIOS[name](fds)
+    twin, _ = scenarios.SCENARIOS[name](fds)
+    for component in scenarios.component_names(field):
+        getattr(field, component).outputs = []
+    field.simulate(steps)
+    twin.simulate(steps)
+    for component in scenarios.component_names(field):
+        assert np.array_equal(bits(getattr(field, component).values),
+                              bits(getattr(twin, component).values)), component
+    launches, spl, kernel = field.__dict__['_engine_state'].engine.last_launch_info()
+    if name != 'thermal2d':         # 44 cells wide: one-step kernel
+        assert spl >= 4 and launches <= -(-steps // 4) + 1, (kernel, launches, spl)
+
+
 @pytest.mark.parametrize('name', ['acoustic2d_lossless', 'acoustic1d_lossy', 'thermal2d'])
 def test_single_steps_equal_one_run(library, name):
     """sim_step() is the coupling seam (pyfds/coupling.py:81-87): host values must be coherent before
