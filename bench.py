@@ -128,14 +128,18 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def ncu_traffic(kernel, nx, rows):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of the same kernel
+    on the same per-GPU grid, if there is one (null otherwise: a capture of another grid says nothing
+    about this one)."""
     path = os.path.join(ROOT, 'profiles', 'traffic.json')
     if os.path.exists(path):
         try:
-            return json.load(open(path)).get(kernel)
+            entry = json.load(open(path)).get(kernel)
         except ValueError:
             return None
+        if isinstance(entry, dict):
+            return entry.get('{}x{}'.format(nx, rows))
     return None
 
 
@@ -330,6 +334,7 @@ def main():
                'host_cores': os.cpu_count()}
 
     if rank == 0:
+        traffic = ncu_traffic(kernel, nx, rows)
         line = {
             'metric': METRIC, 'value': value, 'unit': 'Gcell-updates/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': device_ms / args.steps,
@@ -343,10 +348,15 @@ def main():
                     6 * per_gpu_cells * 8 / 1e6),
                 'kernel': kernel, 'steps_per_launch': steps_per_launch},
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': ncu_traffic(kernel),
+                         'frac': achieved / peak, 'traffic': traffic,
                          'peak_source': peak_source,
                          'bytes_per_cell_update': BYTES_PER_CELL_UPDATE,
-                         'launch_ms': launch_ms},
+                         'launch_ms': launch_ms,
+                         # what the HBM actually carried: the committed ncu byte count of one launch
+                         # over the launch time measured in this run (temporal blocking puts the
+                         # algorithmic figure above the peak; this one cannot exceed it)
+                         'dram_gbs': traffic / (launch_ms * 1e6) if traffic else None,
+                         'dram_frac': traffic / (launch_ms * 1e6) / peak if traffic else None},
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
             'wall_seconds': wall,
         }

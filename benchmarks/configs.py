@@ -97,10 +97,28 @@ def config5(nx=32768, ny=4096, t_samples=1000):
     return bench.build_field(fds, nx, ny, t_samples), 48
 
 
-CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5}
+def config6(nx=4096, ny=4096, t_samples=1000):
+    """The lossy twin of config 2 (SURVEY.md 8d 'C2 inputs'): shear_viscosity = 1e-3 in the main
+    material, absorption_coef = 7.7 in the region; same source, wall and probes."""
+    fld = fds.Acoustic2D(t_delta=1e-7, t_samples=t_samples, x_delta=1e-3, x_samples=nx,
+                         y_delta=1e-3, y_samples=ny,
+                         material=fds.AcousticMaterial(1500, 1000, shear_viscosity=1e-3))
+    qx, qy = nx // 4, ny // 4
+    fld.add_material_region(fld.get_rect_region((qx * 1e-3, qy * 1e-3, qx * 1e-3, qy * 1e-3)),
+                            fds.AcousticMaterial(1200, 900, absorption_coef=7.7))
+    k = np.arange(t_samples)
+    fld.pressure.add_boundary(fld.get_point_region(((nx // 2) * 1e-3, (ny // 2) * 1e-3)),
+                              value=np.sin(0.1 * k) * np.exp(-((k - 200) / 60) ** 2), additive=True)
+    fld.velocity_x.add_boundary(fld.get_line_region((0, 0, 0, (ny - 1) * 1e-3)))
+    for m in range(1, 5):
+        fld.pressure.add_output(fld.get_point_region(((m * nx // 8) * 1e-3, (m * ny // 8) * 1e-3)))
+    return fld, 48
+
+
+CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5, 6: config6}
 SMALL = {1: dict(t_samples=600, nx=3000), 2: dict(nx=256, ny=192, t_samples=60),
          3: dict(nx=256, ny=160, t_samples=50), 4: dict(nx=192, ny=160, t_samples=80),
-         5: dict(nx=512, ny=96, t_samples=40)}
+         5: dict(nx=512, ny=96, t_samples=40), 6: dict(nx=256, ny=192, t_samples=60)}
 
 
 def check(number):

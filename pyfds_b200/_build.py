@@ -9,7 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, 'csrc')
 LIBRARY = os.path.join(_HERE, 'libfdsb200.so')
 SOURCES = ['fds_abi.cu']
-HEADERS = ['fds_common.cuh', 'fds_step1d.cuh', 'fds_step2d.cuh', 'fds_stream2d.cuh',
+HEADERS = ['fds_common.cuh', 'fds_aux.cuh', 'fds_step1d.cuh', 'fds_line1d.cuh', 'fds_step2d.cuh',
+           'fds_stream2d.cuh',
            'fds_streamv.cuh',
            os.path.join('..', '..', 'include', 'fdsb200.h')]
 

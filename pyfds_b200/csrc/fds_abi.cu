@@ -489,14 +489,13 @@ bool stream_supported(const fds_desc &d) {
 
 bool streamv_supported(const fds_desc &d) {
     const bool model_ok = (d.model == FDS_ACOUSTIC2D && d.lossy) || d.model == FDS_ACOUSTIC3DAXI;
-    return model_ok && d.nx % 4 == 0 && d.nx >= kStripCells;
+    return model_ok && d.nx % 4 == 0 && d.nx >= 128;
 }
 
 // steps per launch the streaming kernels support for this model
 int stream_max_steps(const fds_ctx *ctx) {
-    // the three-row window costs 64 registers per stage: a second stage spills and is slower
-    // (measured 75 vs 100 Gcell-updates/s at 4096^2)
-    if (ctx->use_streamv) return 1;
+    // the viscous / axisymmetric kernel: the 4-cell strip halo covers two steps of its stencil
+    if (ctx->use_streamv) return kMaxStreamVSteps;
     return kMaxStreamSteps;
 }
 
@@ -506,7 +505,8 @@ int stream_max_steps(const fds_ctx *ctx) {
 // vote in fds_stream2d.cuh): one warp per (strip, row).
 constexpr int kCensusBlockRows = 32;   // the census counts per strip and block of rows
 
-template <int C>   // cells per lane: 2 (fds_stream2d.cuh) or 4 (fds_streamv.cuh)
+// ONE_MATERIAL: rows of several materials never count as steady (fds_streamv.cuh)
+template <int C, bool ONE_MATERIAL>   // C = cells per lane
 __global__ void strip_census_kernel(const map_t *map, long long nx, long long rows, int n_strips,
                                     int stride, int halo, int n_blocks, int *nonplain) {
     const int lane = threadIdx.x & 31;
@@ -533,7 +533,8 @@ __global__ void strip_census_kernel(const map_t *map, long long nx, long long ro
                 comps |= 1u << c;
         const bool uniform = __all_sync(0xffffffffu, (raw & (kIdMask * unit)) == first * unit);
         const bool ok = (raw & ((kFlagBound | kFlagProbe) * unit)) == 0 && (row == 0 || raw == prev);
-        const bool classes_ok = uniform ? (comps & (comps - 1u)) == 0u : comps == 0u;
+        const bool classes_ok =
+            uniform ? (comps & (comps - 1u)) == 0u : (!ONE_MATERIAL && comps == 0u);
         if ((!__all_sync(0xffffffffu, ok) || !classes_ok) && lane == 0)
             atomicAdd(nonplain + (long long)strip * n_blocks + row / kCensusBlockRows, 1);
     }
@@ -546,10 +547,10 @@ int strip_census(fds_ctx *ctx, int n_strips) {
     if (dev_alloc(ctx, (void **)&d_counts, sizeof(int) * n, true)) return 1;
     const map_t *map = ctx->map + ctx->pad + ctx->halo;
     if (ctx->use_streamv)
-        strip_census_kernel<4><<<148 * 4, 256, 0, ctx->stream>>>(
-            map, ctx->d.nx, ctx->d.rows, n_strips, kStripStride, kStripHalo, n_blocks, d_counts);
+        strip_census_kernel<kS2LaneCells, true><<<148 * 4, 256, 0, ctx->stream>>>(
+            map, ctx->d.nx, ctx->d.rows, n_strips, kS2StripStride, kS2StripHalo, n_blocks, d_counts);
     else
-        strip_census_kernel<kS2LaneCells><<<148 * 4, 256, 0, ctx->stream>>>(
+        strip_census_kernel<kS2LaneCells, false><<<148 * 4, 256, 0, ctx->stream>>>(
             map, ctx->d.nx, ctx->d.rows, n_strips, kS2StripStride, kS2StripHalo, n_blocks, d_counts);
     FDS_CUDA(ctx, cudaGetLastError());
     ctx->strip_nonplain.assign(n, 0);
@@ -585,12 +586,10 @@ void invalidate_plans(fds_ctx *ctx) {
 // the rest chunk-major (dynamic distribution absorbs what the model misses).
 int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int k, int lag_rows) {
     const long long rows = plan.row_end - plan.row_begin;
-    const double slots = 148.0 * (ctx->use_streamv ? kStreamCtasPerSm : kS2CtasPerSm) * kStreamWarps;
+    const double slots = 148.0 * (ctx->use_streamv ? kSVCtasPerSm : kS2CtasPerSm) * kStreamWarps;
     const double overhead = 2.0 * lag_rows + 4.0;
-    // measured on B200 (4096^2, bench.py, 3 CTAs/SM): 1.5 and 2.5 -> 346, 4 -> 341 Gcell-updates/s. The
-    // viscous / axisymmetric kernel has its own fast-path test and no branch-free body: all rows
-    // count alike.
-    double general_weight = ctx->use_streamv ? 1.0 : 2.5;
+    // measured on B200 (4096^2, bench.py, 3 CTAs/SM): 1.5 and 2.5 -> 346, 4 -> 341 Gcell-updates/s.
+    double general_weight = 2.5;
     if (const char *env = getenv("FDS_GENERAL_WEIGHT")) general_weight = atof(env);
     const int nb = ctx->census_blocks;
     auto row_cost = [&](int s, long long row) {
@@ -632,7 +631,7 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
         // 4 rounds 361, 16 rounds of 128-row tasks 401 Gcell-updates/s -- a quarter of the time was
         // the tail of the slowest SMs), so tasks stay about kTargetRows tall and the dynamic
         // distribution evens the SMs out; shorter tasks pay more for the rows streamed twice.
-        double target_rows = ctx->use_streamv ? 64.0 : 128.0;
+        double target_rows = 128.0;
         if (const char *env = getenv("FDS_TARGET_ROWS")) target_rows = std::max(8.0, atof(env));
         double total_cost = 0;
         for (int s = 0; s < n_strips; ++s) total_cost += strip_cost[(size_t)s];
@@ -745,14 +744,14 @@ int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
 template <int K, bool AXI, bool VISC>
 int launch_streamv(fds_ctx *ctx, const StreamVArgs &av) {
     auto kernel = streamv_kernel<K, AXI, VISC>;
-    const int smem = kStreamWarps * kWarpRingBytes;
+    const int smem = kStreamWarps * kS2WarpRingBytes;
     static bool configured = false;
     if (!configured) {
         FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     const long long want = (av.base.n_tasks + kStreamWarps - 1) / kStreamWarps;
-    const long long ctas = std::min<long long>(want, 148 * kStreamCtasPerSm);
+    const long long ctas = std::min<long long>(want, 148 * kSVCtasPerSm);
     kernel<<<(unsigned)ctas, kStreamWarps * 32, smem, ctx->stream>>>(av);
     FDS_CUDA(ctx, cudaGetLastError());
     return 0;
@@ -761,7 +760,7 @@ int launch_streamv(fds_ctx *ctx, const StreamVArgs &av) {
 int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     const long long rows = a.row_end - a.row_begin;
     if (rows <= 0) return 0;
-    const int stride = ctx->use_streamv ? kStripStride : kS2StripStride;
+    const int stride = kS2StripStride;
     a.n_strips = (int)((a.nx + stride - 1) / stride);
     if (!ctx->census_valid && strip_census(ctx, a.n_strips)) return 1;
     fds_ctx::StreamPlan *plan = nullptr;
@@ -792,11 +791,20 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
         av.cvec = ctx->cvec;
         av.n_mat1 = ctx->d.n_materials + 1;
         const bool lossy = ctx->d.lossy != 0;
-        if (ctx->d.model == FDS_ACOUSTIC3DAXI && k == 1)
-            return lossy ? launch_streamv<1, true, true>(ctx, av) : launch_streamv<1, true, false>(ctx, av);
-        if (ctx->d.model == FDS_ACOUSTIC2D && lossy && k == 1)
-            return launch_streamv<1, false, true>(ctx, av);
-        return fail(ctx, "streamv: unsupported model / step count");
+        const bool axi = ctx->d.model == FDS_ACOUSTIC3DAXI;
+        if (!axi && !(ctx->d.model == FDS_ACOUSTIC2D && lossy))
+            return fail(ctx, "streamv: unsupported model");
+#define FDS_STREAMV_CASE(K_)                                                                 \
+    case K_:                                                                                 \
+        return !axi    ? launch_streamv<K_, false, true>(ctx, av)                            \
+               : lossy ? launch_streamv<K_, true, true>(ctx, av)                             \
+                       : launch_streamv<K_, true, false>(ctx, av);
+        switch (k) {
+            FDS_STREAMV_CASE(1)
+            FDS_STREAMV_CASE(2)
+        }
+#undef FDS_STREAMV_CASE
+        return fail(ctx, "streamv: bad step count");
     }
 #define FDS_STREAM_CASE(K_)                                                                  \
     case K_:                                                                                 \

@@ -41,24 +41,8 @@
 
 namespace fds {
 
-// ---- shared with fds_streamv.cuh (viscous / axisymmetric kernel: 4 cells per lane, 128-cell strips)
-constexpr int kStripCells = 128;     // cells a warp streams per row (4 per lane)
-constexpr int kStripHalo = 4;        // halo cells either side = one lane
-constexpr int kStripStride = kStripCells - 2 * kStripHalo;   // 120 owned cells per strip
-#ifndef FDS_STREAM_MIN_CTAS
-#define FDS_STREAM_MIN_CTAS 2
-#endif
-#ifndef FDS_STREAM_RING
-#define FDS_STREAM_RING 6
-#endif
-constexpr int kStreamCtasPerSm = FDS_STREAM_MIN_CTAS;   // resident CTAs per SM (register budget)
-constexpr int kRingDepth = FDS_STREAM_RING;   // rows in flight per warp
 constexpr int kStreamWarps = 4;      // warps per CTA
 constexpr int kMaxStreamSteps = 4;   // K
-constexpr int kMapWindowBytes = kStripCells * 2 + 16;         // 128 map entries + alignment slack
-constexpr int kSlotBytes = 3 * kStripCells * 8 + kMapWindowBytes + 16;   // p, vx, vy rows + map
-constexpr int kScratchBytes = 32 * 64;                        // slow path: 8 doubles per lane
-constexpr int kWarpRingBytes = kRingDepth * kSlotBytes + kScratchBytes + 64;   // + mbarriers
 
 struct Stream2DArgs {
     const double *in[3];
@@ -125,41 +109,6 @@ __device__ __forceinline__ double shfl_up1(double v) {
 __device__ __forceinline__ double shfl_down1(double v) {
     return __shfl_down_sync(0xffffffffu, v, 1);
 }
-
-// Slow path, taken only by rows that carry a boundary operation or a probe: applies the boundary
-// operations of `n_comp` consecutive components (first_comp, first_comp + 1) to this lane's 4 cells and
-// records probes. Values travel through a per-lane shared-memory scratch so that the call site stays a
-// handful of instructions (the pipeline itself must fit the instruction cache).
-__device__ __noinline__ void stream_slow_cells(const StepTables *__restrict__ tp, int first_comp,
-                                               int n_comp, long long sig, long long record_row,
-                                               long long cell0, unsigned long long ids, bool owned,
-                                               double *scratch) {
-    for (int k = 0; k < n_comp; ++k) {
-        const int comp = first_comp + k;
-        for (int c = 0; c < 4; ++c) {
-            const unsigned f = (unsigned)(ids >> (16 * c));
-            if (!(f & (kFlagBound | kFlagProbe))) continue;
-            double v = scratch[4 * k + c];
-            if (f & kFlagBound) {
-                v = apply_bounds(tp->bound[comp], tp->rows, tp->signals, tp->sig_steps, sig,
-                                 cell0 + c, v);
-                scratch[4 * k + c] = v;
-            }
-            if ((f & kFlagProbe) && owned)
-                write_probes(tp->probe[comp], tp->rows, tp->ring + record_row * tp->n_slots,
-                             cell0 + c, v);
-        }
-    }
-}
-
-// Row metadata that travels through the pipeline with the row.
-struct RowInfo {
-    unsigned long long ids;   // the 4 map entries of this lane's cells
-    int uniform;       // material id shared by all cells of the row that matter, or -1
-    bool flagged;      // some cell of the row (any lane) needs the slow path (table lookup, probe)
-    unsigned classed;  // bit c set: some cell of the row (any lane) carries an inline constant
-                       // boundary operation on component c
-};
 
 // =====================================================================================================
 // stream2d_kernel: lossless Acoustic2D / Thermal2D, K steps per launch
@@ -235,7 +184,10 @@ __device__ __forceinline__ RowTag s2_row_meta(const unsigned char *src, int map_
     return m;
 }
 
-// Slow path of this kernel (see stream_slow_cells): 2 cells per lane, 32-bit map word.
+// Slow path, taken only by rows that carry a boundary operation or a probe: applies the boundary
+// operations of `n_comp` consecutive components (first_comp, first_comp + 1) to this lane's 2 cells and
+// records probes. Values travel through a per-lane shared-memory scratch so that the call site stays a
+// handful of instructions (the pipeline itself must fit the instruction cache).
 __device__ __noinline__ void s2_slow_cells(const StepTables *__restrict__ tp, int first_comp,
                                            int n_comp, long long sig, long long record_row,
                                            long long cell0, unsigned ids, bool owned,

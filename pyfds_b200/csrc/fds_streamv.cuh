@@ -1,17 +1,27 @@
 // Streaming kernel for the viscous (lossy) Acoustic2D leapfrog and for Acoustic3DAxi (lossless and
-// lossy): pyfds/acoustics.py:111-128 and 205-225. Same machinery as fds_stream2d.cuh (one warp = one
-// 120-cell strip x a chunk of rows, rows through a TMA ring, K-stage time pipeline in registers, lanes
-// hold 4 consecutive cells, x-neighbours by shuffle), but the viscous 5-point operator on the OLD
-// velocities needs a three-row window, so a stage lags TWO rows behind its input:
+// lossy): pyfds/acoustics.py:111-128 and 205-225, K <= 2 time steps per launch.
+//
+// Same machinery and geometry as stream2d_kernel (fds_stream2d.cuh): one warp = one 64-cell strip
+// (2 cells per lane, 4 halo cells either side, 56 owned) x a chunk of rows, rows arriving in pairs
+// through the bulk-copy ring, a K-stage time pipeline in registers, x-neighbours by warp shuffle,
+// tasks from the cost-balanced table. What differs is the stage: the viscous 5-point operator works
+// on the OLD velocities, so a stage needs a three-row window and lags TWO rows behind its input:
 //
 //   row q arrives at level s  ->  new vx, vy of row q-1 (needs old vx, vy of rows q-2, q-1, q and p of
 //   rows q-2, q-1)            ->  new p of row q-2 (needs new vx of row q-2, new vy of rows q-2, q-1)
 //
-// and the dependency cone grows 1 cell to the left and 2 to the right per step, which the 4-cell strip
-// halo covers for K <= 2 (only K = 1 is instantiated: a second stage spills registers and is slower). Per stage 8 row fragments stay in registers (p after boundaries, old vx, vy
-// of two rows; new vx, vy of one row). Axisymmetric coefficients depend on the column: for the
-// warp-uniform material path the per-column values of this lane's cells (and its two neighbours) are
-// kept in registers and reloaded only when the material changes; K = 1 there (register budget).
+// Per stage eight row fragments stay in registers (p after boundaries, old vx, old vy of rows q-1 and
+// q-2; new vx, vy of row q-2): 32 registers per lane and stage. The dependency cone grows one cell to
+// the left and two to the right per step, which the 4-cell strip halo covers for K <= 2.
+//
+// STEADY rows (one material, no table lookup, no probe, constant operations on at most one component,
+// the lane's map word repeating row after row) run through a branch-free body that takes two rows per
+// iteration; the two window rows swap roles between the halves of the iteration, so no register is
+// moved. Material coefficients -- and, for the axisymmetric model, the per-column values of this
+// lane's cells and of its two neighbours (a_p_vx / r, the viscous x diagonals with the 1/r term, r,
+// r^2) -- are loaded into registers when such a run starts. Every other row takes the general row
+// iteration: one rolled copy of the stage code with per-cell coefficient lookups, inline classes and
+// the table slow path.
 //
 // Every value is produced by the same __dmul_rn/__dadd_rn sequence as cell_body in fds_step2d.cuh.
 #pragma once
@@ -28,8 +38,112 @@ struct StreamVArgs {
     int n_mat1;
 };
 
+#ifndef FDS_SV_CTAS
+#define FDS_SV_CTAS 3
+#endif
+constexpr int kSVCtasPerSm = FDS_SV_CTAS;   // resident CTAs per SM (register budget: 168 at 3)
+constexpr int kMaxStreamVSteps = 2;         // K: bounded by the strip halo (see above)
+
+// Coefficients of ONE material for this lane's cells (steady rows). Members a model does not use are
+// never loaded (the struct lives in registers, everything is inlined).
+template <bool AXI>
+struct SVCoef {
+    double gx, gy, fy, fx0;                         // a_vx_p, a_vy_p, a_p_vy, a_p_vx factors
+    double v0, vmn, vpn, vm1s, vp1s, eb;            // a_v_v diagonals, axisymmetric extra term
+    double fxc[kS2LaneCells + 1];                   // AXI: a_p_vx / r of columns x0 .. x0+C
+    double vm1c[kS2LaneCells], vp1c[kS2LaneCells];  // AXI: x diagonals of cells c-1 / c+1
+    double r[kS2LaneCells + 1], rr[kS2LaneCells];   // AXI: r of columns x0 .. x0+C, r^2 of x0 .. x0+C-1
+    __device__ __forceinline__ double fx(int c) const { return AXI ? fxc[c] : fx0; }
+    __device__ __forceinline__ double vm1(int c) const { return AXI ? vm1c[c] : vm1s; }
+    __device__ __forceinline__ double vp1(int c) const { return AXI ? vp1c[c] : vp1s; }
+};
+
+// One stage on a steady row: `cur` = row q at level s on entry, row q-2 at level s+1 on exit.
+// pA/uA/vA = p (after boundaries), old vx, old vy of row q-1; pB/uB/vB = the same of row q-2 on entry
+// and of row q on exit (the next row's "A": the caller swaps the roles). U/V = new vx, vy of row q-2
+// (read), Un/Vn = new vx, vy of row q-1 (written). CC, ca, cv: as in steady_stage (fds_stream2d.cuh).
+template <bool AXI, bool VISC, int CC>
+__device__ __forceinline__ void sv_steady_stage(
+    double (&cur)[3][kS2LaneCells], const double (&pA)[kS2LaneCells],
+    const double (&uA)[kS2LaneCells], const double (&vA)[kS2LaneCells], double (&pB)[kS2LaneCells],
+    double (&uB)[kS2LaneCells], double (&vB)[kS2LaneCells], const double (&U)[kS2LaneCells],
+    const double (&V)[kS2LaneCells], double (&Un)[kS2LaneCells], double (&Vn)[kS2LaneCells],
+    const SVCoef<AXI> &k, const double (&ca)[kS2LaneCells], const double (&cv)[kS2LaneCells]) {
+    constexpr int C = kS2LaneCells;
+    if (CC == 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) cur[0][c] = add(mul(ca[c], cur[0][c]), cv[c]);
+    }
+    const double p1_left = shfl_up1(pA[C - 1]);
+    double u1_left = 0, u1_right = 0, v1_left = 0, v1_right = 0;
+    if (VISC) {
+        u1_left = shfl_up1(uA[C - 1]);
+        u1_right = shfl_down1(uA[0]);
+        v1_left = shfl_up1(vA[C - 1]);
+        v1_right = shfl_down1(vA[0]);
+    }
+    const double un2_right = shfl_down1(U[0]);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const double pl = c ? pA[c - 1] : p1_left;
+        const double du = diff2(k.gx, pl, k.gx, pA[c]);
+        const double dv = diff2(k.gy, pB[c], k.gy, pA[c]);
+        const double uold = uA[c], vold = vA[c];
+        if (VISC) {
+            const double ul = c ? uA[c - 1] : u1_left;
+            const double ur = c < C - 1 ? uA[c + 1] : u1_right;
+            const double vl = c ? vA[c - 1] : v1_left;
+            const double vr = c < C - 1 ? vA[c + 1] : v1_right;
+            double vis = acc0(mul(k.vmn, uB[c]));
+            vis = add(vis, mul(k.vm1(c), ul));
+            vis = add(vis, mul(k.v0, uold));
+            vis = add(vis, mul(k.vp1(c), ur));
+            vis = add(vis, mul(k.vpn, cur[1][c]));
+            double rhs = sub(du, vis);
+            if (AXI) rhs = add(rhs, mul(k.eb, uold) / k.rr[c]);
+            Un[c] = sub(uold, rhs);
+            double visv = acc0(mul(k.vmn, vB[c]));
+            visv = add(visv, mul(k.vm1(c), vl));
+            visv = add(visv, mul(k.v0, vold));
+            visv = add(visv, mul(k.vp1(c), vr));
+            visv = add(visv, mul(k.vpn, cur[2][c]));
+            Vn[c] = sub(vold, sub(dv, visv));
+        } else {
+            Un[c] = AXI ? sub(uold, add(du, mul(0.0, uold))) : sub(uold, du);
+            Vn[c] = sub(vold, dv);
+        }
+        if (CC == 1) Un[c] = add(mul(ca[c], Un[c]), cv[c]);
+        if (CC == 2) Vn[c] = add(mul(ca[c], Vn[c]), cv[c]);
+    }
+    double np[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        double f0 = U[c], f1 = c < C - 1 ? U[c + 1] : un2_right;
+        if (AXI) {
+            f0 = mul(f0, k.r[c]);
+            f1 = mul(f1, k.r[c + 1]);
+        }
+        const double divx = diff2(k.fx(c), f0, k.fx(c + 1), f1);
+        const double divy = diff2(k.fy, V[c], k.fy, Vn[c]);
+        np[c] = sub(pB[c], add(divx, divy));
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        pB[c] = cur[0][c];
+        uB[c] = cur[1][c];
+        vB[c] = cur[2][c];
+        cur[0][c] = np[c];
+        cur[1][c] = U[c];
+        cur[2][c] = V[c];
+    }
+}
+
 template <int K, bool AXI, bool VISC>
-__global__ void __launch_bounds__(kStreamWarps * 32, 2) streamv_kernel(StreamVArgs av) {
+__global__ void __launch_bounds__(kStreamWarps * 32, kSVCtasPerSm) streamv_kernel(StreamVArgs av) {
+    constexpr int C = kS2LaneCells;
+    constexpr int kLag = 2 * K;     // rows between the input row and the row stored
+    constexpr int W = 2 * K + 1;    // row tags in flight: rows r .. r-2K
+    static_assert(K >= 1 && K <= kMaxStreamVSteps, "the strip halo covers two steps");
     const Stream2DArgs &a = av.base;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double tabs[FDS_TAB_COUNT][kMaxMaterials];
@@ -45,17 +159,15 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) streamv_kernel(StreamVAr
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nx = a.nx;
-    unsigned char *ring = smem_raw + warp * kWarpRingBytes;
-    double *scratch = reinterpret_cast<double *>(ring + kRingDepth * kSlotBytes) + lane * 8;
-    unsigned long long *bars =
-        reinterpret_cast<unsigned long long *>(ring + kRingDepth * kSlotBytes + kScratchBytes);
-    const int swap = (lane >> 2) & 1;
-    const int off_a = lane * 32 + swap * 16, off_b = lane * 32 + (swap ^ 1) * 16;
-    unsigned phase_bits = 0;
-    constexpr int kLag = 2 * K;     // rows between the input row and the row stored
+    unsigned char *ring = smem_raw + warp * kS2WarpRingBytes;
+    double *scratch =
+        reinterpret_cast<double *>(ring + kS2RingDepth * kS2SlotBytes) + lane * 2 * C;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(
+        ring + kS2RingDepth * kS2SlotBytes + kS2ScratchBytes);
+    unsigned phase_bits = 0;   // parity of every pair barrier (the barriers live across tasks)
 
     if (lane == 0) {
-        for (int d = 0; d < kRingDepth; ++d) mbar_init(&bars[d], 1);
+        for (int d = 0; d < kS2RingDepth / 2; ++d) mbar_init(&bars[d], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -66,320 +178,428 @@ __global__ void __launch_bounds__(kStreamWarps * 32, 2) streamv_kernel(StreamVAr
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= a.n_tasks) break;
         const int4 tk = __ldg(a.tasks + task);
-        const long long ys = tk.y, ye = tk.z;
-        const long long xs = (long long)tk.x * kStripStride - kStripHalo;
-        const long long r0 = ys - kLag, r1 = ye + kLag;
+        const int ys = tk.y, ye = tk.z;
+        const long long xs = (long long)tk.x * kS2StripStride - kS2StripHalo;   // column of lane 0
+        const int r0 = ys - kLag, r1 = ye + kLag;                               // rows streamed in
 
-        auto issue = [&](long long r, int slot) {
-            const long long base = r * nx + xs;
-            const long long base8 = base & ~7LL;
-            unsigned char *dst = ring + slot * kSlotBytes;
-            mbar_expect_tx(&bars[slot], 3 * kStripCells * 8 + kMapWindowBytes);
-            bulk_load(dst, a.in[0] + base, kStripCells * 8, &bars[slot]);
-            bulk_load(dst + kStripCells * 8, a.in[1] + base, kStripCells * 8, &bars[slot]);
-            bulk_load(dst + 2 * kStripCells * 8, a.in[2] + base, kStripCells * 8, &bars[slot]);
-            bulk_load(dst + 3 * kStripCells * 8, a.map + base8, kMapWindowBytes, &bars[slot]);
+        // rows r, r+1 (r - r0 even) into ring slots `slot`, `slot` + 1 (slot even), one barrier
+        auto issue_pair = [&](int r, int slot) {
+            const int n_rows = r + 1 < r1 ? 2 : 1;
+            void *bar = &bars[slot >> 1];
+            mbar_expect_tx(bar, n_rows * (3 * kS2FieldBytes + kS2MapWindowBytes));
+            long long base = (long long)r * nx + xs;   // flat cell index of the strip start
+            unsigned char *dst = ring + slot * kS2SlotBytes;
+            for (int h = 0; h < n_rows; ++h) {
+                bulk_load(dst, a.in[0] + base, kS2FieldBytes, bar);
+                bulk_load(dst + kS2FieldBytes, a.in[1] + base, kS2FieldBytes, bar);
+                bulk_load(dst + 2 * kS2FieldBytes, a.in[2] + base, kS2FieldBytes, bar);
+                bulk_load(dst + 3 * kS2FieldBytes, a.map + (base & ~7LL), kS2MapWindowBytes, bar);
+                base += nx;
+                dst += kS2SlotBytes;
+            }
         };
         if (lane == 0)
-            for (int d = 0; d < kRingDepth && r0 + d < r1; ++d) issue(r0 + d, d);
+            for (int d = 0; d < kS2RingDepth && r0 + d < r1; d += 2) issue_pair(r0 + d, d);
+        // optional counters (tests): as in stream2d_kernel, a.stats[4] stays 0 here
+        if (a.stats && lane == 0) atomicAdd(a.stats + 6, (unsigned long long)(r1 - r0));
 
-        // per stage: p after boundaries, old vx, old vy of rows q-1 [0] and q-2 [1]; new vx, vy of
-        // row q-2
-        double pb[K][2][4], uo[K][2][4], vo[K][2][4], un[K][4], vn[K][4];
-        RowInfo info[2 * K + 1];
+        // pipeline state per stage: p after boundaries, old vx, old vy of rows q-1 (A) and q-2 (B);
+        // new vx, vy of row q-2
+        double pA[K][C], uA[K][C], vA[K][C], pB[K][C], uB[K][C], vB[K][C], un[K][C], vn[K][C];
+        RowTag info[W];
 #pragma unroll
         for (int s = 0; s < K; ++s)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                pb[s][0][c] = pb[s][1][c] = uo[s][0][c] = uo[s][1][c] = 0.0;
-                vo[s][0][c] = vo[s][1][c] = un[s][c] = vn[s][c] = 0.0;
+            for (int c = 0; c < C; ++c) {
+                pA[s][c] = uA[s][c] = vA[s][c] = pB[s][c] = uB[s][c] = vB[s][c] = 0.0;
+                un[s][c] = vn[s][c] = 0.0;
             }
 #pragma unroll
-        for (int s = 0; s <= 2 * K; ++s) info[s] = RowInfo{0ull, 0, false, 0u};
+        for (int s = 0; s < W; ++s) info[s] = RowTag{0u, 0u};
+        int run = 0;
 
-        const long long x0 = xs + 4 * lane;
-        const bool lane_owned = lane >= 1 && lane <= 30 && x0 < nx;
-        long long cell_r = r0 * nx + x0;
+        const long long x0 = xs + C * lane;
+        const bool lane_owned = lane >= kS2HaloLanes && lane < 32 - kS2HaloLanes && x0 < nx;
+        const bool lane_relevant = x0 < nx + kS2StripHalo;
+        long long cell_r = (long long)r0 * nx + x0;   // flat index of this lane's first cell in row r
         const int map_step = (int)(nx & 7LL);
-        int map_off = (int)((r0 * nx + xs) & 7LL);
+        int map_off = (int)(((long long)r0 * nx + xs) & 7LL);   // entry offset in the map window
 
-        // axisymmetric: per-column values of the uniform material for columns x0-1 .. x0+4
-        double cx_fx[5], cx_vm1[4], cx_vp1[4], cx_r[5], cx_rr[4];
-        long long cols[6];
-        int cx_material = -1;
-        if (AXI) {
-#pragma unroll
-            for (int c = 0; c < 6; ++c) {
-                long long col = (x0 - 1 + c) % nx;
-                cols[c] = col < 0 ? col + nx : col;
-            }
-#pragma unroll
-            for (int c = 0; c < 5; ++c) cx_r[c] = __ldg(av.cvec + FDS_CVEC_R * nx + cols[c + 1]);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) cx_rr[c] = __ldg(av.cvec + FDS_CVEC_RR * nx + cols[c + 1]);
-        }
+        // column of cell c (-1 .. C) of this lane, wrapped into the row like the flat index
+        auto col_of = [&](int c) {
+            long long col = x0 + c;
+            if (col < 0) col += nx;
+            if (col >= nx) col -= nx;
+            if (col >= nx) col -= nx;
+            return col;
+        };
         auto ctab = [&](int which, int m, long long col) {
             return __ldg(av.ctab + ((long long)which * av.n_mat1 + m) * nx + col);
         };
 
-        int slot = 0;
-        for (long long r = r0; r < r1; ++r) {
-            mbar_wait(&bars[slot], (phase_bits >> slot) & 1u);
-            phase_bits ^= 1u << slot;
-            const unsigned char *src = ring + slot * kSlotBytes;
-            double cur[3][4];
+        auto load_row = [&](double (&cur)[3][C], const unsigned char *src) {
 #pragma unroll
             for (int f = 0; f < 3; ++f) {
-                const double2 va =
-                    *reinterpret_cast<const double2 *>(src + f * kStripCells * 8 + off_a);
-                const double2 vb =
-                    *reinterpret_cast<const double2 *>(src + f * kStripCells * 8 + off_b);
-                cur[f][0] = swap ? vb.x : va.x;
-                cur[f][1] = swap ? vb.y : va.y;
-                cur[f][2] = swap ? va.x : vb.x;
-                cur[f][3] = swap ? va.y : vb.y;
+                const double2 v =
+                    *reinterpret_cast<const double2 *>(src + f * kS2FieldBytes + lane * 16);
+                cur[f][0] = v.x;
+                cur[f][1] = v.y;
             }
-            const unsigned long long idw = *reinterpret_cast<const unsigned long long *>(
-                src + 3 * kStripCells * 8 + 2 * map_off + 8 * lane);
-            map_off = (map_off + map_step) & 7;
-            __syncwarp();
-            if (lane == 0 && r + kRingDepth < r1) issue(r + kRingDepth, slot);
-            if (++slot == kRingDepth) slot = 0;
+        };
+        auto store_row = [&](const double (&cur)[3][C], int orow, long long o) {
+            if (lane_owned && orow >= ys && orow < ye) {
+#pragma unroll
+                for (int f = 0; f < 3; ++f)
+                    __stcs(reinterpret_cast<double2 *>(a.out[f] + o),
+                           make_double2(cur[f][0], cur[f][1]));
+            }
+        };
 
+        // metadata is fetched two rows ahead of the arithmetic: m0 = row r, m1 = row r+1
+        int fetch_row = r0, fetch_slot = 0;
+        int arrived = r0;       // rows below this one have landed in the ring (always whole pairs)
+        auto await = [&](int row, int slot) {
+            if (row >= arrived) {
+                mbar_wait(&bars[slot >> 1], (phase_bits >> (slot >> 1)) & 1u);
+                phase_bits ^= 1u << (slot >> 1);
+                arrived += 2;
+            }
+        };
+        auto fetch = [&]() {
+            RowTag m = RowTag{0u, 32u};   // past the last row: never steady
+            if (fetch_row < r1) {
+                await(fetch_row, fetch_slot);
+                m = s2_row_meta(ring + fetch_slot * kS2SlotBytes, map_off, lane, lane_relevant);
+                map_off = (map_off + map_step) & 7;
+                if (++fetch_slot == kS2RingDepth) fetch_slot = 0;
+                ++fetch_row;
+            }
+            return m;
+        };
+        // steady for THIS kernel: RowTag::steady and of one material
+        auto sv_steady = [](const RowTag &t) { return t.steady() && !(t.bits & 32u); };
+        RowTag m0 = fetch(), m1 = fetch();
+        // What the pipeline computes from the rows above r0 (zero state) never reaches an owned row,
+        // so those rows may as well count as rows like the first one (see stream2d_kernel).
+        if (sv_steady(m0)) {
 #pragma unroll
-            for (int s = 2 * K; s > 0; --s) info[s] = info[s - 1];
-            {
-                const unsigned long long first = __shfl_sync(0xffffffffu, idw, 0) & kIdMask;
-                const bool uni = __all_sync(0xffffffffu, (idw & 0x001f001f001f001full) ==
-                                                             first * 0x0001000100010001ull);
-                info[0].ids = idw;
-                info[0].uniform = uni ? (int)first : -1;
-                info[0].flagged = __any_sync(0xffffffffu, (idw & 0x0060006000600060ull) != 0);
-                info[0].classed = 0u;
-                if (__any_sync(0xffffffffu, (idw & 0xff80ff80ff80ff80ull) != 0)) {
+            for (int s = 0; s < W; ++s) info[s] = m0;
+            run = W;
+        }
+
+        int slot = 0;
+        int r = r0;
+        // ---- steady pairs: rows r-2K .. r+1 carry the same map words (one material, no table
+        // lookup, no probe, constant operations on component CC only, or none: CC = -1) -------------
+        auto steady_pairs = [&](auto cc_tag) {
+            constexpr int CC = decltype(cc_tag)::value;
+            if (a.stats && lane == 0) atomicAdd(a.stats + CC + 1, 1ull);
+            const unsigned my_ids = info[0].ids;
+            const int m = (int)(info[0].bits & kIdMask);
+            SVCoef<AXI> k;
+            k.gx = tabs[FDS_TAB_GX][m];
+            k.gy = tabs[FDS_TAB_GY][m];
+            k.fy = tabs[FDS_TAB_FY][m];
+            k.fx0 = tabs[FDS_TAB_FX][m];
+            if (VISC) {
+                k.v0 = tabs[FDS_TAB_V0][m];
+                k.vmn = tabs[FDS_TAB_VMN][m];
+                k.vpn = tabs[FDS_TAB_VPN][m];
+                k.vm1s = tabs[FDS_TAB_VM1][m];
+                k.vp1s = tabs[FDS_TAB_VP1][m];
+                k.eb = tabs[FDS_TAB_EB][m];
+            }
+            if (AXI) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const unsigned long long m = 0x0007000700070007ull << class_shift(c);
-                        if (__any_sync(0xffffffffu, (idw & m) != 0)) info[0].classed |= 1u << c;
+                for (int c = 0; c <= C; ++c) {
+                    k.fxc[c] = ctab(FDS_CTAB_FX, m, col_of(c));
+                    k.r[c] = __ldg(av.cvec + FDS_CVEC_R * nx + col_of(c));
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    k.rr[c] = __ldg(av.cvec + FDS_CVEC_RR * nx + col_of(c));
+                    if (VISC) {
+                        k.vm1c[c] = ctab(FDS_CTAB_VM1, m, col_of(c - 1));
+                        k.vp1c[c] = ctab(FDS_CTAB_VP1, m, col_of(c + 1));
                     }
                 }
             }
+            double ca[C], cv[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const unsigned kc =
+                    CC < 0 ? 0u : (my_ids >> (16 * c + class_shift(CC < 0 ? 0 : CC))) & 7u;
+                ca[c] = kc ? cls_alpha[CC < 0 ? 0 : CC][kc] : 1.0;
+                cv[c] = kc ? cls_value[CC < 0 ? 0 : CC][kc] : -0.0;
+            }
+            for (;;) {
+                double cur[3][C], un1[K][C], vn1[K][C];
+                load_row(cur, ring + slot * kS2SlotBytes);
+#pragma unroll
+                for (int s = 0; s < K; ++s)
+                    sv_steady_stage<AXI, VISC, CC>(cur, pA[s], uA[s], vA[s], pB[s], uB[s], vB[s],
+                                                   un[s], vn[s], un1[s], vn1[s], k, ca, cv);
+                store_row(cur, r - kLag, cell_r - kLag * nx);
+
+                load_row(cur, ring + (slot + 1) * kS2SlotBytes);
+                __syncwarp();
+                if (lane == 0 && r + kS2RingDepth < r1) issue_pair(r + kS2RingDepth, slot);
+#pragma unroll
+                for (int s = 0; s < K; ++s)
+                    sv_steady_stage<AXI, VISC, CC>(cur, pB[s], uB[s], vB[s], pA[s], uA[s], vA[s],
+                                                   un1[s], vn1[s], un[s], vn[s], k, ca, cv);
+                store_row(cur, r + 1 - kLag, cell_r + nx - kLag * nx);
+                cell_r += 2 * nx;
+                r += 2;
+                slot = slot + 2 == kS2RingDepth ? 0 : slot + 2;
+                // the lookahead is implied in here: rows r, r+1 have landed and been examined
+                fetch_row = r;
+                fetch_slot = slot;
+                arrived = r;
+                if (r + 1 < r1) {
+                    // next pair: one vote instead of the full metadata
+                    mbar_wait(&bars[slot >> 1], (phase_bits >> (slot >> 1)) & 1u);
+                    phase_bits ^= 1u << (slot >> 1);
+                    arrived = r + 2;
+                    const unsigned char *src = ring + slot * kS2SlotBytes + 3 * kS2FieldBytes;
+                    const int map_off1 = (map_off + map_step) & 7;
+                    const unsigned raw0 =
+                        *reinterpret_cast<const unsigned *>(src + 2 * map_off + 4 * lane);
+                    const unsigned raw1 = *reinterpret_cast<const unsigned *>(
+                        src + kS2SlotBytes + 2 * map_off1 + 4 * lane);
+                    if (__all_sync(0xffffffffu,
+                                   !lane_relevant || (raw0 == my_ids && raw1 == my_ids))) {
+                        map_off = (map_off1 + map_step) & 7;
+                        continue;
+                    }
+                }
+                m0 = fetch();
+                m1 = fetch();
+                break;
+            }
+        };
+
+        while (r < r1) {
+            if (run >= W && !(slot & 1) && sv_steady(m0) && m0.bits == info[0].bits &&
+                m1.bits == m0.bits &&
+                (m0.plain() ||
+                 __all_sync(0xffffffffu, m0.ids == info[0].ids && m1.ids == info[0].ids))) {
+                using std::integral_constant;
+                switch (m0.classed()) {
+                    case 0u: steady_pairs(integral_constant<int, -1>{}); break;
+                    case 1u: steady_pairs(integral_constant<int, 0>{}); break;
+                    case 2u: steady_pairs(integral_constant<int, 1>{}); break;
+                    default: steady_pairs(integral_constant<int, 2>{}); break;
+                }
+                continue;
+            }
+
+            // ---- general row iteration -----------------------------------------------------------
+            if (a.stats && lane == 0) atomicAdd(a.stats + 5, 1ull);
+            double cur[3][C];
+            load_row(cur, ring + slot * kS2SlotBytes);
+            __syncwarp();
+            // the pair of ring slots is free once its second row has been read
+            if (lane == 0 && (slot & 1) && r - 1 + kS2RingDepth < r1)
+                issue_pair(r - 1 + kS2RingDepth, slot - 1);
 
 #pragma unroll
+            for (int s = W - 1; s > 0; --s) info[s] = info[s - 1];
+            info[0] = m0;
+            // run = rows in a row, the last one being info[0], that are steady with the same map words
+            if (!sv_steady(info[0]))
+                run = 0;
+            else if (run > 0 && info[0].bits == info[1].bits &&
+                     (info[0].plain() || __all_sync(0xffffffffu, info[0].ids == info[1].ids)))
+                ++run;
+            else
+                run = 1;
+
+            // The K stages run as a rolled loop over one copy of the stage code: stage s works on
+            // state index 0 and on the tags info[0..2] (rows q, q-1, q-2); after each stage the state
+            // rotates by one place and the tags by two. K rotations put the state back in place, the
+            // 2K + 1 tags need one more place after the loop.
+#pragma unroll 1
             for (int s = 0; s < K; ++s) {
-                // stage s: cur = row q = r - 2s at level s -> cur = row q-2 at level s+1
-                const RowInfo &rq = info[2 * s], &r1i = info[2 * s + 1], &r2i = info[2 * s + 2];
+                // stage s: cur = row q = r - 2s at level s  ->  cur = row q-2 at level s+1
+                const RowTag rq = info[0], r1i = info[1], r2i = info[W > 2 ? 2 : 0];
+                const int q = r - 2 * s;
                 const long long cell_q = cell_r - 2 * s * nx;
 
                 // 1. boundaries and probes of p (row q)
-                if (rq.classed & 1u) {
+                if (rq.classed() & 1u) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        cur[0][c] = apply_class(cls_alpha, cls_value, 0,
-                                                (unsigned)(rq.ids >> (16 * c)), cur[0][c]);
+                    for (int c = 0; c < C; ++c)
+                        cur[0][c] = apply_class(cls_alpha, cls_value, 0, rq.ids >> (16 * c), cur[0][c]);
                 }
-                if (rq.flagged) {
-                    const long long q = r - 2 * s;
+                if (rq.flagged()) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) scratch[c] = cur[0][c];
-                    stream_slow_cells(a.tables, 0, 1, a.sig_index + s, a.ring_row + s, cell_q, rq.ids,
-                                      lane_owned && q >= ys && q < ye, scratch);
+                    for (int c = 0; c < C; ++c) scratch[c] = cur[0][c];
+                    s2_slow_cells(a.tables, 0, 1, a.sig_index + s, a.ring_row + s, cell_q, rq.ids,
+                                  lane_owned && q >= ys && q < ye, scratch);
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) cur[0][c] = scratch[c];
+                    for (int c = 0; c < C; ++c) cur[0][c] = scratch[c];
                 }
 
-                // x-neighbours living in the adjacent lanes (row q-1 operands)
-                const double p1_left = shfl_up1(pb[s][0][3]);
-                double u1_left = 0, u1_right = 0, v1_left = 0, v1_right = 0;
-                if (VISC) {
-                    u1_left = shfl_up1(uo[s][0][3]);
-                    u1_right = shfl_down1(uo[s][0][0]);
-                    v1_left = shfl_up1(vo[s][0][3]);
-                    v1_right = shfl_down1(vo[s][0][0]);
-                }
-                const double un2_right = shfl_down1(un[s][0]);
-
-                // 2. new vx, vy of row q-1; 3. new p of row q-2.
-                // coef.*(c): material coefficient of cell c of a row; c = -1 / 4 are the neighbour
-                // lanes' cells. Rows: 0 = q, 1 = q-1, 2 = q-2.
-                double nu[4], nv[4], np[4];
-                auto math = [&](const auto &coef) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const double pl = c ? pb[s][0][c - 1] : p1_left;
-                        const double du = diff2(coef.gx(1, c - 1), pl, coef.gx(1, c), pb[s][0][c]);
-                        const double dv = diff2(coef.gy(2, c), pb[s][1][c], coef.gy(1, c), pb[s][0][c]);
-                        const double uold = uo[s][0][c], vold = vo[s][0][c];
-                        if (VISC) {
-                            const double ul = c ? uo[s][0][c - 1] : u1_left;
-                            const double ur = c < 3 ? uo[s][0][c + 1] : u1_right;
-                            const double vl = c ? vo[s][0][c - 1] : v1_left;
-                            const double vr = c < 3 ? vo[s][0][c + 1] : v1_right;
-                            const double cm1 = coef.vm1(c - 1), cp1 = coef.vp1(c + 1);
-                            double vis = acc0(mul(coef.vmn(2, c), uo[s][1][c]));
-                            vis = add(vis, mul(cm1, ul));
-                            vis = add(vis, mul(coef.v0(c), uold));
-                            vis = add(vis, mul(cp1, ur));
-                            vis = add(vis, mul(coef.vpn(0, c), cur[1][c]));
-                            double rhs = sub(du, vis);
-                            if (AXI) rhs = add(rhs, mul(coef.eb(c), uold) / coef.rr(c));
-                            nu[c] = sub(uold, rhs);
-                            double visv = acc0(mul(coef.vmn(2, c), vo[s][1][c]));
-                            visv = add(visv, mul(cm1, vl));
-                            visv = add(visv, mul(coef.v0(c), vold));
-                            visv = add(visv, mul(cp1, vr));
-                            visv = add(visv, mul(coef.vpn(0, c), cur[2][c]));
-                            nv[c] = sub(vold, sub(dv, visv));
-                        } else {
-                            nu[c] = AXI ? sub(uold, add(du, mul(0.0, uold))) : sub(uold, du);
-                            nv[c] = sub(vold, dv);
-                        }
-                    }
-                    if (r1i.classed & 2u) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            nu[c] = apply_class(cls_alpha, cls_value, 1,
-                                                (unsigned)(r1i.ids >> (16 * c)), nu[c]);
-                    }
-                    if (r1i.classed & 4u) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c)
-                            nv[c] = apply_class(cls_alpha, cls_value, 2,
-                                                (unsigned)(r1i.ids >> (16 * c)), nv[c]);
-                    }
-                    if (r1i.flagged) {
-                        const long long q1 = r - 2 * s - 1;
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) { scratch[c] = nu[c]; scratch[4 + c] = nv[c]; }
-                        stream_slow_cells(a.tables, 1, 2, a.sig_index + s, a.ring_row + s,
-                                          cell_q - nx, r1i.ids,
-                                          lane_owned && q1 >= ys && q1 < ye, scratch);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) { nu[c] = scratch[c]; nv[c] = scratch[4 + c]; }
-                    }
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        double f0 = un[s][c], f1 = c < 3 ? un[s][c + 1] : un2_right;
-                        if (AXI) {
-                            f0 = mul(f0, coef.r(c));
-                            f1 = mul(f1, coef.r(c + 1));
-                        }
-                        const double divx = diff2(coef.fx(c), f0, coef.fx(c + 1), f1);
-                        const double divy = diff2(coef.fy(2, c), vn[s][c], coef.fy(1, c), nv[c]);
-                        np[c] = sub(pb[s][1][c], add(divx, divy));
-                    }
+                // material of cell c (-1 .. C) of row 0 = q, 1 = q-1, 2 = q-2
+                const unsigned left1 = __shfl_up_sync(0xffffffffu, r1i.ids, 1);
+                const unsigned right1 = __shfl_down_sync(0xffffffffu, r1i.ids, 1);
+                const unsigned right2 = __shfl_down_sync(0xffffffffu, r2i.ids, 1);
+                auto mat = [&](int row, int c) {
+                    if (c < 0) return (int)((left1 >> (16 * (C - 1))) & kIdMask);     // row 1 only
+                    if (c >= C) return (int)((row == 1 ? right1 : right2) & kIdMask);
+                    const unsigned ids = row == 0 ? rq.ids : row == 1 ? r1i.ids : r2i.ids;
+                    return (int)((ids >> (16 * c)) & kIdMask);
+                };
+                auto vm1_of = [&](int c) {   // x diagonal at offset -1: coefficient of cell c (row q-1)
+                    return AXI ? ctab(FDS_CTAB_VM1, mat(1, c), col_of(c)) : tabs[FDS_TAB_VM1][mat(1, c)];
+                };
+                auto vp1_of = [&](int c) {
+                    return AXI ? ctab(FDS_CTAB_VP1, mat(1, c), col_of(c)) : tabs[FDS_TAB_VP1][mat(1, c)];
+                };
+                auto fx_of = [&](int c) {    // row q-2
+                    return AXI ? ctab(FDS_CTAB_FX, mat(2, c), col_of(c)) : tabs[FDS_TAB_FX][mat(2, c)];
                 };
 
-                const bool uniform = rq.uniform >= 0 && rq.uniform == r1i.uniform &&
-                                     rq.uniform == r2i.uniform;
-                if (uniform) {
-                    const int m = rq.uniform;
-                    if (AXI && m != cx_material) {
-                        // per-column coefficients of this material for columns x0-1 .. x0+4
+                // x-neighbours living in the adjacent lanes (row q-1 operands)
+                const double p1_left = shfl_up1(pA[0][C - 1]);
+                double u1_left = 0, u1_right = 0, v1_left = 0, v1_right = 0;
+                if (VISC) {
+                    u1_left = shfl_up1(uA[0][C - 1]);
+                    u1_right = shfl_down1(uA[0][0]);
+                    v1_left = shfl_up1(vA[0][C - 1]);
+                    v1_right = shfl_down1(vA[0][0]);
+                }
+                const double un2_right = shfl_down1(un[0][0]);
+
+                // 2. new vx, vy of row q-1
+                double nu[C], nv[C], np[C];
 #pragma unroll
-                        for (int c = 0; c < 5; ++c) cx_fx[c] = ctab(FDS_CTAB_FX, m, cols[c + 1]);
-                        if (VISC) {
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) {
-                                cx_vm1[c] = ctab(FDS_CTAB_VM1, m, cols[c]);       // column of cell c-1
-                                cx_vp1[c] = ctab(FDS_CTAB_VP1, m, cols[c + 2]);   // column of cell c+1
-                            }
-                        }
-                        cx_material = m;
+                for (int c = 0; c < C; ++c) {
+                    const double pl = c ? pA[0][c - 1] : p1_left;
+                    const double du = diff2(tabs[FDS_TAB_GX][mat(1, c - 1)], pl,
+                                            tabs[FDS_TAB_GX][mat(1, c)], pA[0][c]);
+                    const double dv = diff2(tabs[FDS_TAB_GY][mat(2, c)], pB[0][c],
+                                            tabs[FDS_TAB_GY][mat(1, c)], pA[0][c]);
+                    const double uold = uA[0][c], vold = vA[0][c];
+                    if (VISC) {
+                        const double ul = c ? uA[0][c - 1] : u1_left;
+                        const double ur = c < C - 1 ? uA[0][c + 1] : u1_right;
+                        const double vl = c ? vA[0][c - 1] : v1_left;
+                        const double vr = c < C - 1 ? vA[0][c + 1] : v1_right;
+                        const double cm1 = vm1_of(c - 1), cp1 = vp1_of(c + 1);
+                        const double c0 = tabs[FDS_TAB_V0][mat(1, c)];
+                        const double cmn = tabs[FDS_TAB_VMN][mat(2, c)];
+                        const double cpn = tabs[FDS_TAB_VPN][mat(0, c)];
+                        double vis = acc0(mul(cmn, uB[0][c]));
+                        vis = add(vis, mul(cm1, ul));
+                        vis = add(vis, mul(c0, uold));
+                        vis = add(vis, mul(cp1, ur));
+                        vis = add(vis, mul(cpn, cur[1][c]));
+                        double rhs = sub(du, vis);
+                        if (AXI)
+                            rhs = add(rhs, mul(tabs[FDS_TAB_EB][mat(1, c)], uold) /
+                                               __ldg(av.cvec + FDS_CVEC_RR * nx + col_of(c)));
+                        nu[c] = sub(uold, rhs);
+                        double visv = acc0(mul(cmn, vB[0][c]));
+                        visv = add(visv, mul(cm1, vl));
+                        visv = add(visv, mul(c0, vold));
+                        visv = add(visv, mul(cp1, vr));
+                        visv = add(visv, mul(cpn, cur[2][c]));
+                        nv[c] = sub(vold, sub(dv, visv));
+                    } else {
+                        nu[c] = AXI ? sub(uold, add(du, mul(0.0, uold))) : sub(uold, du);
+                        nv[c] = sub(vold, dv);
                     }
-                    struct {
-                        double g0, g1, f0, f1, h0, hp, hm, hmn, hpn, e0;
-                        const double *fxc, *vm1c, *vp1c, *rc, *rrc;
-                        __device__ double gx(int, int) const { return g0; }
-                        __device__ double gy(int, int) const { return g1; }
-                        __device__ double fx(int c) const { return AXI ? fxc[c] : f0; }
-                        __device__ double fy(int, int) const { return f1; }
-                        __device__ double vm1(int c) const { return AXI ? vm1c[c + 1] : hm; }
-                        __device__ double vp1(int c) const { return AXI ? vp1c[c - 1] : hp; }
-                        __device__ double vmn(int, int) const { return hmn; }
-                        __device__ double vpn(int, int) const { return hpn; }
-                        __device__ double v0(int) const { return h0; }
-                        __device__ double eb(int) const { return e0; }
-                        __device__ double r(int c) const { return rc[c]; }
-                        __device__ double rr(int c) const { return rrc[c]; }
-                    } coef{tabs[FDS_TAB_GX][m], tabs[FDS_TAB_GY][m], tabs[FDS_TAB_FX][m],
-                           tabs[FDS_TAB_FY][m], tabs[FDS_TAB_V0][m], tabs[FDS_TAB_VP1][m],
-                           tabs[FDS_TAB_VM1][m], tabs[FDS_TAB_VMN][m], tabs[FDS_TAB_VPN][m],
-                           tabs[FDS_TAB_EB][m], cx_fx, cx_vm1, cx_vp1, cx_r, cx_rr};
-                    math(coef);
-                } else {
-                    struct {
-                        const double (*tabs)[kMaxMaterials];
-                        unsigned long long ids[3], left[3], right[3];
-                        const double *ctab_base, *rc, *rrc;
-                        const long long *cols;
-                        long long nx;
-                        int n_mat1;
-                        // material of cell c (-1 .. 4) of row `row`
-                        __device__ int mat(int row, int c) const {
-                            if (c < 0) return (int)(left[row] >> 48) & kIdMask;
-                            if (c > 3) return (int)right[row] & kIdMask;
-                            return (int)(ids[row] >> (16 * c)) & kIdMask;
-                        }
-                        __device__ double ct(int which, int m, int c) const {   // column of cell c
-                            return __ldg(ctab_base + ((long long)which * n_mat1 + m) * nx + cols[c + 1]);
-                        }
-                        __device__ double gx(int row, int c) const { return tabs[FDS_TAB_GX][mat(row, c)]; }
-                        __device__ double gy(int row, int c) const { return tabs[FDS_TAB_GY][mat(row, c)]; }
-                        __device__ double fx(int c) const {
-                            return AXI ? ct(FDS_CTAB_FX, mat(2, c), c) : tabs[FDS_TAB_FX][mat(2, c)];
-                        }
-                        __device__ double fy(int row, int c) const { return tabs[FDS_TAB_FY][mat(row, c)]; }
-                        __device__ double vm1(int c) const {
-                            return AXI ? ct(FDS_CTAB_VM1, mat(1, c), c) : tabs[FDS_TAB_VM1][mat(1, c)];
-                        }
-                        __device__ double vp1(int c) const {
-                            return AXI ? ct(FDS_CTAB_VP1, mat(1, c), c) : tabs[FDS_TAB_VP1][mat(1, c)];
-                        }
-                        __device__ double vmn(int row, int c) const { return tabs[FDS_TAB_VMN][mat(row, c)]; }
-                        __device__ double vpn(int row, int c) const { return tabs[FDS_TAB_VPN][mat(row, c)]; }
-                        __device__ double v0(int c) const { return tabs[FDS_TAB_V0][mat(1, c)]; }
-                        __device__ double eb(int c) const { return tabs[FDS_TAB_EB][mat(1, c)]; }
-                        __device__ double r(int c) const { return rc[c]; }
-                        __device__ double rr(int c) const { return rrc[c]; }
-                    } coef{tabs,
-                           {rq.ids, r1i.ids, r2i.ids},
-                           {0ull, __shfl_up_sync(0xffffffffu, r1i.ids, 1), 0ull},
-                           {0ull, __shfl_down_sync(0xffffffffu, r1i.ids, 1),
-                            __shfl_down_sync(0xffffffffu, r2i.ids, 1)},
-                           av.ctab, cx_r, cx_rr, cols, nx, av.n_mat1};
-                    math(coef);
+                }
+                if (r1i.classed() & 2u) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        nu[c] = apply_class(cls_alpha, cls_value, 1, r1i.ids >> (16 * c), nu[c]);
+                }
+                if (r1i.classed() & 4u) {
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        nv[c] = apply_class(cls_alpha, cls_value, 2, r1i.ids >> (16 * c), nv[c]);
+                }
+                if (r1i.flagged()) {
+                    const int q1 = q - 1;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        scratch[c] = nu[c];
+                        scratch[C + c] = nv[c];
+                    }
+                    s2_slow_cells(a.tables, 1, 2, a.sig_index + s, a.ring_row + s, cell_q - nx,
+                                  r1i.ids, lane_owned && q1 >= ys && q1 < ye, scratch);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        nu[c] = scratch[c];
+                        nv[c] = scratch[C + c];
+                    }
+                }
+                // 3. new p of row q-2
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    double f0 = un[0][c], f1 = c < C - 1 ? un[0][c + 1] : un2_right;
+                    if (AXI) {
+                        f0 = mul(f0, __ldg(av.cvec + FDS_CVEC_R * nx + col_of(c)));
+                        f1 = mul(f1, __ldg(av.cvec + FDS_CVEC_R * nx + col_of(c + 1)));
+                    }
+                    const double divx = diff2(fx_of(c), f0, fx_of(c + 1), f1);
+                    const double divy = diff2(tabs[FDS_TAB_FY][mat(2, c)], vn[0][c],
+                                              tabs[FDS_TAB_FY][mat(1, c)], nv[c]);
+                    np[c] = sub(pB[0][c], add(divx, divy));
                 }
 
-                // 4. row q-2 at level s+1 goes to the next stage; shift the window
+                // 4. row q-2 at level s+1 goes to the next stage; shift the window; rotate
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < C; ++c) {
                     const double keep_p = cur[0][c], keep_u = cur[1][c], keep_v = cur[2][c];
+                    const double old_pa = pA[0][c], old_ua = uA[0][c], old_va = vA[0][c];
                     cur[0][c] = np[c];
-                    cur[1][c] = un[s][c];
-                    cur[2][c] = vn[s][c];
-                    pb[s][1][c] = pb[s][0][c];
-                    pb[s][0][c] = keep_p;
-                    uo[s][1][c] = uo[s][0][c];
-                    uo[s][0][c] = keep_u;
-                    vo[s][1][c] = vo[s][0][c];
-                    vo[s][0][c] = keep_v;
-                    un[s][c] = nu[c];
-                    vn[s][c] = nv[c];
+                    cur[1][c] = un[0][c];
+                    cur[2][c] = vn[0][c];
+#pragma unroll
+                    for (int j = 0; j + 1 < K; ++j) {
+                        pA[j][c] = pA[j + 1][c];
+                        uA[j][c] = uA[j + 1][c];
+                        vA[j][c] = vA[j + 1][c];
+                        pB[j][c] = pB[j + 1][c];
+                        uB[j][c] = uB[j + 1][c];
+                        vB[j][c] = vB[j + 1][c];
+                        un[j][c] = un[j + 1][c];
+                        vn[j][c] = vn[j + 1][c];
+                    }
+                    pA[K - 1][c] = keep_p;
+                    uA[K - 1][c] = keep_u;
+                    vA[K - 1][c] = keep_v;
+                    pB[K - 1][c] = old_pa;
+                    uB[K - 1][c] = old_ua;
+                    vB[K - 1][c] = old_va;
+                    un[K - 1][c] = nu[c];
+                    vn[K - 1][c] = nv[c];
                 }
+                {
+                    const RowTag t0 = info[0], t1 = info[1];
+#pragma unroll
+                    for (int j = 0; j + 2 < W; ++j) info[j] = info[j + 2];
+                    info[W - 2] = t0;
+                    info[W - 1] = t1;
+                }
+            }
+            {
+                const RowTag first = info[0];
+#pragma unroll
+                for (int j = 0; j + 1 < W; ++j) info[j] = info[j + 1];
+                info[W - 1] = first;
             }
 
-            const long long orow = r - kLag;
-            if (lane_owned && orow >= ys && orow < ye) {
-                const long long o = cell_r - kLag * nx;
-#pragma unroll
-                for (int f = 0; f < 3; ++f) {
-                    *reinterpret_cast<double2 *>(a.out[f] + o) = make_double2(cur[f][0], cur[f][1]);
-                    *reinterpret_cast<double2 *>(a.out[f] + o + 2) =
-                        make_double2(cur[f][2], cur[f][3]);
-                }
-            }
+            store_row(cur, r - kLag, cell_r - kLag * nx);   // row r-2K at level K
             cell_r += nx;
+            ++r;
+            if (++slot == kS2RingDepth) slot = 0;
+            m0 = m1;
+            m1 = fetch();
         }
     }
 }

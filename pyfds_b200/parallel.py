@@ -18,6 +18,8 @@ from . import _bake, _engine
 
 #: steps per launch of the streaming kernel = halo rows it needs on a lossless grid
 STREAM_STEPS = 4
+#: steps per launch of the viscous / axisymmetric streaming kernel (fds_streamv.cuh)
+STREAMV_STEPS = 2
 
 
 def partition_rows(ny, world):
@@ -48,7 +50,7 @@ def stencil_reach(field):
 
 def streaming_steps(field):
     """Time steps per launch of the streaming kernels for this field (0: not eligible): 4 for lossless
-    Acoustic2D and Thermal2D, 1 for lossy Acoustic2D and Acoustic3DAxi."""
+    Acoustic2D and Thermal2D, 2 for lossy Acoustic2D and Acoustic3DAxi."""
     nx = field.x.samples
     if nx % 4 or nx < 128:
         return 0
@@ -56,7 +58,7 @@ def streaming_steps(field):
     if model == 'thermal2d' or (model == 'acoustic2d' and not is_lossy(field)):
         return STREAM_STEPS
     if model in ('acoustic2d', 'acoustic3daxi'):
-        return 1
+        return STREAMV_STEPS
     return 0
 
 

@@ -267,17 +267,20 @@ def test_streaming_kernel_step_counts_and_chunking(library, max_k, chunk, monkey
 
 # ---- the branch-free (steady-row) variants of the streaming kernel and the rows between them --------
 
-def _steady_case(pattern, nx, ny, steps, seed, kernel):
+def _steady_case(pattern, nx, ny, steps, seed, kernel, klass='Acoustic2D', lossy=False):
     """Maps laid out for the kernel's geometry (56 owned cells per strip, seams at x = 56, 112, ...):
     long stretches of rows with the same map word per lane -- walls, constant sources and material
     interfaces ALONG y -- separated by a few rows that break them."""
     mm = 1e-3
-    f = fds.Acoustic2D(t_delta=1e-7, t_samples=steps, x_delta=mm, x_samples=nx, y_delta=mm,
-                       y_samples=ny, material=fds.AcousticMaterial(1500, 1000))
+    f = getattr(fds, klass)(t_delta=1e-7, t_samples=steps, x_delta=mm, x_samples=nx, y_delta=mm,
+                            y_samples=ny,
+                            material=fds.AcousticMaterial(1500, 1000,
+                                                          shear_viscosity=1e-3 if lossy else 0))
     f.device_kernel = kernel
     scenarios._randomise(f, ('pressure', 'velocity_x', 'velocity_y'), seed)
     top = (ny - 1) * mm
-    second, third = fds.AcousticMaterial(1200, 900), fds.AcousticMaterial(1350, 950)
+    second = fds.AcousticMaterial(1200, 900, absorption_coef=7.7 if lossy else None)
+    third = fds.AcousticMaterial(1350, 950, absorption_coef=300 if lossy else None)
 
     def column(x, y0=0, y1=None):
         return f.get_line_region((x * mm, y0 * mm, x * mm, top if y1 is None else y1 * mm))
@@ -411,7 +414,10 @@ def test_tile_kernel_equals_one_step_kernel(library, builder, args, monkeypatch)
 
 @pytest.mark.parametrize('klass,lossy,max_k,chunk', [
     ('Acoustic2D', True, 1, 0), ('Acoustic2D', True, 1, 11), ('Acoustic2D', True, 1, 6),
-    ('Acoustic3DAxi', False, 1, 0), ('Acoustic3DAxi', True, 1, 0), ('Acoustic3DAxi', True, 1, 9)])
+    ('Acoustic3DAxi', False, 1, 0), ('Acoustic3DAxi', True, 1, 0), ('Acoustic3DAxi', True, 1, 9),
+    ('Acoustic2D', True, 2, 0), ('Acoustic2D', True, 2, 11), ('Acoustic2D', True, 2, 6),
+    ('Acoustic3DAxi', False, 2, 0), ('Acoustic3DAxi', False, 2, 7), ('Acoustic3DAxi', True, 2, 0),
+    ('Acoustic3DAxi', True, 2, 9)])
 def test_viscous_streaming_kernel_equals_one_step_kernel(library, klass, lossy, max_k, chunk,
                                                          monkeypatch):
     monkeypatch.setenv('FDS_MAX_K', str(max_k))
@@ -430,3 +436,49 @@ def test_viscous_streaming_kernel_equals_one_step_kernel(library, klass, lossy, 
 def test_viscous_streaming_kernel_vs_oracle(library):
     f = _stream_case(256, 70, 12, seed=62, kernel=2, klass='Acoustic3DAxi', lossy=True)
     _vs_oracle(f, 12, 'streamv axi lossy 256x70')
+
+
+@pytest.mark.parametrize('klass,lossy', [('Acoustic2D', True), ('Acoustic3DAxi', False),
+                                         ('Acoustic3DAxi', True)])
+@pytest.mark.parametrize('pattern', STEADY_PATTERNS)
+@pytest.mark.parametrize('max_k,chunk', [(2, 0), (2, 23), (1, 0)])
+def test_viscous_streaming_kernel_steady_variants(library, klass, lossy, pattern, max_k, chunk,
+                                                  monkeypatch):
+    """The branch-free body of the viscous / axisymmetric kernel (one material; constant operations on
+    no component or on exactly one), the general rows between such runs and strips that never
+    qualify (several materials): bit for bit what the one-step kernel computes, with the kernel's
+    counters proving which path the rows took."""
+    monkeypatch.setenv('FDS_MAX_K', str(max_k))
+    monkeypatch.setenv('FDS_CHUNK_ROWS', str(chunk))
+    monkeypatch.setenv('FDS_STREAM_STATS', '1')
+    results = []
+    for kernel in (1, 2):
+        f = _steady_case(pattern, 256, 118, 9, seed=74, kernel=kernel, klass=klass, lossy=lossy)
+        f.simulate(5)         # launches of 2 + 2 + 1 steps
+        f.simulate(4)
+        results.append(scenarios.collect(f))
+        engine = f.__dict__['_engine_state'].engine
+        launches, spl, name = engine.last_launch_info()
+        assert ('streamv' in name) == (kernel == 2), name
+        if kernel == 2:
+            assert spl == max_k, (name, spl)
+            stats = engine.stream_stats()
+    assert_same(results[1], results[0], 'streamv steady {} {} lossy={}'.format(pattern, klass, lossy))
+    plain, comp0, comp1, comp2, materials, general, rows = stats[:7]
+    assert plain > 0 and rows > 0 and materials == 0, stats
+    expected = {'vx_walls': comp1, 'p_columns': comp0, 'vy_columns': comp2,
+                'partial_height': comp1 + comp0}
+    if pattern in expected:
+        assert expected[pattern] > 0, (pattern, stats)
+    if pattern in ('plain', 'vx_walls', 'p_columns', 'vy_columns') and chunk == 0:
+        assert general < 0.3 * rows, (pattern, stats)
+    if pattern in ('interfaces_y', 'interface_and_wall', 'two_components'):
+        assert general > 0, (pattern, stats)
+
+
+@pytest.mark.parametrize('klass,lossy,pattern', [('Acoustic2D', True, 'vx_walls'),
+                                                 ('Acoustic3DAxi', True, 'partial_height'),
+                                                 ('Acoustic3DAxi', False, 'p_columns')])
+def test_viscous_streaming_kernel_steady_variants_vs_oracle(library, klass, lossy, pattern):
+    f = _steady_case(pattern, 192, 97, 11, seed=75, kernel=2, klass=klass, lossy=lossy)
+    _vs_oracle(f, 11, 'streamv steady {} {} vs oracle'.format(klass, pattern))
