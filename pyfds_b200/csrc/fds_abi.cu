@@ -741,9 +741,13 @@ int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
                    : launch_stream2d_as<K, THERMAL, false>(ctx, a);
 }
 
+// Resident CTAs per SM (measured on B200, Gcell-updates/s at K = 2, lossy Acoustic2D 4096^2 /
+// Acoustic3DAxi 8192x4096): 2 CTAs (no spills) 164 / 109, 3 CTAs (168 registers, a few spills in the
+// general row iteration) 172 / 110, 4 CTAs (128 registers, spills in the loop) 122 / 69.
 template <int K, bool AXI, bool VISC>
 int launch_streamv(fds_ctx *ctx, const StreamVArgs &av) {
-    auto kernel = streamv_kernel<K, AXI, VISC>;
+    constexpr int CTAS = kSVCtasPerSm;
+    auto kernel = streamv_kernel<K, AXI, VISC, CTAS>;
     const int smem = kStreamWarps * kS2WarpRingBytes;
     static bool configured = false;
     if (!configured) {
@@ -751,7 +755,7 @@ int launch_streamv(fds_ctx *ctx, const StreamVArgs &av) {
         configured = true;
     }
     const long long want = (av.base.n_tasks + kStreamWarps - 1) / kStreamWarps;
-    const long long ctas = std::min<long long>(want, 148 * kSVCtasPerSm);
+    const long long ctas = std::min<long long>(want, 148 * CTAS);
     kernel<<<(unsigned)ctas, kStreamWarps * 32, smem, ctx->stream>>>(av);
     FDS_CUDA(ctx, cudaGetLastError());
     return 0;

@@ -38,10 +38,7 @@ struct StreamVArgs {
     int n_mat1;
 };
 
-#ifndef FDS_SV_CTAS
-#define FDS_SV_CTAS 3
-#endif
-constexpr int kSVCtasPerSm = FDS_SV_CTAS;   // resident CTAs per SM (register budget: 168 at 3)
+constexpr int kSVCtasPerSm = 3;             // resident CTAs per SM (register budget: 168)
 constexpr int kMaxStreamVSteps = 2;         // K: bounded by the strip halo (see above)
 
 // Coefficients of ONE material for this lane's cells (steady rows). Members a model does not use are
@@ -138,8 +135,8 @@ __device__ __forceinline__ void sv_steady_stage(
     }
 }
 
-template <int K, bool AXI, bool VISC>
-__global__ void __launch_bounds__(kStreamWarps * 32, kSVCtasPerSm) streamv_kernel(StreamVArgs av) {
+template <int K, bool AXI, bool VISC, int CTAS = kSVCtasPerSm>
+__global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(StreamVArgs av) {
     constexpr int C = kS2LaneCells;
     constexpr int kLag = 2 * K;     // rows between the input row and the row stored
     constexpr int W = 2 * K + 1;    // row tags in flight: rows r .. r-2K
