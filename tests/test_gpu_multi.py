@@ -35,6 +35,12 @@ def _build(name):
         return scenarios._acoustic2d(fds, lossy=False, nx=512, ny=300, steps=37, seed=41)
     if name == 'big_lossy':
         return scenarios._acoustic2d(fds, lossy=True, nx=256, ny=130, steps=21, seed=42)
+    if name == 'big_axi_lossy':      # viscous streaming kernel, 2 steps per launch, 4 halo rows
+        return scenarios._acoustic2d(fds, lossy=True, nx=256, ny=140, steps=19, seed=43,
+                                     klass='Acoustic3DAxi')
+    if name == 'big_axi_lossless':
+        return scenarios._acoustic2d(fds, lossy=False, nx=384, ny=90, steps=17, seed=44,
+                                     klass='Acoustic3DAxi')
     return scenarios.SCENARIOS[name](fds)
 
 
@@ -60,7 +66,8 @@ def _worker(rank, world, port, name, kernel, queue):
 @pytest.mark.parametrize('name,kernel', [
     ('big_lossless', 0), ('big_lossless', 1), ('big_lossy', 0), ('acoustic2d_wide', 0),
     ('acoustic2d_boundaries', 0), ('thermal2d', 0), ('acoustic3daxi_lossy', 0),
-    ('acoustic_flow2d', 0), ('acoustic_flow2d_wide', 0)])
+    ('acoustic_flow2d', 0), ('acoustic_flow2d_wide', 0), ('big_axi_lossy', 0),
+    ('big_axi_lossless', 0)])
 def test_two_slabs_equal_single_domain(library, name, kernel):
     if _gpu_count() < 2:
         pytest.skip('needs 2 GPUs')
