@@ -51,10 +51,11 @@ def config2(nx=4096, ny=4096, t_samples=1000):
     return bench.build_field(fds, nx, ny, t_samples), 48
 
 
-def config3(nx=8192, ny=4096, t_samples=1000):
+def config3(nx=8192, ny=4096, t_samples=1000, lossy=True):
     """Acoustic3DAxi with lossy sponge regions, Dirichlet lines, line source, line probe."""
-    main = fds.AcousticMaterial(1500, 1000, shear_viscosity=1e-3)
-    sponge = fds.AcousticMaterial(1500, 1000, absorption_coef=500)
+    main = fds.AcousticMaterial(1500, 1000, shear_viscosity=1e-3 if lossy else 0)
+    sponge = fds.AcousticMaterial(1500, 1000, absorption_coef=500) if lossy \
+        else fds.AcousticMaterial(1400, 1100)
     fld = fds.Acoustic3DAxi(t_delta=1e-7, t_samples=t_samples, x_delta=1e-3, x_samples=nx,
                             y_delta=1e-3, y_samples=ny, material=main)
     w = max(2, nx // 128)
@@ -73,10 +74,11 @@ def config3(nx=8192, ny=4096, t_samples=1000):
     return fld, 48
 
 
-def config4(nx=8192, ny=8192, t_samples=1000):
+def config4(nx=8192, ny=8192, t_samples=1000, klass='Thermal2D'):
     """Thermal2D explicit diffusion with mixed Dirichlet / Neumann boundaries."""
-    fld = fds.Thermal2D(t_delta=1e-3, t_samples=t_samples, x_delta=1e-3, x_samples=nx,
-                        y_delta=1e-3, y_samples=ny, material=fds.ThermalMaterial(900, 2700, 200))
+    fld = getattr(fds, klass)(t_delta=1e-3, t_samples=t_samples, x_delta=1e-3, x_samples=nx,
+                              y_delta=1e-3, y_samples=ny,
+                              material=fds.ThermalMaterial(900, 2700, 200))
     fld.add_material_region(
         fld.get_rect_region(((nx // 3) * 1e-3, (ny // 3) * 1e-3, (nx // 4) * 1e-3,
                              (ny // 4) * 1e-3)), fds.ThermalMaterial(450, 7800, (50, 30)))
@@ -115,10 +117,22 @@ def config6(nx=4096, ny=4096, t_samples=1000):
     return fld, 48
 
 
-CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5, 6: config6}
+def config7(**kwargs):
+    """Config 3 without losses: the axisymmetric model on the lossless streaming kernel."""
+    return config3(lossy=False, **kwargs)
+
+
+def config8(**kwargs):
+    """Config 4 as Thermal3DAxi."""
+    return config4(klass='Thermal3DAxi', **kwargs)
+
+
+CONFIGS = {1: config1, 2: config2, 3: config3, 4: config4, 5: config5, 6: config6, 7: config7,
+           8: config8}
 SMALL = {1: dict(t_samples=600, nx=3000), 2: dict(nx=256, ny=192, t_samples=60),
          3: dict(nx=256, ny=160, t_samples=50), 4: dict(nx=192, ny=160, t_samples=80),
-         5: dict(nx=512, ny=96, t_samples=40), 6: dict(nx=256, ny=192, t_samples=60)}
+         5: dict(nx=512, ny=96, t_samples=40), 6: dict(nx=256, ny=192, t_samples=60),
+         7: dict(nx=256, ny=160, t_samples=50), 8: dict(nx=192, ny=160, t_samples=80)}
 
 
 def check(number):

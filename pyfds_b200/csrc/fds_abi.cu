@@ -483,12 +483,13 @@ const char *step2d_name(const fds_ctx *ctx) {
 // ---- streaming multi-step kernel (fds_stream2d.cuh) ---------------------------------------------
 
 bool stream_supported(const fds_desc &d) {
-    const bool model_ok = (d.model == FDS_ACOUSTIC2D && !d.lossy) || d.model == FDS_THERMAL2D;
+    const bool model_ok = ((d.model == FDS_ACOUSTIC2D || d.model == FDS_ACOUSTIC3DAXI) && !d.lossy) ||
+                          d.model == FDS_THERMAL2D || d.model == FDS_THERMAL3DAXI;
     return model_ok && d.nx % 4 == 0 && d.nx >= 128;
 }
 
 bool streamv_supported(const fds_desc &d) {
-    const bool model_ok = (d.model == FDS_ACOUSTIC2D && d.lossy) || d.model == FDS_ACOUSTIC3DAXI;
+    const bool model_ok = (d.model == FDS_ACOUSTIC2D || d.model == FDS_ACOUSTIC3DAXI) && d.lossy;
     return model_ok && d.nx % 4 == 0 && d.nx >= 128;
 }
 
@@ -718,9 +719,9 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
     return 0;
 }
 
-template <int K, bool THERMAL, bool STATS>
+template <int K, bool THERMAL, bool STATS, bool AXI>
 int launch_stream2d_as(fds_ctx *ctx, const Stream2DArgs &a) {
-    auto kernel = stream2d_kernel<K, THERMAL, STATS>;
+    auto kernel = stream2d_kernel<K, THERMAL, STATS, AXI>;
     const int smem = kStreamWarps * kS2WarpRingBytes;
     static bool configured = false;
     if (!configured) {
@@ -737,8 +738,11 @@ int launch_stream2d_as(fds_ctx *ctx, const Stream2DArgs &a) {
 
 template <int K, bool THERMAL>
 int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
-    return a.stats ? launch_stream2d_as<K, THERMAL, true>(ctx, a)
-                   : launch_stream2d_as<K, THERMAL, false>(ctx, a);
+    if (ctx->axi)
+        return a.stats ? launch_stream2d_as<K, THERMAL, true, true>(ctx, a)
+                       : launch_stream2d_as<K, THERMAL, false, true>(ctx, a);
+    return a.stats ? launch_stream2d_as<K, THERMAL, true, false>(ctx, a)
+                   : launch_stream2d_as<K, THERMAL, false, false>(ctx, a);
 }
 
 // Resident CTAs per SM (measured on B200, Gcell-updates/s at K = 2, lossy Acoustic2D 4096^2 /
@@ -788,6 +792,9 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     a.map = ctx->map + ctx->pad + ctx->halo;
     a.tab = ctx->tab;
     a.tables = ctx->d_tables;
+    a.ctab = ctx->ctab;
+    a.cvec = ctx->cvec;
+    a.n_mat1 = ctx->d.n_materials + 1;
     if (ctx->use_streamv) {
         StreamVArgs av{};
         av.base = a;
@@ -796,13 +803,12 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
         av.n_mat1 = ctx->d.n_materials + 1;
         const bool lossy = ctx->d.lossy != 0;
         const bool axi = ctx->d.model == FDS_ACOUSTIC3DAXI;
-        if (!axi && !(ctx->d.model == FDS_ACOUSTIC2D && lossy))
+        if (!lossy || (!axi && ctx->d.model != FDS_ACOUSTIC2D))
             return fail(ctx, "streamv: unsupported model");
 #define FDS_STREAMV_CASE(K_)                                                                 \
     case K_:                                                                                 \
-        return !axi    ? launch_streamv<K_, false, true>(ctx, av)                            \
-               : lossy ? launch_streamv<K_, true, true>(ctx, av)                             \
-                       : launch_streamv<K_, true, false>(ctx, av);
+        return axi ? launch_streamv<K_, true, true>(ctx, av)                                 \
+                   : launch_streamv<K_, false, true>(ctx, av);
         switch (k) {
             FDS_STREAMV_CASE(1)
             FDS_STREAMV_CASE(2)
@@ -1174,12 +1180,13 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 ctx->last_steps_per_launch = std::max<long long>(ctx->last_steps_per_launch, k);
                 ctx->last_kernel =
                     ctx->use_streamv
-                        ? (ctx->d.model == FDS_ACOUSTIC3DAXI
-                               ? (ctx->d.lossy ? "streamv_kernel<acoustic3daxi,lossy>"
-                                               : "streamv_kernel<acoustic3daxi,lossless>")
-                               : "streamv_kernel<acoustic2d,lossy>")
-                        : (ctx->thermal ? "stream2d_kernel<thermal2d>"
-                                        : "stream2d_kernel<acoustic2d,lossless>");
+                        ? (ctx->d.model == FDS_ACOUSTIC3DAXI ? "streamv_kernel<acoustic3daxi,lossy>"
+                                                             : "streamv_kernel<acoustic2d,lossy>")
+                        : ctx->axi
+                              ? (ctx->thermal ? "stream2d_kernel<thermal3daxi>"
+                                              : "stream2d_kernel<acoustic3daxi,lossless>")
+                              : (ctx->thermal ? "stream2d_kernel<thermal2d>"
+                                              : "stream2d_kernel<acoustic2d,lossless>");
             } else {
                 Step2DArgs a{};
                 for (int c = 0; c < 3; ++c) {

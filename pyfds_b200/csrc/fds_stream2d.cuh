@@ -1,6 +1,7 @@
-// Streaming multi-step kernel for the lossless Acoustic2D leapfrog (pyfds/acoustics.py:111-128) and
-// for Thermal2D (pyfds/thermal.py:92-107): K time steps per launch with ONE read and ONE write of the
-// state (temporal blocking).
+// Streaming multi-step kernel for the lossless Acoustic2D leapfrog (pyfds/acoustics.py:111-128), for
+// Thermal2D (pyfds/thermal.py:92-107) and for their axisymmetric counterparts (lossless Acoustic3DAxi,
+// pyfds/acoustics.py:205-225; Thermal3DAxi, pyfds/thermal.py:160-176): K time steps per launch with
+// ONE read and ONE write of the state (temporal blocking).
 //
 // Work decomposition -- every warp is autonomous, there is no block-level synchronisation in the loop:
 //   * a warp owns an x-strip of 56 cells and a chunk of rows; it streams the strip (64 cells wide:
@@ -64,6 +65,11 @@ struct Stream2DArgs {
     // body by variant (no operation, operations on component 0 / 1 / 2, several materials),
     // [5] rows through the general row iteration, [6] rows streamed in total
     unsigned long long *stats;
+    // axisymmetric models (Acoustic3DAxi lossless, Thermal3DAxi): per-(material, column) and per-column
+    // values, as in StepTables
+    const double *ctab;    // [FDS_CTAB_COUNT][n_mat1][nx]
+    const double *cvec;    // [FDS_CVEC_COUNT][nx]
+    int n_mat1;
 };
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) {
@@ -220,7 +226,11 @@ __device__ __noinline__ void s2_slow_cells(const StepTables *__restrict__ tp, in
 // gx[c] = x-gradient coefficient of cell c-1 (gx[0]: the left-hand lane's last cell), gy[c], fy[c] =
 // y coefficients of cell c, fx[c] = x-divergence coefficient of cell c (fx[C]: the right-hand lane's
 // first cell): the same for rows q-1 and q, because steady rows repeat their map words.
-template <bool THERMAL, int CC>
+// AXI (pyfds/acoustics.py:205-225 without losses, pyfds/thermal.py:160-176): fx[] holds the
+// per-column a_p_vx / r (a_t_qx / r) values, the x-divergence is applied to vx * r (rv[c] = r of cell c,
+// rv[C]: the right-hand lane's first cell), and the lossless vx update carries the reference's
+// (0 * vx) / r^2 term as + 0 * vx.
+template <bool THERMAL, int CC, bool AXI = false>
 __device__ __forceinline__ void steady_stage(double (&cur)[3][kS2LaneCells],
                                              const double (&P)[kS2LaneCells],
                                              const double (&U)[kS2LaneCells],
@@ -232,7 +242,8 @@ __device__ __forceinline__ void steady_stage(double (&cur)[3][kS2LaneCells],
                                              const double (&fx)[kS2LaneCells + 1],
                                              const double (&fy)[kS2LaneCells],
                                              const double (&ca)[kS2LaneCells],
-                                             const double (&cv)[kS2LaneCells]) {
+                                             const double (&cv)[kS2LaneCells],
+                                             const double (&rv)[kS2LaneCells + 1]) {
     constexpr int C = kS2LaneCells;
     if (CC == 0) {
 #pragma unroll
@@ -245,7 +256,9 @@ __device__ __forceinline__ void steady_stage(double (&cur)[3][kS2LaneCells],
         const double pl = c ? cur[0][c - 1] : p_left;
         const double dx_ = diff2(gx[c], pl, gx[c + 1], cur[0][c]);
         const double dy_ = diff2(gy[c], P[c], gy[c], cur[0][c]);
-        Un[c] = THERMAL ? -dx_ : sub(cur[1][c], dx_);
+        Un[c] = THERMAL ? -dx_
+                : AXI   ? sub(cur[1][c], add(dx_, mul(0.0, cur[1][c])))
+                        : sub(cur[1][c], dx_);
         Vn[c] = THERMAL ? -dy_ : sub(cur[2][c], dy_);
         if (CC == 1) Un[c] = add(mul(ca[c], Un[c]), cv[c]);
         if (CC == 2) Vn[c] = add(mul(ca[c], Vn[c]), cv[c]);
@@ -253,8 +266,12 @@ __device__ __forceinline__ void steady_stage(double (&cur)[3][kS2LaneCells],
     const double u_right = shfl_down1(U[0]);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-        const double ur = c < C - 1 ? U[c + 1] : u_right;
-        const double divx = diff2(fx[c], U[c], fx[c + 1], ur);
+        double ul = U[c], ur = c < C - 1 ? U[c + 1] : u_right;
+        if (AXI) {
+            ul = mul(ul, rv[c]);
+            ur = mul(ur, rv[c + 1]);
+        }
+        const double divx = diff2(fx[c], ul, fx[c + 1], ur);
         const double divy = diff2(fy[c], V[c], fy[c], Vn[c]);
         np[c] = sub(P[c], add(divx, divy));
     }
@@ -278,7 +295,7 @@ __device__ __forceinline__ void steady_stage(double (&cur)[3][kS2LaneCells],
 // takes the general row iteration.
 // STATS: count in a.stats what the rows went through (tests only: a separate instantiation, so that
 // the counters cannot disturb the register allocation of the production kernel).
-template <int K, bool THERMAL, bool STATS = false>
+template <int K, bool THERMAL, bool STATS = false, bool AXI = false>
 __global__ void __launch_bounds__(kStreamWarps * 32, kS2CtasPerSm)
 stream2d_kernel(Stream2DArgs a) {
     constexpr int C = kS2LaneCells;
@@ -363,6 +380,20 @@ stream2d_kernel(Stream2DArgs a) {
         const int map_step = (int)(nx & 7LL);
         int map_off = (int)(((long long)r0 * nx + xs) & 7LL);   // entry offset in the map window
 
+        // axisymmetric: column of cell c (0 .. C) of this lane, wrapped into the row like the flat
+        // index; a_p_vx / r of a material and column; r of a column
+        auto col_of = [&](int c) {
+            long long col = x0 + c;
+            if (col < 0) col += nx;
+            if (col >= nx) col -= nx;
+            if (col >= nx) col -= nx;
+            return col;
+        };
+        auto fx_col = [&](unsigned m, int c) {
+            return __ldg(a.ctab + ((long long)FDS_CTAB_FX * a.n_mat1 + (m & kIdMask)) * nx + col_of(c));
+        };
+        auto r_col = [&](int c) { return __ldg(a.cvec + FDS_CVEC_R * nx + col_of(c)); };
+
         // a lane's 2 cells are one 16-byte word: rows are read and written with 128-bit accesses,
         // lane after lane, free of bank conflicts
         auto load_row = [&](double (&cur)[3][C], const unsigned char *src) {
@@ -446,7 +477,8 @@ stream2d_kernel(Stream2DArgs a) {
                     const unsigned below = c ? my_ids >> (16 * (c - 1)) : left >> (16 * (C - 1));
                     const unsigned here = c < C ? my_ids >> (16 * c) : right;
                     gx[c] = tabs[FDS_TAB_GX][UNI ? material : (below & kIdMask)];
-                    fx[c] = tabs[FDS_TAB_FX][UNI ? material : (here & kIdMask)];
+                    fx[c] = AXI ? fx_col(UNI ? material : here, c)
+                                : tabs[FDS_TAB_FX][UNI ? material : (here & kIdMask)];
                     if (c < C) {
                         gy[c] = tabs[FDS_TAB_GY][UNI ? material : (here & kIdMask)];
                         fy[c] = tabs[FDS_TAB_FY][UNI ? material : (here & kIdMask)];
@@ -461,13 +493,16 @@ stream2d_kernel(Stream2DArgs a) {
                 ca[c] = k ? cls_alpha[CC < 0 ? 0 : CC][k] : 1.0;
                 cv[c] = k ? cls_value[CC < 0 ? 0 : CC][k] : -0.0;
             }
+            double rv[C + 1];
+#pragma unroll
+            for (int c = 0; c <= C; ++c) rv[c] = AXI ? r_col(c) : 1.0;
             for (;;) {
                 double cur[3][C], pb1[K][C], un1[K][C], vn1[K][C];
                 load_row(cur, ring + slot * kS2SlotBytes);
 #pragma unroll
                 for (int s = 0; s < K; ++s)
-                    steady_stage<THERMAL, CC>(cur, pb[s], un[s], vn[s], pb1[s], un1[s], vn1[s], gx,
-                                              gy, fx, fy, ca, cv);
+                    steady_stage<THERMAL, CC, AXI>(cur, pb[s], un[s], vn[s], pb1[s], un1[s], vn1[s],
+                                                   gx, gy, fx, fy, ca, cv, rv);
                 store_row(cur, r - K, cell_r - K * nx);
 
                 load_row(cur, ring + (slot + 1) * kS2SlotBytes);
@@ -475,8 +510,8 @@ stream2d_kernel(Stream2DArgs a) {
                 if (lane == 0 && r + kS2RingDepth < r1) issue_pair(r + kS2RingDepth, slot);
 #pragma unroll
                 for (int s = 0; s < K; ++s)
-                    steady_stage<THERMAL, CC>(cur, pb1[s], un1[s], vn1[s], pb[s], un[s], vn[s], gx,
-                                              gy, fx, fy, ca, cv);
+                    steady_stage<THERMAL, CC, AXI>(cur, pb1[s], un1[s], vn1[s], pb[s], un[s], vn[s],
+                                                   gx, gy, fx, fy, ca, cv, rv);
                 store_row(cur, r + 1 - K, cell_r + nx - K * nx);
                 // the window info[0..K] stays what it was: steady rows with these map words
                 cell_r += 2 * nx;
@@ -597,7 +632,9 @@ stream2d_kernel(Stream2DArgs a) {
                         const double pl = c ? cur[0][c - 1] : p_left;
                         const double dx_ = diff2(coef.gx(c), pl, coef.gx(c + 1), cur[0][c]);
                         const double dy_ = diff2(coef.gyp(c), pb[0][c], coef.gyc(c), cur[0][c]);
-                        nu[c] = THERMAL ? -dx_ : sub(cur[1][c], dx_);
+                        nu[c] = THERMAL ? -dx_
+                                : AXI   ? sub(cur[1][c], add(dx_, mul(0.0, cur[1][c])))
+                                        : sub(cur[1][c], dx_);
                         nv[c] = THERMAL ? -dy_ : sub(cur[2][c], dy_);
                     }
                     if (ri.classed() & 2u) {
@@ -628,8 +665,15 @@ stream2d_kernel(Stream2DArgs a) {
                     const double u_right = shfl_down1(un[0][0]);
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const double ur = c < C - 1 ? un[0][c + 1] : u_right;
-                        const double divx = diff2(coef.fxp(c), un[0][c], coef.fxp(c + 1), ur);
+                        double ul = un[0][c], ur = c < C - 1 ? un[0][c + 1] : u_right;
+                        double fxa = coef.fxp(c), fxb = coef.fxp(c + 1);
+                        if (AXI) {
+                            ul = mul(ul, r_col(c));
+                            ur = mul(ur, r_col(c + 1));
+                            fxa = fx_col(coef.mfxp(c), c);
+                            fxb = fx_col(coef.mfxp(c + 1), c + 1);
+                        }
+                        const double divx = diff2(fxa, ul, fxb, ur);
                         const double divy = diff2(coef.fyp(c), vn[0][c], coef.fyc(c), nv[c]);
                         np[c] = sub(pb[0][c], add(divx, divy));
                     }
@@ -638,6 +682,8 @@ stream2d_kernel(Stream2DArgs a) {
                     // all cells of rows q-1 and q share one material: 4 coefficients in registers
                     struct {
                         double g0, g1, f0, f1;
+                        unsigned material;
+                        __device__ unsigned mfxp(int) const { return material; }
                         __device__ double gx(int) const { return g0; }
                         __device__ double gyc(int) const { return g1; }
                         __device__ double gyp(int) const { return g1; }
@@ -645,7 +691,8 @@ stream2d_kernel(Stream2DArgs a) {
                         __device__ double fyp(int) const { return f1; }
                         __device__ double fyc(int) const { return f1; }
                     } coef{tabs[FDS_TAB_GX][ri_uniform], tabs[FDS_TAB_GY][ri_uniform],
-                           tabs[FDS_TAB_FX][ri_uniform], tabs[FDS_TAB_FY][ri_uniform]};
+                           tabs[FDS_TAB_FX][ri_uniform], tabs[FDS_TAB_FY][ri_uniform],
+                           (unsigned)ri_uniform};
                     math(coef);
                 } else {
                     struct {
@@ -659,6 +706,9 @@ stream2d_kernel(Stream2DArgs a) {
                         }
                         __device__ double gyc(int c) const { return tabs[FDS_TAB_GY][mc(c)]; }
                         __device__ double gyp(int c) const { return tabs[FDS_TAB_GY][mp(c)]; }
+                        __device__ unsigned mfxp(int c) const {
+                            return c < C ? (unsigned)mp(c) : (right & kIdMask);
+                        }
                         __device__ double fxp(int c) const {
                             return tabs[FDS_TAB_FX][c < C ? mp(c) : (int)(right & kIdMask)];
                         }

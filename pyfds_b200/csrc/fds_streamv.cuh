@@ -1,5 +1,7 @@
-// Streaming kernel for the viscous (lossy) Acoustic2D leapfrog and for Acoustic3DAxi (lossless and
-// lossy): pyfds/acoustics.py:111-128 and 205-225, K <= 2 time steps per launch.
+// Streaming kernel for the viscous (lossy) Acoustic2D leapfrog and for lossy Acoustic3DAxi:
+// pyfds/acoustics.py:111-128 and 205-225, K <= 2 time steps per launch. (The lossless axisymmetric
+// model runs on stream2d_kernel<AXI>; the VISC = false instantiation of this template is not
+// dispatched.)
 //
 // Same machinery and geometry as stream2d_kernel (fds_stream2d.cuh): one warp = one 64-cell strip
 // (2 cells per lane, 4 halo cells either side, 56 owned) x a chunk of rows, rows arriving in pairs

@@ -49,13 +49,15 @@ def stencil_reach(field):
 
 
 def streaming_steps(field):
-    """Time steps per launch of the streaming kernels for this field (0: not eligible): 4 for lossless
-    Acoustic2D and Thermal2D, 2 for lossy Acoustic2D and Acoustic3DAxi."""
+    """Time steps per launch of the streaming kernels for this field (0: not eligible): 4 for the
+    lossless acoustic and the thermal 2-D models (plain and axisymmetric), 2 for the lossy ones."""
     nx = field.x.samples
     if nx % 4 or nx < 128:
         return 0
     model = field._device_model
-    if model == 'thermal2d' or (model == 'acoustic2d' and not is_lossy(field)):
+    if model in ('thermal2d', 'thermal3daxi'):
+        return STREAM_STEPS
+    if model in ('acoustic2d', 'acoustic3daxi') and not is_lossy(field):
         return STREAM_STEPS
     if model in ('acoustic2d', 'acoustic3daxi'):
         return STREAMV_STEPS

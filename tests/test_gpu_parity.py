@@ -370,21 +370,28 @@ def test_streaming_kernel_steady_variants_vs_oracle(library, pattern):
     _vs_oracle(f, 11, 'steady {} vs oracle'.format(pattern))
 
 
+@pytest.mark.parametrize('klass', ['Thermal2D', 'Thermal3DAxi'])
 @pytest.mark.parametrize('chunk', [0, 17])
-def test_streaming_kernel_thermal_equals_one_step_kernel(library, chunk, monkeypatch):
-    """Thermal2D on the streaming kernel: Dirichlet temperature columns (component 0 operations),
-    zero-flux rows, an anisotropic material block."""
+def test_streaming_kernel_thermal_equals_one_step_kernel(library, chunk, klass, monkeypatch):
+    """Thermal2D / Thermal3DAxi on the streaming kernel: Dirichlet temperature columns (component 0
+    operations), zero-flux rows, an anisotropic material block."""
     monkeypatch.setenv('FDS_CHUNK_ROWS', str(chunk))
     results = []
     for kernel in (1, 2):
-        f, steps = scenarios._thermal2d(fds, 'Thermal2D', 256, 101, 14, seed=73)
+        f, steps = scenarios._thermal2d(fds, klass, 256, 101, 14, seed=73)
         f.device_kernel = kernel
         f.simulate(6)
         f.simulate(8)
         results.append(scenarios.collect(f))
         name = f.__dict__['_engine_state'].engine.last_launch_info()[2]
         assert ('stream2d' in name) == (kernel == 2), name
-    assert_same(results[1], results[0], 'thermal stream vs step chunk={}'.format(chunk))
+    assert_same(results[1], results[0], 'thermal stream vs step chunk={} {}'.format(chunk, klass))
+
+
+def test_streaming_kernel_thermal_axisymmetric_vs_oracle(library):
+    f, steps = scenarios._thermal2d(fds, 'Thermal3DAxi', 192, 75, 13, seed=78)
+    f.device_kernel = 2
+    _vs_oracle(f, steps, 'stream2d thermal3daxi 192x75')
 
 
 # ---- shared-memory tile kernel vs one-step kernel --------------------------------------------------
@@ -429,8 +436,33 @@ def test_viscous_streaming_kernel_equals_one_step_kernel(library, klass, lossy, 
         f.simulate(8)
         results.append(scenarios.collect(f))
         name = f.__dict__['_engine_state'].engine.last_launch_info()[2]
-        assert ('streamv' in name) == (kernel == 2), name
+        # lossy models: the viscous kernel; the lossless axisymmetric model: stream2d_kernel<AXI>
+        assert (('streamv' if lossy else 'stream2d') in name) == (kernel == 2), name
     assert_same(results[1], results[0], 'streamv vs step {} lossy={}'.format(klass, lossy))
+
+
+@pytest.mark.parametrize('pattern', STEADY_PATTERNS)
+@pytest.mark.parametrize('chunk', [0, 23])
+def test_streaming_kernel_axisymmetric_lossless_four_steps(library, pattern, chunk, monkeypatch):
+    """Lossless Acoustic3DAxi runs on stream2d_kernel<AXI> with up to 4 steps per launch: per-column
+    a_p_vx / r, the divergence of vx * r and the + 0 * vx term (pyfds/acoustics.py:205-225)."""
+    monkeypatch.setenv('FDS_CHUNK_ROWS', str(chunk))
+    results = []
+    for kernel in (1, 2):
+        f = _steady_case(pattern, 256, 118, 13, seed=76, kernel=kernel, klass='Acoustic3DAxi')
+        f.simulate(9)         # launches of 4 + 4 + 1 steps
+        f.simulate(4)
+        results.append(scenarios.collect(f))
+        launches, spl, name = f.__dict__['_engine_state'].engine.last_launch_info()
+        assert ('stream2d_kernel<acoustic3daxi' in name) == (kernel == 2), name
+        if kernel == 2:
+            assert spl == 4, (name, spl)
+    assert_same(results[1], results[0], 'axi lossless K=4 {} chunk={}'.format(pattern, chunk))
+
+
+def test_streaming_kernel_axisymmetric_lossless_vs_oracle(library):
+    f = _stream_case(364, 90, 18, seed=77, kernel=2, klass='Acoustic3DAxi', lossy=False)
+    _vs_oracle(f, 18, 'stream2d axi lossless 364x90')
 
 
 def test_viscous_streaming_kernel_vs_oracle(library):
@@ -459,20 +491,22 @@ def test_viscous_streaming_kernel_steady_variants(library, klass, lossy, pattern
         results.append(scenarios.collect(f))
         engine = f.__dict__['_engine_state'].engine
         launches, spl, name = engine.last_launch_info()
-        assert ('streamv' in name) == (kernel == 2), name
+        assert (('streamv' if lossy else 'stream2d') in name) == (kernel == 2), name
         if kernel == 2:
             assert spl == max_k, (name, spl)
             stats = engine.stream_stats()
     assert_same(results[1], results[0], 'streamv steady {} {} lossy={}'.format(pattern, klass, lossy))
     plain, comp0, comp1, comp2, materials, general, rows = stats[:7]
-    assert plain > 0 and rows > 0 and materials == 0, stats
+    assert plain > 0 and rows > 0, stats
+    if lossy:
+        assert materials == 0, stats     # the viscous kernel's branch-free body: one material only
     expected = {'vx_walls': comp1, 'p_columns': comp0, 'vy_columns': comp2,
                 'partial_height': comp1 + comp0}
     if pattern in expected:
         assert expected[pattern] > 0, (pattern, stats)
     if pattern in ('plain', 'vx_walls', 'p_columns', 'vy_columns') and chunk == 0:
         assert general < 0.3 * rows, (pattern, stats)
-    if pattern in ('interfaces_y', 'interface_and_wall', 'two_components'):
+    if pattern in ('interface_and_wall', 'two_components') or (lossy and pattern == 'interfaces_y'):
         assert general > 0, (pattern, stats)
 
 
