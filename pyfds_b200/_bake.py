@@ -194,9 +194,17 @@ def boundary_table(boundaries, first_step, n_steps, cell_lo, cell_hi, signals):
             op_value = np.full(n, float(bound.value))
             op_signal = np.full(n, -1, dtype=np.int32)
         elif kind == 'signal' and np.ndim(bound.value) == 1:
-            signals.append(_window(bound.value, first_step, n_steps))
+            # one signal for the whole region; boundaries driven by equal signals share one window
+            # (the device applies such sources through a handful of classes, see fds_upload_boundaries)
+            window = _window(bound.value, first_step, n_steps)
+            shared = next((k for k, other in enumerate(signals)
+                           if other.shape == window.shape and
+                           np.array_equal(other.view(np.int64), window.view(np.int64))), None)
+            if shared is None:
+                signals.append(window)
+                shared = len(signals) - 1
             op_value = np.zeros(n)
-            op_signal = np.full(n, len(signals) - 1, dtype=np.int32)
+            op_signal = np.full(n, shared, dtype=np.int32)
         else:
             # one signal per point: a list of signals, or a 2-D array [step][point]
             per_point = list(np.asarray(bound.value).T) if kind == 'signal' else list(bound.value)

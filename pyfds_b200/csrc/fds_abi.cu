@@ -115,6 +115,7 @@ struct fds_ctx {
     DevArray ccells[3], cclass[3];
     long long n_ccells[3] = {0, 0, 0};
     double cls_alpha[3][kMaxClasses] = {}, cls_value[3][kMaxClasses] = {};
+    int cls_signal[3][kMaxClasses];   // signal behind a class's value, -1 = constant (set by fds_create)
     // task tables of the streaming kernels, one per (row range, steps per launch) seen so far, and
     // the census they are balanced with: rows per strip that cannot take the branch-free body
     struct StreamPlan {
@@ -388,6 +389,7 @@ StepTables make_tables(fds_ctx *ctx) {
     t.rows.halo_cells = ctx->halo;
     memcpy(t.cls_alpha, ctx->cls_alpha, sizeof(t.cls_alpha));
     memcpy(t.cls_value, ctx->cls_value, sizeof(t.cls_value));
+    memcpy(t.cls_signal, ctx->cls_signal, sizeof(t.cls_signal));
     return t;
 }
 
@@ -1379,6 +1381,8 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
     ctx->thermal = (d.model == FDS_THERMAL1D || d.model == FDS_THERMAL2D ||
                     d.model == FDS_THERMAL3DAXI);
     ctx->axi = (d.model == FDS_ACOUSTIC3DAXI || d.model == FDS_THERMAL3DAXI);
+    for (int c = 0; c < 3; ++c)
+        for (int k = 0; k < kMaxClasses; ++k) ctx->cls_signal[c][k] = -1;
     ctx->owned = d.rows * d.nx;
     ctx->halo = (long long)d.halo_rows * d.nx;
     if (d.kernel == 2 && !stream_supported(d) && !streamv_supported(d)) {
@@ -1601,10 +1605,15 @@ int fds_upload_boundaries(fds_ctx *ctx, int32_t component, const int64_t *cells,
     FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
     const int c = component;
 
-    // Cells with exactly one scalar operation get a class (applied inline by the kernels, no table
-    // access); all others stay in the lookup table of the slow path.
+    // Cells with exactly one operation whose value is a scalar -- or, for the 2-D models, a signal (a
+    // source line driven by one signal is a handful of classes at most) -- get a class (applied inline
+    // by the kernels, no table access); all others stay in the lookup table of the slow path.
+    const bool signal_classes = ctx->dims == 2;
     int n_classes = 1;
-    for (int k = 0; k < kMaxClasses; ++k) ctx->cls_alpha[c][k] = ctx->cls_value[c][k] = 0.0;
+    for (int k = 0; k < kMaxClasses; ++k) {
+        ctx->cls_alpha[c][k] = ctx->cls_value[c][k] = 0.0;
+        ctx->cls_signal[c][k] = -1;
+    }
     std::vector<long long> class_cells, slow_cells;
     std::vector<int> class_ids, slow_offsets, slow_signal;
     std::vector<double> slow_alpha, slow_value;
@@ -1612,15 +1621,18 @@ int fds_upload_boundaries(fds_ctx *ctx, int32_t component, const int64_t *cells,
     for (int64_t k = 0; k < n_cells; ++k) {
         const int b = offsets[k], e = offsets[k + 1];
         int cls = 0;
-        if (e - b == 1 && signal[b] < 0) {
+        if (e - b == 1 && (signal[b] < 0 || signal_classes)) {
+            const double constant = signal[b] < 0 ? value[b] : 0.0;
             for (int j = 1; j < n_classes && !cls; ++j)
                 if (memcmp(&ctx->cls_alpha[c][j], &alpha[b], 8) == 0 &&
-                    memcmp(&ctx->cls_value[c][j], &value[b], 8) == 0)
+                    memcmp(&ctx->cls_value[c][j], &constant, 8) == 0 &&
+                    ctx->cls_signal[c][j] == (signal[b] < 0 ? -1 : signal[b]))
                     cls = j;
             if (!cls && n_classes < kMaxClasses) {
                 cls = n_classes++;
                 ctx->cls_alpha[c][cls] = alpha[b];
-                ctx->cls_value[c][cls] = value[b];
+                ctx->cls_value[c][cls] = constant;
+                ctx->cls_signal[c][cls] = signal[b] < 0 ? -1 : signal[b];
             }
         }
         if (cls) {

@@ -73,8 +73,9 @@ struct StepTables {
     double *ring;              // probe records [ring_steps][n_slots]
     int n_slots;
     RowIndex rows;
-    double cls_alpha[3][kMaxClasses];   // constant boundary operations by class
-    double cls_value[3][kMaxClasses];
+    double cls_alpha[3][kMaxClasses];   // single boundary operations by class: v = alpha * v + value,
+    double cls_value[3][kMaxClasses];   // value constant, or (2-D models) sample `step` of signal
+    int cls_signal[3][kMaxClasses];     // cls_signal (-1: constant)
 };
 
 __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
@@ -96,6 +97,13 @@ __device__ __forceinline__ double apply_class(const double (*alpha)[kMaxClasses]
                                               unsigned entry, double v) {
     const unsigned k = (entry >> class_shift(comp)) & (kMaxClasses - 1);
     return k ? add(mul(alpha[comp][k], v), value[comp][k]) : v;
+}
+
+// Value of class k of component comp at signal sample `sig` (index into the uploaded window).
+__device__ __forceinline__ double class_value(const StepTables &t, int comp, unsigned k,
+                                              long long sig) {
+    const int sidx = t.cls_signal[comp][k];
+    return sidx >= 0 ? __ldg(t.signals + (long long)sidx * t.sig_steps + sig) : t.cls_value[comp][k];
 }
 
 // Position of `cell` in the sorted array `cells[lo, hi)` or the position of the first larger entry.

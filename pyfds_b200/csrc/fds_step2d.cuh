@@ -104,7 +104,8 @@ __device__ __forceinline__ void cell_body(const Step2DArgs &a, const StepTables 
     // boundary operations of one cell and component: the inline constant class, else the table
     auto bound = [&](int comp, unsigned m, long long cell, double v) {
         if (FLAGS && (m & (kFlagBound | ((kMaxClasses - 1u) << class_shift(comp))))) {
-            v = apply_class(t.cls_alpha, t.cls_value, comp, m, v);
+            const unsigned k = (m >> class_shift(comp)) & (kMaxClasses - 1);
+            if (k) v = add(mul(t.cls_alpha[comp][k], v), class_value(t, comp, k, a.sig_index));
             if (m & kFlagBound)
                 v = apply_bounds(t.bound[comp], t.rows, t.signals, t.sig_steps, a.sig_index, cell, v);
         }

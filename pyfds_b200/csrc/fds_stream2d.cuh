@@ -190,6 +190,24 @@ __device__ __forceinline__ RowTag s2_row_meta(const unsigned char *src, int map_
     return m;
 }
 
+// Class tables of one launch in shared memory: alpha by class, value by stage and class (stage s works
+// on step sig_index + s, so a class that stands for a signal takes that sample).
+template <int K>
+__device__ __forceinline__ void stage_class_tables(const Stream2DArgs &a,
+                                                   double (*cls_alpha)[kMaxClasses],
+                                                   double (*cls_value)[3][kMaxClasses]) {
+    const StepTables *__restrict__ t = a.tables;
+    for (int k = threadIdx.x; k < 3 * kMaxClasses; k += blockDim.x) {
+        (&cls_alpha[0][0])[k] = (&t->cls_alpha[0][0])[k];
+        const int sidx = (&t->cls_signal[0][0])[k];
+#pragma unroll
+        for (int s = 0; s < K; ++s)
+            (&cls_value[s][0][0])[k] =
+                sidx >= 0 ? t->signals[(long long)sidx * t->sig_steps + a.sig_index + s]
+                          : (&t->cls_value[0][0])[k];
+    }
+}
+
 // Slow path, taken only by rows that carry a boundary operation or a probe: applies the boundary
 // operations of `n_comp` consecutive components (first_comp, first_comp + 1) to this lane's 2 cells and
 // records probes. Values travel through a per-lane shared-memory scratch so that the call site stays a
@@ -301,13 +319,11 @@ stream2d_kernel(Stream2DArgs a) {
     constexpr int C = kS2LaneCells;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double tabs[4][kMaxMaterials];   // FDS_TAB_GX, GY, FX, FY
-    __shared__ double cls_alpha[3][kMaxClasses], cls_value[3][kMaxClasses];
+    // class operations; the value by stage: a class may stand for a signal (one sample per step)
+    __shared__ double cls_alpha[3][kMaxClasses], cls_value[K][3][kMaxClasses];
 
     for (int k = threadIdx.x; k < 4 * kMaxMaterials; k += blockDim.x) (&tabs[0][0])[k] = a.tab[k];
-    for (int k = threadIdx.x; k < 3 * kMaxClasses; k += blockDim.x) {
-        (&cls_alpha[0][0])[k] = (&a.tables->cls_alpha[0][0])[k];
-        (&cls_value[0][0])[k] = (&a.tables->cls_value[0][0])[k];
-    }
+    stage_class_tables<K>(a, cls_alpha, cls_value);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -485,13 +501,14 @@ stream2d_kernel(Stream2DArgs a) {
                     }
                 }
             }
-            double ca[C], cv[C];
+            double ca[C], cv[K][C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const unsigned k =
                     CC < 0 ? 0u : (my_ids >> (16 * c + class_shift(CC < 0 ? 0 : CC))) & 7u;
                 ca[c] = k ? cls_alpha[CC < 0 ? 0 : CC][k] : 1.0;
-                cv[c] = k ? cls_value[CC < 0 ? 0 : CC][k] : -0.0;
+#pragma unroll
+                for (int s = 0; s < K; ++s) cv[s][c] = k ? cls_value[s][CC < 0 ? 0 : CC][k] : -0.0;
             }
             double rv[C + 1];
 #pragma unroll
@@ -502,7 +519,7 @@ stream2d_kernel(Stream2DArgs a) {
 #pragma unroll
                 for (int s = 0; s < K; ++s)
                     steady_stage<THERMAL, CC, AXI>(cur, pb[s], un[s], vn[s], pb1[s], un1[s], vn1[s],
-                                                   gx, gy, fx, fy, ca, cv, rv);
+                                                   gx, gy, fx, fy, ca, cv[s], rv);
                 store_row(cur, r - K, cell_r - K * nx);
 
                 load_row(cur, ring + (slot + 1) * kS2SlotBytes);
@@ -511,7 +528,7 @@ stream2d_kernel(Stream2DArgs a) {
 #pragma unroll
                 for (int s = 0; s < K; ++s)
                     steady_stage<THERMAL, CC, AXI>(cur, pb1[s], un1[s], vn1[s], pb[s], un[s], vn[s],
-                                                   gx, gy, fx, fy, ca, cv, rv);
+                                                   gx, gy, fx, fy, ca, cv[s], rv);
                 store_row(cur, r + 1 - K, cell_r + nx - K * nx);
                 // the window info[0..K] stays what it was: steady rows with these map words
                 cell_r += 2 * nx;
@@ -607,7 +624,7 @@ stream2d_kernel(Stream2DArgs a) {
                 if (ri.classed() & 1u) {
 #pragma unroll
                     for (int c = 0; c < C; ++c)
-                        cur[0][c] = apply_class(cls_alpha, cls_value, 0, ri.ids >> (16 * c),
+                        cur[0][c] = apply_class(cls_alpha, cls_value[s], 0, ri.ids >> (16 * c),
                                                 cur[0][c]);
                 }
                 if (ri.flagged()) {
@@ -640,12 +657,12 @@ stream2d_kernel(Stream2DArgs a) {
                     if (ri.classed() & 2u) {
 #pragma unroll
                         for (int c = 0; c < C; ++c)
-                            nu[c] = apply_class(cls_alpha, cls_value, 1, ri.ids >> (16 * c), nu[c]);
+                            nu[c] = apply_class(cls_alpha, cls_value[s], 1, ri.ids >> (16 * c), nu[c]);
                     }
                     if (ri.classed() & 4u) {
 #pragma unroll
                         for (int c = 0; c < C; ++c)
-                            nv[c] = apply_class(cls_alpha, cls_value, 2, ri.ids >> (16 * c), nv[c]);
+                            nv[c] = apply_class(cls_alpha, cls_value[s], 2, ri.ids >> (16 * c), nv[c]);
                     }
                     if (ri.flagged()) {
 #pragma unroll

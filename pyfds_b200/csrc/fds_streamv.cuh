@@ -146,14 +146,11 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
     const Stream2DArgs &a = av.base;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double tabs[FDS_TAB_COUNT][kMaxMaterials];
-    __shared__ double cls_alpha[3][kMaxClasses], cls_value[3][kMaxClasses];
+    __shared__ double cls_alpha[3][kMaxClasses], cls_value[K][3][kMaxClasses];
 
     for (int k = threadIdx.x; k < FDS_TAB_COUNT * kMaxMaterials; k += blockDim.x)
         (&tabs[0][0])[k] = a.tab[k];
-    for (int k = threadIdx.x; k < 3 * kMaxClasses; k += blockDim.x) {
-        (&cls_alpha[0][0])[k] = (&a.tables->cls_alpha[0][0])[k];
-        (&cls_value[0][0])[k] = (&a.tables->cls_value[0][0])[k];
-    }
+    stage_class_tables<K>(a, cls_alpha, cls_value);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -323,13 +320,14 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
                     }
                 }
             }
-            double ca[C], cv[C];
+            double ca[C], cv[K][C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const unsigned kc =
                     CC < 0 ? 0u : (my_ids >> (16 * c + class_shift(CC < 0 ? 0 : CC))) & 7u;
                 ca[c] = kc ? cls_alpha[CC < 0 ? 0 : CC][kc] : 1.0;
-                cv[c] = kc ? cls_value[CC < 0 ? 0 : CC][kc] : -0.0;
+#pragma unroll
+                for (int s = 0; s < K; ++s) cv[s][c] = kc ? cls_value[s][CC < 0 ? 0 : CC][kc] : -0.0;
             }
             for (;;) {
                 double cur[3][C], un1[K][C], vn1[K][C];
@@ -337,7 +335,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
 #pragma unroll
                 for (int s = 0; s < K; ++s)
                     sv_steady_stage<AXI, VISC, CC>(cur, pA[s], uA[s], vA[s], pB[s], uB[s], vB[s],
-                                                   un[s], vn[s], un1[s], vn1[s], k, ca, cv);
+                                                   un[s], vn[s], un1[s], vn1[s], k, ca, cv[s]);
                 store_row(cur, r - kLag, cell_r - kLag * nx);
 
                 load_row(cur, ring + (slot + 1) * kS2SlotBytes);
@@ -346,7 +344,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
 #pragma unroll
                 for (int s = 0; s < K; ++s)
                     sv_steady_stage<AXI, VISC, CC>(cur, pB[s], uB[s], vB[s], pA[s], uA[s], vA[s],
-                                                   un1[s], vn1[s], un[s], vn[s], k, ca, cv);
+                                                   un1[s], vn1[s], un[s], vn[s], k, ca, cv[s]);
                 store_row(cur, r + 1 - kLag, cell_r + nx - kLag * nx);
                 cell_r += 2 * nx;
                 r += 2;
@@ -429,7 +427,8 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
                 if (rq.classed() & 1u) {
 #pragma unroll
                     for (int c = 0; c < C; ++c)
-                        cur[0][c] = apply_class(cls_alpha, cls_value, 0, rq.ids >> (16 * c), cur[0][c]);
+                        cur[0][c] =
+                            apply_class(cls_alpha, cls_value[s], 0, rq.ids >> (16 * c), cur[0][c]);
                 }
                 if (rq.flagged()) {
 #pragma unroll
@@ -514,12 +513,12 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
                 if (r1i.classed() & 2u) {
 #pragma unroll
                     for (int c = 0; c < C; ++c)
-                        nu[c] = apply_class(cls_alpha, cls_value, 1, r1i.ids >> (16 * c), nu[c]);
+                        nu[c] = apply_class(cls_alpha, cls_value[s], 1, r1i.ids >> (16 * c), nu[c]);
                 }
                 if (r1i.classed() & 4u) {
 #pragma unroll
                     for (int c = 0; c < C; ++c)
-                        nv[c] = apply_class(cls_alpha, cls_value, 2, r1i.ids >> (16 * c), nv[c]);
+                        nv[c] = apply_class(cls_alpha, cls_value[s], 2, r1i.ids >> (16 * c), nv[c]);
                 }
                 if (r1i.flagged()) {
                     const int q1 = q - 1;

@@ -298,6 +298,14 @@ def _steady_case(pattern, nx, ny, steps, seed, kernel, klass='Acoustic2D', lossy
     elif pattern == 'vy_columns':        # component 2
         f.velocity_y.add_boundary(column(111), value=2e-6, additive=True)
         f.velocity_y.add_boundary(column(5))
+    elif pattern == 'signal_columns':    # sources along y driven by a signal: classes whose value
+        f.pressure.add_boundary(column(60), value=scenarios._pulse(steps, 5, 3), additive=True)
+        f.pressure.add_boundary(column(nx - 56, 10, ny - 20), value=-scenarios._pulse(steps, 7, 2))
+    elif pattern == 'signal_vx':         # is a sample per step (component 1; a row of them: general)
+        f.velocity_x.add_boundary(column(113), value=1e-3 * scenarios._pulse(steps, 4, 3),
+                                  additive=True)
+        f.velocity_x.add_boundary(f.get_line_region((20 * mm, 50 * mm, (nx - 26) * mm, 50 * mm)),
+                                  value=1e-3 * scenarios._pulse(steps, 6, 3), additive=True)
     elif pattern == 'interfaces_y':      # several materials, interfaces inside a strip and on seams
         f.add_material_region(f.get_rect_region((50 * mm, 0, 80 * mm, top)), second)
         f.add_material_region(f.get_rect_region((112 * mm, 0, 3 * mm, top)), third)
@@ -328,7 +336,8 @@ def _steady_case(pattern, nx, ny, steps, seed, kernel, klass='Acoustic2D', lossy
 
 
 STEADY_PATTERNS = ['plain', 'vx_walls', 'p_columns', 'vy_columns', 'interfaces_y',
-                   'interface_and_wall', 'two_components', 'partial_height']
+                   'interface_and_wall', 'two_components', 'partial_height', 'signal_columns',
+                   'signal_vx']
 
 
 @pytest.mark.parametrize('pattern', STEADY_PATTERNS)
@@ -355,16 +364,19 @@ def test_streaming_kernel_steady_variants_equal_one_step_kernel(library, pattern
     plain, comp0, comp1, comp2, materials, general, rows = stats[:7]
     assert plain > 0 and rows > 0, stats
     expected = {'vx_walls': comp1, 'p_columns': comp0, 'vy_columns': comp2, 'interfaces_y': materials,
-                'partial_height': comp1 + comp0 + materials}
+                'partial_height': comp1 + comp0 + materials, 'signal_columns': comp0,
+                'signal_vx': comp1}
     if pattern in expected:
         assert expected[pattern] > 0, (pattern, stats)
-    if pattern in ('plain', 'vx_walls', 'p_columns', 'vy_columns', 'interfaces_y') and chunk == 0:
+    if pattern in ('plain', 'vx_walls', 'p_columns', 'vy_columns', 'interfaces_y',
+                   'signal_columns', 'signal_vx') and chunk == 0:
         assert general < 0.25 * rows, (pattern, stats)     # only the rows around source and probes
     if pattern in ('interface_and_wall', 'two_components'):
         assert general > 0, (pattern, stats)
 
 
-@pytest.mark.parametrize('pattern', ['vx_walls', 'interfaces_y', 'partial_height'])
+@pytest.mark.parametrize('pattern', ['vx_walls', 'interfaces_y', 'partial_height', 'signal_columns',
+                                     'signal_vx'])
 def test_streaming_kernel_steady_variants_vs_oracle(library, pattern):
     f = _steady_case(pattern, 192, 97, 11, seed=72, kernel=2)
     _vs_oracle(f, 11, 'steady {} vs oracle'.format(pattern))
@@ -501,10 +513,11 @@ def test_viscous_streaming_kernel_steady_variants(library, klass, lossy, pattern
     if lossy:
         assert materials == 0, stats     # the viscous kernel's branch-free body: one material only
     expected = {'vx_walls': comp1, 'p_columns': comp0, 'vy_columns': comp2,
-                'partial_height': comp1 + comp0}
+                'partial_height': comp1 + comp0, 'signal_columns': comp0, 'signal_vx': comp1}
     if pattern in expected:
         assert expected[pattern] > 0, (pattern, stats)
-    if pattern in ('plain', 'vx_walls', 'p_columns', 'vy_columns') and chunk == 0:
+    if pattern in ('plain', 'vx_walls', 'p_columns', 'vy_columns', 'signal_columns',
+                   'signal_vx') and chunk == 0:
         assert general < 0.3 * rows, (pattern, stats)
     if pattern in ('interface_and_wall', 'two_components') or (lossy and pattern == 'interfaces_y'):
         assert general > 0, (pattern, stats)
@@ -512,7 +525,9 @@ def test_viscous_streaming_kernel_steady_variants(library, klass, lossy, pattern
 
 @pytest.mark.parametrize('klass,lossy,pattern', [('Acoustic2D', True, 'vx_walls'),
                                                  ('Acoustic3DAxi', True, 'partial_height'),
-                                                 ('Acoustic3DAxi', False, 'p_columns')])
+                                                 ('Acoustic3DAxi', False, 'p_columns'),
+                                                 ('Acoustic2D', True, 'signal_columns'),
+                                                 ('Acoustic3DAxi', True, 'signal_vx')])
 def test_viscous_streaming_kernel_steady_variants_vs_oracle(library, klass, lossy, pattern):
     f = _steady_case(pattern, 192, 97, 11, seed=75, kernel=2, klass=klass, lossy=lossy)
     _vs_oracle(f, 11, 'streamv steady {} {} vs oracle'.format(klass, pattern))
