@@ -549,7 +549,7 @@ int strip_census(fds_ctx *ctx, int n_strips) {
     int *d_counts = nullptr;
     if (dev_alloc(ctx, (void **)&d_counts, sizeof(int) * n, true)) return 1;
     const map_t *map = ctx->map + ctx->pad + ctx->halo;
-    if (ctx->use_streamv)
+    if (ctx->use_streamv && ctx->axi)   // its branch-free body takes rows of one material only
         strip_census_kernel<kS2LaneCells, true><<<148 * 4, 256, 0, ctx->stream>>>(
             map, ctx->d.nx, ctx->d.rows, n_strips, kS2StripStride, kS2StripHalo, n_blocks, d_counts);
     else

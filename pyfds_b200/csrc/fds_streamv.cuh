@@ -16,8 +16,9 @@
 // q-2; new vx, vy of row q-2): 32 registers per lane and stage. The dependency cone grows one cell to
 // the left and two to the right per step, which the 4-cell strip halo covers for K <= 2.
 //
-// STEADY rows (one material, no table lookup, no probe, constant operations on at most one component,
-// the lane's map word repeating row after row) run through a branch-free body that takes two rows per
+// STEADY rows (no table lookup, no probe, the lane's map word repeating row after row; one material
+// with class operations on at most one component, or several materials -- interfaces along y --
+// without operations) run through a branch-free body that takes two rows per
 // iteration; the two window rows swap roles between the halves of the iteration, so no register is
 // moved. Material coefficients -- and, for the axisymmetric model, the per-column values of this
 // lane's cells and of its two neighbours (a_p_vx / r, the viscous x diagonals with the 1/r term, r,
@@ -43,18 +44,19 @@ struct StreamVArgs {
 constexpr int kSVCtasPerSm = 3;             // resident CTAs per SM (register budget: 168)
 constexpr int kMaxStreamVSteps = 2;         // K: bounded by the strip halo (see above)
 
-// Coefficients of ONE material for this lane's cells (steady rows). Members a model does not use are
-// never loaded (the struct lives in registers, everything is inlined).
-template <bool AXI>
+// Coefficients of this lane's cells on steady rows (the same for rows q, q-1, q-2: steady rows repeat
+// their map words). Rows of one material fill every entry from the same register; members a model
+// does not use are never loaded (the struct lives in registers, everything is inlined).
 struct SVCoef {
-    double gx, gy, fy, fx0;                         // a_vx_p, a_vy_p, a_p_vy, a_p_vx factors
-    double v0, vmn, vpn, vm1s, vp1s, eb;            // a_v_v diagonals, axisymmetric extra term
-    double fxc[kS2LaneCells + 1];                   // AXI: a_p_vx / r of columns x0 .. x0+C
-    double vm1c[kS2LaneCells], vp1c[kS2LaneCells];  // AXI: x diagonals of cells c-1 / c+1
-    double r[kS2LaneCells + 1], rr[kS2LaneCells];   // AXI: r of columns x0 .. x0+C, r^2 of x0 .. x0+C-1
-    __device__ __forceinline__ double fx(int c) const { return AXI ? fxc[c] : fx0; }
-    __device__ __forceinline__ double vm1(int c) const { return AXI ? vm1c[c] : vm1s; }
-    __device__ __forceinline__ double vp1(int c) const { return AXI ? vp1c[c] : vp1s; }
+    static constexpr int C = kS2LaneCells;
+    double gx[C + 1];            // a_vx_p factor of cell c-1 (gx[0]: the left-hand lane's last cell)
+    double gy[C], fy[C];         // a_vy_p, a_p_vy factors of cell c
+    double fx[C + 1];            // a_p_vx factor of cell c (fx[C]: the right-hand lane's first cell);
+                                 // axisymmetric: divided by r of the column
+    double v0[C], vmn[C], vpn[C];   // a_v_v main and +-nx diagonals of cell c
+    double vm1[C], vp1[C];       // a_v_v x diagonals: entry of cell c-1 / of cell c+1
+    double eb[C];                // axisymmetric extra term dt*mu/rho of cell c
+    double r[C + 1], rr[C];      // axisymmetric: r of columns x0 .. x0+C, r^2 of x0 .. x0+C-1
 };
 
 // One stage on a steady row: `cur` = row q at level s on entry, row q-2 at level s+1 on exit.
@@ -67,7 +69,7 @@ __device__ __forceinline__ void sv_steady_stage(
     const double (&uA)[kS2LaneCells], const double (&vA)[kS2LaneCells], double (&pB)[kS2LaneCells],
     double (&uB)[kS2LaneCells], double (&vB)[kS2LaneCells], const double (&U)[kS2LaneCells],
     const double (&V)[kS2LaneCells], double (&Un)[kS2LaneCells], double (&Vn)[kS2LaneCells],
-    const SVCoef<AXI> &k, const double (&ca)[kS2LaneCells], const double (&cv)[kS2LaneCells]) {
+    const SVCoef &k, const double (&ca)[kS2LaneCells], const double (&cv)[kS2LaneCells]) {
     constexpr int C = kS2LaneCells;
     if (CC == 0) {
 #pragma unroll
@@ -85,27 +87,27 @@ __device__ __forceinline__ void sv_steady_stage(
 #pragma unroll
     for (int c = 0; c < C; ++c) {
         const double pl = c ? pA[c - 1] : p1_left;
-        const double du = diff2(k.gx, pl, k.gx, pA[c]);
-        const double dv = diff2(k.gy, pB[c], k.gy, pA[c]);
+        const double du = diff2(k.gx[c], pl, k.gx[c + 1], pA[c]);
+        const double dv = diff2(k.gy[c], pB[c], k.gy[c], pA[c]);
         const double uold = uA[c], vold = vA[c];
         if (VISC) {
             const double ul = c ? uA[c - 1] : u1_left;
             const double ur = c < C - 1 ? uA[c + 1] : u1_right;
             const double vl = c ? vA[c - 1] : v1_left;
             const double vr = c < C - 1 ? vA[c + 1] : v1_right;
-            double vis = acc0(mul(k.vmn, uB[c]));
-            vis = add(vis, mul(k.vm1(c), ul));
-            vis = add(vis, mul(k.v0, uold));
-            vis = add(vis, mul(k.vp1(c), ur));
-            vis = add(vis, mul(k.vpn, cur[1][c]));
+            double vis = acc0(mul(k.vmn[c], uB[c]));
+            vis = add(vis, mul(k.vm1[c], ul));
+            vis = add(vis, mul(k.v0[c], uold));
+            vis = add(vis, mul(k.vp1[c], ur));
+            vis = add(vis, mul(k.vpn[c], cur[1][c]));
             double rhs = sub(du, vis);
-            if (AXI) rhs = add(rhs, mul(k.eb, uold) / k.rr[c]);
+            if (AXI) rhs = add(rhs, mul(k.eb[c], uold) / k.rr[c]);
             Un[c] = sub(uold, rhs);
-            double visv = acc0(mul(k.vmn, vB[c]));
-            visv = add(visv, mul(k.vm1(c), vl));
-            visv = add(visv, mul(k.v0, vold));
-            visv = add(visv, mul(k.vp1(c), vr));
-            visv = add(visv, mul(k.vpn, cur[2][c]));
+            double visv = acc0(mul(k.vmn[c], vB[c]));
+            visv = add(visv, mul(k.vm1[c], vl));
+            visv = add(visv, mul(k.v0[c], vold));
+            visv = add(visv, mul(k.vp1[c], vr));
+            visv = add(visv, mul(k.vpn[c], cur[2][c]));
             Vn[c] = sub(vold, sub(dv, visv));
         } else {
             Un[c] = AXI ? sub(uold, add(du, mul(0.0, uold))) : sub(uold, du);
@@ -122,8 +124,8 @@ __device__ __forceinline__ void sv_steady_stage(
             f0 = mul(f0, k.r[c]);
             f1 = mul(f1, k.r[c + 1]);
         }
-        const double divx = diff2(k.fx(c), f0, k.fx(c + 1), f1);
-        const double divy = diff2(k.fy, V[c], k.fy, Vn[c]);
+        const double divx = diff2(k.fx[c], f0, k.fx[c + 1], f1);
+        const double divy = diff2(k.fy[c], V[c], k.fy[c], Vn[c]);
         np[c] = sub(pB[c], add(divx, divy));
     }
 #pragma unroll
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
         };
         if (lane == 0)
             for (int d = 0; d < kS2RingDepth && r0 + d < r1; d += 2) issue_pair(r0 + d, d);
-        // optional counters (tests): as in stream2d_kernel, a.stats[4] stays 0 here
+        // optional counters (tests): as in stream2d_kernel
         if (a.stats && lane == 0) atomicAdd(a.stats + 6, (unsigned long long)(r1 - r0));
 
         // pipeline state per stage: p after boundaries, old vx, old vy of rows q-1 (A) and q-2 (B);
@@ -272,8 +274,9 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
             }
             return m;
         };
-        // steady for THIS kernel: RowTag::steady and of one material
-        auto sv_steady = [](const RowTag &t) { return t.steady() && !(t.bits & 32u); };
+        // (the axisymmetric model keeps rows of several materials on the general row iteration: per-lane
+        // copies of its per-column AND per-material coefficients do not fit the register budget)
+        auto sv_steady = [](const RowTag &t) { return t.steady() && !(AXI && (t.bits & 32u)); };
         RowTag m0 = fetch(), m1 = fetch();
         // What the pipeline computes from the rows above r0 (zero state) never reaches an owned row,
         // so those rows may as well count as rows like the first one (see stream2d_kernel).
@@ -287,36 +290,53 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
         int r = r0;
         // ---- steady pairs: rows r-2K .. r+1 carry the same map words (one material, no table
         // lookup, no probe, constant operations on component CC only, or none: CC = -1) -------------
-        auto steady_pairs = [&](auto cc_tag) {
+        auto steady_pairs = [&](auto cc_tag, auto uni_tag) {
             constexpr int CC = decltype(cc_tag)::value;
-            if (a.stats && lane == 0) atomicAdd(a.stats + CC + 1, 1ull);
+            constexpr bool UNI = decltype(uni_tag)::value;   // one material: warp-uniform coefficients
+            if (a.stats && lane == 0) atomicAdd(a.stats + (UNI ? CC + 1 : 4), 1ull);
             const unsigned my_ids = info[0].ids;
-            const int m = (int)(info[0].bits & kIdMask);
-            SVCoef<AXI> k;
-            k.gx = tabs[FDS_TAB_GX][m];
-            k.gy = tabs[FDS_TAB_GY][m];
-            k.fy = tabs[FDS_TAB_FY][m];
-            k.fx0 = tabs[FDS_TAB_FX][m];
-            if (VISC) {
-                k.v0 = tabs[FDS_TAB_V0][m];
-                k.vmn = tabs[FDS_TAB_VMN][m];
-                k.vpn = tabs[FDS_TAB_VPN][m];
-                k.vm1s = tabs[FDS_TAB_VM1][m];
-                k.vp1s = tabs[FDS_TAB_VP1][m];
-                k.eb = tabs[FDS_TAB_EB][m];
-            }
-            if (AXI) {
+            SVCoef k;
+            {
+                const unsigned material = info[0].bits & kIdMask;
+                const unsigned left = __shfl_up_sync(0xffffffffu, my_ids, 1) >> (16 * (C - 1));
+                const unsigned right = __shfl_down_sync(0xffffffffu, my_ids, 1);
+                // material of cell c (-1 .. C) of this lane
+                auto mat = [&](int c) {
+                    if (UNI) return material;
+                    return (c < 0 ? left : c >= C ? right : my_ids >> (16 * c)) & kIdMask;
+                };
+                // one material: every entry of a table comes from ONE register
+                auto tab = [&](int which, int c) {
+                    return tabs[which][mat(c)];
+                };
+                const double u_gx = tabs[FDS_TAB_GX][material], u_gy = tabs[FDS_TAB_GY][material];
+                const double u_fx = tabs[FDS_TAB_FX][material], u_fy = tabs[FDS_TAB_FY][material];
+                const double u_v0 = tabs[FDS_TAB_V0][material], u_eb = tabs[FDS_TAB_EB][material];
+                const double u_vmn = tabs[FDS_TAB_VMN][material];
+                const double u_vpn = tabs[FDS_TAB_VPN][material];
+                const double u_vm1 = tabs[FDS_TAB_VM1][material];
+                const double u_vp1 = tabs[FDS_TAB_VP1][material];
 #pragma unroll
                 for (int c = 0; c <= C; ++c) {
-                    k.fxc[c] = ctab(FDS_CTAB_FX, m, col_of(c));
-                    k.r[c] = __ldg(av.cvec + FDS_CVEC_R * nx + col_of(c));
+                    k.gx[c] = UNI ? u_gx : tab(FDS_TAB_GX, c - 1);
+                    k.fx[c] = AXI ? ctab(FDS_CTAB_FX, mat(c), col_of(c))
+                                  : UNI ? u_fx : tab(FDS_TAB_FX, c);
+                    if (AXI) k.r[c] = __ldg(av.cvec + FDS_CVEC_R * nx + col_of(c));
                 }
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    k.rr[c] = __ldg(av.cvec + FDS_CVEC_RR * nx + col_of(c));
+                    k.gy[c] = UNI ? u_gy : tab(FDS_TAB_GY, c);
+                    k.fy[c] = UNI ? u_fy : tab(FDS_TAB_FY, c);
+                    if (AXI) k.rr[c] = __ldg(av.cvec + FDS_CVEC_RR * nx + col_of(c));
                     if (VISC) {
-                        k.vm1c[c] = ctab(FDS_CTAB_VM1, m, col_of(c - 1));
-                        k.vp1c[c] = ctab(FDS_CTAB_VP1, m, col_of(c + 1));
+                        k.v0[c] = UNI ? u_v0 : tab(FDS_TAB_V0, c);
+                        k.vmn[c] = UNI ? u_vmn : tab(FDS_TAB_VMN, c);
+                        k.vpn[c] = UNI ? u_vpn : tab(FDS_TAB_VPN, c);
+                        k.eb[c] = UNI ? u_eb : tab(FDS_TAB_EB, c);
+                        k.vm1[c] = AXI ? ctab(FDS_CTAB_VM1, mat(c - 1), col_of(c - 1))
+                                       : UNI ? u_vm1 : tab(FDS_TAB_VM1, c - 1);
+                        k.vp1[c] = AXI ? ctab(FDS_CTAB_VP1, mat(c + 1), col_of(c + 1))
+                                       : UNI ? u_vp1 : tab(FDS_TAB_VP1, c + 1);
                     }
                 }
             }
@@ -382,12 +402,16 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
                 (m0.plain() ||
                  __all_sync(0xffffffffu, m0.ids == info[0].ids && m1.ids == info[0].ids))) {
                 using std::integral_constant;
-                switch (m0.classed()) {
-                    case 0u: steady_pairs(integral_constant<int, -1>{}); break;
-                    case 1u: steady_pairs(integral_constant<int, 0>{}); break;
-                    case 2u: steady_pairs(integral_constant<int, 1>{}); break;
-                    default: steady_pairs(integral_constant<int, 2>{}); break;
-                }
+                using std::true_type;
+                if (!AXI && (m0.bits & 32u))
+                    steady_pairs(integral_constant<int, -1>{}, std::false_type{});
+                else
+                    switch (m0.classed()) {
+                        case 0u: steady_pairs(integral_constant<int, -1>{}, true_type{}); break;
+                        case 1u: steady_pairs(integral_constant<int, 0>{}, true_type{}); break;
+                        case 2u: steady_pairs(integral_constant<int, 1>{}, true_type{}); break;
+                        default: steady_pairs(integral_constant<int, 2>{}, true_type{}); break;
+                    }
                 continue;
             }
 
