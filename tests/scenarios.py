@@ -245,6 +245,61 @@ def thermal1d(fds):
     return fld, 300
 
 
+# ---- wide grids (nx >= 128, a multiple of 4): every model on its streaming kernel ------------------
+
+def acoustic2d_lossy_wide(fds):
+    """Viscous streaming kernel (2 steps per launch, three strips side by side)."""
+    return _acoustic2d(fds, lossy=True, nx=160, ny=53, steps=45, seed=13)
+
+
+def acoustic3daxi_lossy_wide(fds):
+    return _acoustic2d(fds, lossy=True, nx=144, ny=47, steps=41, seed=14, klass='Acoustic3DAxi')
+
+
+def acoustic3daxi_lossless_wide(fds):
+    """Axisymmetric instantiation of the lossless streaming kernel (4 steps per launch)."""
+    return _acoustic2d(fds, lossy=False, nx=152, ny=49, steps=43, seed=15, klass='Acoustic3DAxi')
+
+
+def thermal2d_wide(fds):
+    return _thermal2d(fds, 'Thermal2D', 136, 45, 50, seed=16)
+
+
+def thermal3daxi_wide(fds):
+    return _thermal2d(fds, 'Thermal3DAxi', 140, 43, 50, seed=17)
+
+
+def acoustic2d_signal_lines(fds):
+    """Source lines driven by ONE signal each (the device applies them as classes, not through the
+    boundary table): a transducer face along y, one along x, two lines sharing a signal, a
+    non-additive signal line on velocity_x, and a per-point signal line (table path) across them."""
+    nx, ny, steps = 168, 57, 48
+    mm = 1e-3
+    fld = fds.Acoustic2D(t_delta=1e-7, t_samples=steps, x_delta=mm, x_samples=nx, y_delta=mm,
+                         y_samples=ny, material=fds.AcousticMaterial(1500, 1000))
+    fld.add_material_region(fld.get_rect_region((100 * mm, 10 * mm, 30 * mm, 30 * mm)),
+                            fds.AcousticMaterial(1200, 900))
+    _randomise(fld, ('pressure', 'velocity_x', 'velocity_y'), seed=18)
+    top = (ny - 1) * mm
+    burst = _pulse(steps, 20, 8)
+    fld.pressure.add_boundary(fld.get_line_region((0, 5 * mm, 0, 45 * mm)), value=burst,
+                              additive=True)
+    fld.pressure.add_boundary(fld.get_line_region((60 * mm, 0, 60 * mm, top)), value=burst.copy(),
+                              additive=True)
+    fld.pressure.add_boundary(fld.get_line_region((10 * mm, 30 * mm, 150 * mm, 30 * mm)),
+                              value=_pulse(steps, 12, 5), additive=True)
+    fld.velocity_x.add_boundary(fld.get_line_region((111 * mm, 0, 111 * mm, top)),
+                                value=1e-4 * _pulse(steps, 25, 10))
+    fld.velocity_y.add_boundary(fld.get_line_region((20 * mm, 50 * mm, 27 * mm, 50 * mm)),
+                                value=[1e-4 * _pulse(steps, 15 + k, 6) for k in range(8)],
+                                additive=True)
+    fld.velocity_x.add_boundary(fld.get_line_region((nx * mm - mm, 0, nx * mm - mm, top)))
+    for m in range(1, 4):
+        fld.pressure.add_output(fld.get_point_region(((m * nx // 4) * mm, (m * ny // 4) * mm)))
+    fld.velocity_x.add_output(fld.get_line_region((58 * mm, 20 * mm, 62 * mm, 20 * mm)))
+    return fld, steps
+
+
 SCENARIOS = {
     'acoustic1d_lossy': acoustic1d_lossy,
     'acoustic1d_lossless': acoustic1d_lossless,
@@ -260,6 +315,12 @@ SCENARIOS = {
     'thermal1d': thermal1d,
     'acoustic_flow2d': acoustic_flow2d,
     'acoustic_flow2d_wide': acoustic_flow2d_wide,
+    'acoustic2d_lossy_wide': acoustic2d_lossy_wide,
+    'acoustic3daxi_lossy_wide': acoustic3daxi_lossy_wide,
+    'acoustic3daxi_lossless_wide': acoustic3daxi_lossless_wide,
+    'thermal2d_wide': thermal2d_wide,
+    'thermal3daxi_wide': thermal3daxi_wide,
+    'acoustic2d_signal_lines': acoustic2d_signal_lines,
 }
 
 

@@ -47,6 +47,17 @@ def test_scenario_matches_reference_golden_bitwise(library, name):
     got = scenarios.collect(field)
     gold = np.load(os.path.join(GOLDEN, name + '.npz'))
     assert_same(got, {k: gold[k] for k in gold.files if k != 'versions'}, name)
+    # the wide scenarios exist to pin the streaming kernels to the real reference
+    expected_kernel = {'acoustic2d_wide': 'stream2d_kernel<acoustic2d',
+                       'acoustic2d_signal_lines': 'stream2d_kernel<acoustic2d',
+                       'acoustic2d_lossy_wide': 'streamv_kernel<acoustic2d',
+                       'acoustic3daxi_lossy_wide': 'streamv_kernel<acoustic3daxi',
+                       'acoustic3daxi_lossless_wide': 'stream2d_kernel<acoustic3daxi',
+                       'thermal2d_wide': 'stream2d_kernel<thermal2d',
+                       'thermal3daxi_wide': 'stream2d_kernel<thermal3daxi'}.get(name)
+    if expected_kernel:
+        launches, spl, kernel = field.__dict__['_engine_state'].engine.last_launch_info()
+        assert expected_kernel in kernel and spl >= 2, (name, kernel, spl)
 
 
 @pytest.mark.parametrize('name', ['acoustic1d_lossy', 'acoustic1d_lossless', 'acoustic1d_long',
