@@ -634,10 +634,15 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
         // 4 rounds 361, 16 rounds of 128-row tasks 401 Gcell-updates/s -- a quarter of the time was
         // the tail of the slowest SMs), so tasks stay about kTargetRows tall and the dynamic
         // distribution evens the SMs out; shorter tasks pay more for the rows streamed twice.
-        double target_rows = 128.0;
-        if (const char *env = getenv("FDS_TARGET_ROWS")) target_rows = std::max(8.0, atof(env));
         double total_cost = 0;
         for (int s = 0; s < n_strips; ++s) total_cost += strip_cost[(size_t)s];
+        // With only a few rounds the tail of the slowest SMs weighs more than the rows streamed
+        // twice: shorter tasks there. Measured (profiles/r1_target_rows.log): lossless 4096^2
+        // 345 / 352 / 341 and axisymmetric 8192x4096 286 / 302 / 304 Gcell-updates/s at 128 / 96 / 64
+        // rows; the viscous kernel (twice the pipeline fill per task) 176 / 163 / 154.
+        double target_rows = 128.0;
+        if (!ctx->use_streamv && total_cost / slots / 128.0 < 4.0) target_rows = 96.0;
+        if (const char *env = getenv("FDS_TARGET_ROWS")) target_rows = std::max(8.0, atof(env));
         const int rounds = (int)std::max(1.0, std::floor(total_cost / slots / target_rows + 0.5));
         double lo = overhead + (double)min_rows, hi = general_weight * (double)rows + overhead;
         if (tasks_for(lo) <= rounds * slots) hi = lo;
