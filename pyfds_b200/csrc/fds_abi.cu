@@ -636,12 +636,14 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
         // distribution evens the SMs out; shorter tasks pay more for the rows streamed twice.
         double total_cost = 0;
         for (int s = 0; s < n_strips; ++s) total_cost += strip_cost[(size_t)s];
-        // With only a few rounds the tail of the slowest SMs weighs more than the rows streamed
-        // twice: shorter tasks there. Measured (profiles/r1_target_rows.log): lossless 4096^2
-        // 345 / 352 / 341 and axisymmetric 8192x4096 286 / 302 / 304 Gcell-updates/s at 128 / 96 / 64
-        // rows; the viscous kernel (twice the pipeline fill per task) 176 / 163 / 154.
+        // With two or three rounds the tail of the slowest SMs weighs more than the rows streamed
+        // twice: shorter tasks there. Measured (profiles/r1_target_rows.log, 128 / 96 / 64 rows):
+        // axisymmetric 8192x4096 (2.7 rounds at 128) 286 / 302 / 304 Gcell-updates/s; lossless 4096^2
+        // (1.3 rounds: one task per warp either way) 342.9 / 340.2 in an alternating 2000-step A/B;
+        // the viscous kernel (twice the pipeline fill per task) 176 / 163 / 154.
         double target_rows = 128.0;
-        if (!ctx->use_streamv && total_cost / slots / 128.0 < 4.0) target_rows = 96.0;
+        const double rounds_at_128 = total_cost / slots / 128.0;
+        if (!ctx->use_streamv && rounds_at_128 >= 2.0 && rounds_at_128 < 4.0) target_rows = 96.0;
         if (const char *env = getenv("FDS_TARGET_ROWS")) target_rows = std::max(8.0, atof(env));
         const int rounds = (int)std::max(1.0, std::floor(total_cost / slots / target_rows + 0.5));
         double lo = overhead + (double)min_rows, hi = general_weight * (double)rows + overhead;
