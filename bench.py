@@ -275,6 +275,13 @@ def main():
         t = torch.tensor([device_ms], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         device_ms = float(t.item())
+        # launches of the step kernel on all ranks (the halo wait / push kernels of the peer-memory
+        # path, two more per launch and rank, are not counted)
+        n = torch.tensor([launches], dtype=torch.int64, device='cuda')
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        total_launches = int(n.item())
+    else:
+        total_launches = launches
 
     cells = nx * ny
     per_gpu_cells = nx * rows
@@ -357,7 +364,7 @@ def main():
                          # algorithmic figure above the peak; this one cannot exceed it)
                          'dram_gbs': traffic / (launch_ms * 1e6) if traffic else None,
                          'dram_frac': traffic / (launch_ms * 1e6) / peak if traffic else None},
-            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': total_launches, 'clocks': clocks,
             'wall_seconds': wall,
         }
         print(json.dumps(line), flush=True)
