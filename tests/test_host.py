@@ -117,6 +117,24 @@ def test_boundary_table_order_duplicates_and_windows():
     assert part.cells.min() >= 0 and part.cells.max() < 10 * nx
 
 
+def test_equal_region_signals_share_one_window():
+    """Boundaries driven by bit-equal signals get ONE signal index (the device applies single-signal
+    cells through at most 7 classes per component); per-point signals keep one index per point."""
+    fld, steps = scenarios.acoustic2d_signal_lines(fds)
+    signals = []
+    table = _bake.boundary_table(fld.pressure.boundaries, 0, steps, 0, fld.num_points, signals)
+    # three boundaries on pressure: two lines with the same burst (one of them a copy), one other pulse
+    assert len(signals) == 2
+    assert sorted(set(table.signal.tolist())) == [0, 1]
+    nx = fld.x.samples
+    first = table.signal[table.offsets[np.searchsorted(table.cells, 5 * nx)]]          # (0, 5)
+    second = table.signal[table.offsets[np.searchsorted(table.cells, 60)]]             # (60, 0)
+    assert first == second
+    # a different window of the same signals is still shared, and a second component appends
+    table_vy = _bake.boundary_table(fld.velocity_y.boundaries, 0, steps, 0, fld.num_points, signals)
+    assert len(signals) == 2 + 8 and len(set(table_vy.signal.tolist())) == 8
+
+
 def test_probe_table_slots():
     fld, _ = scenarios.acoustic2d_boundaries(fds)
     cells, slots, nxt = _bake.probe_table(fld.pressure.outputs, 0, 0, fld.num_points)

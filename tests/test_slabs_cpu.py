@@ -34,6 +34,16 @@ def test_halo_rows():
     assert parallel.halo_rows_for(lossless, 4, kernel=1) == 1
     assert parallel.halo_rows_for(lossy, 2) == 2                           # viscous 5-point operator
     assert parallel.halo_rows_for(thermal, 2) == 1
+    # wide grids: every 2-D model on a streaming kernel, halo = reach x steps per launch
+    lossy_wide, _ = scenarios.acoustic2d_lossy_wide(fds)
+    axi_lossy, _ = scenarios.acoustic3daxi_lossy_wide(fds)
+    axi_lossless, _ = scenarios.acoustic3daxi_lossless_wide(fds)
+    thermal_axi, _ = scenarios.thermal3daxi_wide(fds)
+    assert parallel.halo_rows_for(lossy_wide, 2) == 2 * parallel.STREAMV_STEPS
+    assert parallel.halo_rows_for(axi_lossy, 8) == 2 * parallel.STREAMV_STEPS
+    assert parallel.halo_rows_for(axi_lossless, 2) == parallel.STREAM_STEPS
+    assert parallel.halo_rows_for(thermal_axi, 2) == parallel.STREAM_STEPS
+    assert parallel.halo_rows_for(lossy_wide, 2, kernel=1) == 2
 
 
 def test_slab_tables_cover_the_global_tables():
@@ -76,7 +86,8 @@ def _worker(rank, world, port, name, steps_per_exchange, queue):
 
 @pytest.mark.parametrize('name,steps_per_exchange', [
     ('acoustic2d_lossless', 1), ('acoustic2d_wide', 4), ('acoustic2d_lossy', 1),
-    ('acoustic2d_boundaries', 2), ('thermal2d', 1)])
+    ('acoustic2d_boundaries', 2), ('thermal2d', 1), ('acoustic2d_lossy_wide', 2),
+    ('acoustic3daxi_lossless_wide', 4), ('thermal3daxi_wide', 4), ('acoustic2d_signal_lines', 4)])
 def test_two_rank_halo_protocol_matches_single_domain(name, steps_per_exchange):
     import torch.multiprocessing as mp
     world = 2
