@@ -32,59 +32,56 @@ logger = lo.getLogger('pyfds')
 
 
 class SynchronizedFields(fld.Field):
-    """Several fields with the same time stepping, stepped together.
-    Reference: ``pyfds/coupling.py:14-87``."""
+    """Several fields on the same axes and time base, advanced in lock step, with ``interactions``
+    applied after every common step. Public surface of ``pyfds/coupling.py:14-87``: ``fields``,
+    ``interactions``, the axes ``t`` / ``x`` (/ ``y``) of the first field, every field's components as
+    attributes of the group, ``step`` / ``num_points`` / ``material_regions`` / ``matrices_assembled``
+    as views of the members."""
 
     def __init__(self, fields, interactions):
         self.fields = fields
         self.interactions = interactions
 
-        # expose the components of all fields as attributes (the reference does this for gfx)
-        for field in self.fields:
-            for name, value in vars(field).items():
-                if isinstance(value, fld.FieldComponent):
-                    if not hasattr(self, name):
-                        self.__setattr__(name, value)
-                    else:
-                        raise RuntimeError("Coupling of fields with identically named components "
-                                           "is currently not possible")
+        # The components of all members become attributes of the group (animators and user scripts
+        # address ``group.pressure``); two members with a component of the same name cannot be told
+        # apart that way, which the reference refuses with this very error.
+        for member in fields:
+            components = {name: value for name, value in vars(member).items()
+                          if isinstance(value, fld.FieldComponent)}
+            clash = [name for name in components if hasattr(self, name)]
+            if clash:
+                raise RuntimeError("Coupling of fields with identically named components "
+                                   "is currently not possible")
+            vars(self).update(components)
 
-        self.t = self.fields[0].t
-        self.x = self.fields[0].x
-        if hasattr(self.fields[0], 'y'):
-            self.y = self.fields[0].y
+        leader = fields[0]
+        self.t, self.x = leader.t, leader.x
+        if hasattr(leader, 'y'):
+            self.y = leader.y
 
-    @property
-    def step(self):
-        return self.fields[0].step
+    # the group has no state of its own: these are views of its members
+    step = property(lambda self: self.fields[0].step)
 
     @step.setter
     def step(self, value):
-        for field in self.fields:
-            field.step = value
+        for member in self.fields:
+            member.step = value
 
-    @property
-    def num_points(self):
-        return self.fields[0].num_points
-
-    @property
-    def material_regions(self):
-        regions = []
-        for field in self.fields:
-            regions += field.material_regions
-        return regions
+    num_points = property(lambda self: self.fields[0].num_points)
+    material_regions = property(
+        lambda self: [region for member in self.fields for region in member.material_regions])
+    matrices_assembled = property(
+        lambda self: all(member.matrices_assembled for member in self.fields))
 
     def assemble_matrices(self):
-        for field in self.fields:
-            field.assemble_matrices()
-
-    @property
-    def matrices_assembled(self):
-        return all([field.matrices_assembled for field in self.fields])
+        for member in self.fields:
+            member.assemble_matrices()
 
     def sim_step(self):
-        for field in self.fields:
-            field.sim_step()
+        """One common step (``pyfds/coupling.py:81-87``): every member's own ``sim_step`` -- one device
+        step each, host ``values`` coherent afterwards -- then the interactions in list order."""
+        for member in self.fields:
+            member.sim_step()
         for interaction in self.interactions:
             interaction.apply(self.step)
 
@@ -172,105 +169,112 @@ class SynchronizedFields(fld.Field):
         return True
 
 
-class BoundaryCoupling():
-    """Feeds a function of one component into another component, every ``stepping``-th step,
-    optionally accumulating in between. Reference: ``pyfds/coupling.py:90-140``."""
+class BoundaryCoupling:
+    """``target.values (+)= f(source.values)`` every ``stepping``-th step; with ``accumulate`` the
+    function is evaluated after every step and the sum since the last delivery is handed over.
+    Attributes and behaviour of ``pyfds/coupling.py:90-140`` (``additive`` / ``accumulate`` are compared
+    by identity with ``True`` / ``False`` there, so that is what decides here as well)."""
 
     def __init__(self, source_component, target_component, transfer_function,
                  additive=True, accumulate=False, stepping=1):
-        self.source_component = source_component
-        self.target_component = target_component
+        self.source_component, self.target_component = source_component, target_component
         self.transfer_function = transfer_function
-        self.additive = additive
-        self.accumulate = accumulate
-        self.stepping = stepping
+        self.additive, self.accumulate, self.stepping = additive, accumulate, stepping
+        self.accumulated_transfer = 0      # sum of f(source) since the last delivery
 
-        self.accumulated_transfer = 0
+    def _evaluate(self):
+        return self.transfer_function(self.source_component.values)
 
     def apply(self, step):
         if self.accumulate is True:
-            self.accumulated_transfer += self.transfer_function(self.source_component.values)
+            self.accumulated_transfer += self._evaluate()
+        if step % self.stepping:
+            return
+        if self.accumulate is False:
+            delivery = self._evaluate()
+        else:
+            delivery, self.accumulated_transfer = self.accumulated_transfer, 0
+        target = self.target_component
+        if self.additive is True:
+            target.values += delivery      # in place, like the reference: views stay valid
+        else:
+            target.values = delivery
 
-        if step % self.stepping == 0:
-            if self.accumulate is False:
-                transfer = self.transfer_function(self.source_component.values)
-            else:
-                transfer = self.accumulated_transfer
-                self.accumulated_transfer = 0
-            if self.additive is True:
-                self.target_component.values += transfer
-            else:
-                self.target_component.values = transfer
 
+class MaterialCoupling:
+    """Scales one material parameter of ``target_field`` point by point with a function of another
+    field's component, and re-assembles the target when the factors have moved by more than
+    ``rel_change_threshold`` (always, if that is ``None``). Public surface of
+    ``pyfds/coupling.py:143-215``.
 
-class MaterialCoupling():
-    """Scales one material parameter of a field by a function of another field's component and
-    re-assembles the target field when the factors changed enough.
-    Reference: ``pyfds/coupling.py:143-215``.
-
-    The target field's ``material_vector`` is replaced on the instance, as in the reference; the device
-    engine then bakes its material ids from those per-point vectors (distinct value combinations become
-    materials, at most 31 of them -- see ``_bake.DenseSnapshot``)."""
+    As in the reference the target's ``material_vector`` is shadowed on the instance (the original stays
+    reachable as ``static_material_vector``), so whoever assembles the target sees the scaled parameter;
+    the device engine bakes its material ids from those per-point vectors (distinct value combinations
+    become materials, at most 31 of them -- see ``_bake.DenseSnapshot``)."""
 
     def __init__(self, source_component, target_field, target_parameter,
                  transfer_function, rel_change_threshold=None, stepping=1):
-        self.source_component = source_component
-        self.target_field = target_field
-        self.target_parameter = target_parameter
-        self.transfer_function = transfer_function
-        self.rel_change_threshold = rel_change_threshold
-        self.stepping = stepping
+        self.source_component, self.target_field = source_component, target_field
+        self.target_parameter, self.transfer_function = target_parameter, transfer_function
+        self.rel_change_threshold, self.stepping = rel_change_threshold, stepping
+        self.last_used_factors = 0         # factors of the last re-assembly
+        target_field.static_material_vector = target_field.material_vector
+        target_field.material_vector = self._material_vector
 
-        self.last_used_factors = 0
-
-        self.target_field.static_material_vector = self.target_field.material_vector
-        self.target_field.material_vector = self._material_vector
+    def _factors(self):
+        return self.transfer_function(self.source_component.values)
 
     def _material_vector(self, mat_parameter):
-        if mat_parameter == self.target_parameter:
-            return self.target_field.static_material_vector(mat_parameter) \
-                * self.transfer_function(self.source_component.values)
-        return self.target_field.static_material_vector(mat_parameter)
+        plain = self.target_field.static_material_vector(mat_parameter)
+        return plain * self._factors() if mat_parameter == self.target_parameter else plain
 
     def apply(self, step):
-        if step % self.stepping == 0:
-            transfer_factors = self.transfer_function(self.source_component.values)
-            rel_change = max(abs((transfer_factors - self.last_used_factors) / transfer_factors))
-            if self.rel_change_threshold is None or rel_change > self.rel_change_threshold:
-                self.target_field.assemble_matrices()
-                self.last_used_factors = transfer_factors
-                if self.rel_change_threshold is not None:
-                    logger.info(f"Relative change in parameters is {rel_change}.")
-                    logger.info(f"Matrices reassembled in step {step}.")
+        if step % self.stepping:
+            return
+        factors = self._factors()
+        rel_change = max(abs((factors - self.last_used_factors) / factors))
+        threshold = self.rel_change_threshold
+        if threshold is not None and not rel_change > threshold:
+            return
+        self.target_field.assemble_matrices()
+        self.last_used_factors = factors
+        if threshold is not None:
+            logger.info(f"Relative change in parameters is {rel_change}.")
+            logger.info(f"Matrices reassembled in step {step}.")
 
 
-class MaterialCouplingExponential(MaterialCoupling):
-    """``p * (a + (1 - a) * exp(b * q))``. Reference: ``pyfds/coupling.py:218-259``."""
+class _ParametricMaterialCoupling(MaterialCoupling):
+    """A ``MaterialCoupling`` whose transfer function is a method of the instance."""
+
+    def __init__(self, source_component, target_field, target_parameter, rel_change_threshold,
+                 stepping):
+        super().__init__(source_component, target_field, target_parameter, self.transfer_function,
+                         rel_change_threshold=rel_change_threshold, stepping=stepping)
+
+
+class MaterialCouplingExponential(_ParametricMaterialCoupling):
+    """Factor ``a + (1 - a) * exp(b * q)`` of the source values ``q``
+    (``pyfds/coupling.py:218-259``)."""
 
     def __init__(self, source_component, target_field, target_parameter, a, b,
                  rel_change_threshold=None, stepping=1):
-        self.a = a
-        self.b = b
-        super().__init__(source_component=source_component, target_field=target_field,
-                         target_parameter=target_parameter,
-                         transfer_function=self.transfer_function,
-                         rel_change_threshold=rel_change_threshold, stepping=stepping)
+        self.a, self.b = a, b
+        super().__init__(source_component, target_field, target_parameter, rel_change_threshold,
+                         stepping)
 
     def transfer_function(self, values):
         return self.a + (1 - self.a) * np.exp(self.b * values)
 
 
-class MaterialCouplingPowerLaw(MaterialCoupling):
-    """``p * (1 + factor * q ** power)``. Reference: ``pyfds/coupling.py:262-300``."""
+class MaterialCouplingPowerLaw(_ParametricMaterialCoupling):
+    """Factor ``1 + factor * q ** power`` of the source values ``q``
+    (``pyfds/coupling.py:262-300``)."""
 
     def __init__(self, source_component, target_field, target_parameter, power, factor,
                  rel_change_threshold=None, stepping=1):
-        self.power = power
-        self.factor = factor
-        super().__init__(source_component=source_component, target_field=target_field,
-                         target_parameter=target_parameter,
-                         transfer_function=self.transfer_function,
-                         rel_change_threshold=rel_change_threshold, stepping=stepping)
+        self.power, self.factor = power, factor
+        super().__init__(source_component, target_field, target_parameter, rel_change_threshold,
+                         stepping)
 
     def transfer_function(self, values):
         return 1 + self.factor * values ** self.power
