@@ -8,7 +8,9 @@
   additive point source, rigid line at x = 0, 4 Output probes. State (3 x 134 MB, two buffers) is far
   larger than the 126 MB L2, so successive steps cannot be served from cache.
 * N > 1 (torchrun, one rank per GPU): weak scaling -- every rank owns a 4096-row y-slab of a
-  4096 x (4096 N) grid and exchanges halo rows with its neighbours through NCCL.
+  4096 x (4096 N) grid; after every launch the outermost rows go straight into the neighbours' halo
+  rows over NVLink peer memory (NCCL send/recv if there is no peer access). ``--strong`` cuts ONE
+  size x size grid into slabs instead (BASELINE.json config 5: ``--size 32768 --strong``).
 * ``value``: K steps with the state resident in HBM, timed with CUDA events on the engine's stream
   inside a barrier + device-synchronise bracket, max over ranks.
 * ``e2e``: the same K steps through the public API (``field.simulate(K)``): host arrays in, host
@@ -211,6 +213,10 @@ def main():
     parser.add_argument('--no-cpu-baseline', action='store_true')
     parser.add_argument('--no-e2e', action='store_true')
     parser.add_argument('--no-wall', action='store_true', help='experiment: drop the x=0 rigid line')
+    parser.add_argument('--strong', action='store_true',
+                        help='strong scaling: ONE size x size grid cut into y-slabs over the ranks '
+                             '(BASELINE.json config 5 with --size 32768); default is weak scaling, '
+                             'size x size per GPU')
     args = parser.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -234,6 +240,10 @@ def main():
 
     nx, rows = args.size, args.size
     ny = rows * world
+    if args.strong:
+        if args.size % world:
+            raise SystemExit('--strong needs a size that is a multiple of the number of GPUs')
+        rows, ny = args.size // world, args.size
     total_steps = args.warmup + args.steps
     field = build_field(fds, nx, ny, total_steps + 1, wall=not args.no_wall)
     field.assemble_matrices()
@@ -345,8 +355,8 @@ def main():
         line = {
             'metric': METRIC, 'value': value, 'unit': 'Gcell-updates/s', 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': device_ms / args.steps,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic',
+            'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {
                 'workload': 'Acoustic2D {}x{} fp64 per GPU, 2 material regions, additive point '
                             'source, rigid line x=0, 4 Output probes'.format(nx, rows),
