@@ -1,0 +1,61 @@
+"""The driver-facing contract of bench.py that can be checked without a GPU: the reference arm's JSON
+line, and that the product arm refuses to run (instead of falling back to a CPU path) when there is no
+CUDA device."""
+
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py')] + list(args),
+                          capture_output=True, text=True, cwd=ROOT, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line_with_the_contract_keys():
+    result = _run('--impl', 'reference', '--steps', '2', '--warmup', '3')
+    assert result.returncode == 0, result.stderr[-2000:]
+    lines = [ln for ln in result.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, result.stdout
+    line = json.loads(lines[0])
+    assert line['impl'] == 'reference'
+    assert line['metric'] == 'Acoustic2D Gcell-updates/s' and line['unit'] == 'Gcell-updates/s'
+    assert line['higher_is_better'] is True and line['dtype'] == 'f64'
+    assert line['n_gpus'] == 1 and line['steps'] == 2 and line['warmup'] == 3
+    assert line['value'] > 0 and line['ms_per_step'] > 0
+    assert line['vs_baseline'] is None              # BASELINE.md publishes no number for this metric
+    baseline = line['cpu_baseline']
+    assert baseline['kind'] == 'port' and baseline['cores'] == 1 and baseline['value'] == line['value']
+    assert 'sub-grid' in baseline['sample']
+    e2e = line['e2e']
+    assert e2e['value'] == line['value'] and e2e['h2d_bytes_per_step'] == 0
+    assert e2e['d2h_bytes_per_step'] == 0
+    assert line['gpu_launches'] == 0
+    assert 'workload' in line['config'] and 'model' not in line['config']
+
+
+def test_reference_arm_runs_on_rank_zero_only():
+    env = dict(os.environ, RANK='1', LOCAL_RANK='1', WORLD_SIZE='2')
+    result = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                             '--gpus', '2', '--steps', '2', '--warmup', '3'],
+                            capture_output=True, text=True, cwd=ROOT, timeout=600, env=env)
+    assert result.returncode == 0 and result.stdout.strip() == ''
+
+
+def test_product_arm_fails_loudly_without_a_gpu():
+    import pyfds_b200 as fds
+    from pyfds_b200 import _engine
+    try:
+        if _engine.load_library().fds_device_count() > 0:
+            pytest.skip('a CUDA device is present')
+    except RuntimeError:
+        pass
+    result = _run('--steps', '4', '--warmup', '3', '--size', '256', '--no-cpu-baseline')
+    assert result.returncode != 0
+    assert not any(ln.lstrip().startswith('{') for ln in result.stdout.splitlines()), result.stdout
+    assert fds is not None
