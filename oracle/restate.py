@@ -54,9 +54,19 @@ def dia_matvec(a, x, backend='restated'):
     """``a.dot(x)``: scipy ``dia_matvec`` -- start from zeros, add one diagonal after the other in
     stored order; every ``+=`` is one rounded multiply followed by one rounded add (NumPy never fuses).
     ``backend='scipy'`` runs the same loop in scipy's C++ (the code the reference actually executes,
-    ``pyfds/acoustics.py:117-128``) and is what the CPU baseline times."""
+    ``pyfds/acoustics.py:117-128``) and is what the CPU baseline times; ``backend='c'`` runs the plain C
+    restatement ``oracle/dia_matvec.c`` (a third, independent implementation of the loop)."""
     if backend == 'scipy':
         return a.scipy().dot(x)
+    if backend == 'c':
+        from . import cbuild
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        data = np.ascontiguousarray(a.data, dtype=np.float64)
+        offsets = np.asarray(a.offsets, dtype=np.int64)
+        y = np.empty(a.n)
+        cbuild.library().fds_oracle_dia_matvec(a.n, len(a.offsets), offsets.ctypes.data,
+                                               data.ctypes.data, x.ctypes.data, y.ctypes.data)
+        return y
     n = a.n
     y = np.zeros(n)
     for k, off in enumerate(a.offsets):
