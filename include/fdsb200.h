@@ -168,9 +168,11 @@ int fds_sync(fds_ctx *ctx);
 /* `AcousticFlow2D.apply_flow` (pyfds/acoustic_flow.py:49-57) on the device: after leapfrog step s every
  * owned row n with s % periods[n] == 0 is moved one cell towards +x (row[1:] = row[:-1], row[0] = 0) in
  * all three components. periods[n] = |flow_t_deltas[row0 + n]| (pyfds/acoustic_flow.py:34); 0 and 1
- * both mean "after every step" (numpy evaluates s % 0 to 0). n = rows. The step kernels keep advancing
- * several steps per launch and end a launch where a row has to move. periods == NULL or n == 0 switches
- * the flow off. Acoustic2D only. */
+ * both mean "after every step" (numpy evaluates s % 0 to 0). n = ny: the periods of ALL grid rows --
+ * every slab of a multi-GPU run passes the same array, so that all slabs end their launches at the same
+ * steps (a single-slab context may pass its n = rows periods). The step kernels keep advancing several
+ * steps per launch and end a launch where a row of the grid has to move. periods == NULL or n == 0
+ * switches the flow off. Acoustic2D only. */
 int fds_set_flow(fds_ctx *ctx, const int64_t *periods, int64_t n);
 /* Number of row-shift passes the last fds_step / fds_step_async call launched. */
 int fds_last_flow_shifts(fds_ctx *ctx, int64_t *shifts);

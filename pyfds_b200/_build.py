@@ -39,12 +39,15 @@ def is_stale():
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build_library(force=False, verbose=False, extra_flags=()):
-    """Compile the library if it is missing or older than its sources; returns its path."""
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, extra_flags=(), output=None):
+    """Compile the library if it is missing or older than its sources; returns its path.
+    ``output``: build a tuning variant next to the library instead (always compiled; load it with
+    FDS_LIBRARY_PATH)."""
+    if output is None and not force and not is_stale():
         return LIBRARY
+    target = output or LIBRARY
     cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + \
-        ['-o', LIBRARY] + [os.path.join(CSRC, f) for f in SOURCES] + ['-ldl']
+        ['-o', target] + [os.path.join(CSRC, f) for f in SOURCES] + ['-ldl']
     if verbose:
         print(' '.join(cmd))
     result = subprocess.run(cmd, capture_output=True, text=True)
@@ -52,10 +55,16 @@ def build_library(force=False, verbose=False, extra_flags=()):
         raise RuntimeError('nvcc failed:\n' + result.stdout + result.stderr)
     if verbose and (result.stdout or result.stderr):
         print(result.stdout + result.stderr)
-    return LIBRARY
+    return target
 
 
 if __name__ == '__main__':
+    # python -m pyfds_b200._build [--force] [--ptxas] [--variant NAME -DFLAG=...]
     import sys
-    print(build_library(force='--force' in sys.argv, verbose=True,
-                        extra_flags=['-Xptxas', '-v'] if '--ptxas' in sys.argv else ()))
+    flags = [a for a in sys.argv[1:] if a.startswith('-D')]
+    if '--ptxas' in sys.argv:
+        flags += ['-Xptxas', '-v']
+    out = None
+    if '--variant' in sys.argv:
+        out = os.path.join(_HERE, 'libfdsb200_{}.so'.format(sys.argv[sys.argv.index('--variant') + 1]))
+    print(build_library(force='--force' in sys.argv, verbose=True, extra_flags=flags, output=out))

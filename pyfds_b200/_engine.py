@@ -346,12 +346,14 @@ def halo_rows_for(field, world):
     return 2 if field._baked['lossy'] else 1
 
 
-def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None):
+def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None, lossy=None):
     """Creates (or reuses) the device context of ``field`` and uploads what ``assemble_matrices``
     froze: the material map and the coefficient tables. Returns the ``Engine``.
 
     ``kernel``: 0 automatic, 1 one-step kernel, 2 streaming multi-step kernel (``fds_desc.kernel``);
-    defaults to the field attribute ``device_kernel`` (0 if absent)."""
+    defaults to the field attribute ``device_kernel`` (0 if absent). ``lossy``: True if ANY cell of the
+    grid is lossy -- every slab of a multi-GPU run must pick the same kernel and the same number of
+    steps per launch, whatever materials its own rows hold (default: decided from this window)."""
     if kernel is None:
         kernel = getattr(field, 'device_kernel', 0)
     state = field.__dict__.get('_engine_state')
@@ -369,7 +371,7 @@ def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None):
     ids, values = _bake.material_ids(snapshot, field.num_points, nx, lo, hi)
     tables = field._coefficient_tables(values)
     n_materials = len(next(iter(values.values()))) - 1
-    lossy = bool(tables.get('lossy', False))
+    lossy = bool(tables.get('lossy', False)) or bool(lossy)
     baked['lossy'] = lossy
 
     engine = state.engine
@@ -396,7 +398,8 @@ def upload_run_tables(field, engine, first_step, n_steps):
     lists ``(output, first_slot, n_points)``."""
     nx = engine.nx
     periods = field._device_flow()
-    engine.set_flow(None if periods is None else periods[engine.row0:engine.row0 + engine.rows])
+    # all grid rows: every slab derives the same launch schedule from them (fds_set_flow)
+    engine.set_flow(periods)
     signals = []
     for c, component in enumerate(_components(field)):
         table = _bake.boundary_table(component.boundaries, first_step, n_steps, engine.cell_lo,
@@ -486,7 +489,8 @@ def run(field, n_steps, progress_logger=None, advance=True):
     import time
     clock = time.perf_counter
     t0 = clock()
-    engine = prepare(field)
+    # optional field attribute ``device_index``: CUDA ordinal to run on (default 0)
+    engine = prepare(field, device=int(getattr(field, 'device_index', 0)))
     first_step = field.step
     n_slots, layout = upload_run_tables(field, engine, first_step, n_steps)
     t1 = clock()

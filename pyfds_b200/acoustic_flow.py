@@ -24,21 +24,21 @@ class AcousticFlow2D(acs.Acoustic2D):
     stepped through ``sim_step`` once per step and the override is called on the host arrays."""
 
     def __init__(self, flow, *args, **kwargs):
+        """``flow``: velocity of the medium along x, one number or one per grid row; the remaining
+        arguments are those of ``Field2D`` (``pyfds/acoustic_flow.py:20-43``)."""
         super().__init__(*args, **kwargs)
-
-        if isinstance(flow, (list, np.ndarray)) and len(flow) == self.y.samples:
-            self.flow = np.asarray(flow)
-        elif isinstance(flow, (float, int)):
-            self.flow = np.ones(self.y.samples) * flow
-        else:
+        rows = self.y.samples
+        scalar = isinstance(flow, (float, int))
+        per_row = isinstance(flow, (list, np.ndarray)) and len(flow) == rows
+        if not (scalar or per_row):
             raise ValueError('Flow must either be scalar or a vector with length of y_samples.')
-
-        # period (in steps) after which a row has moved by one cell
+        self.flow = np.asarray(flow) if per_row else np.full(rows, flow, dtype=np.float64)
+        # a row has moved by one cell after this many steps (truncated towards zero, as astype does)
         self.flow_t_deltas = (self.x.increment / self.flow / self.t.increment).astype(int)
-
-        if np.any(self.flow_t_deltas == 1) or np.any(self.flow_t_deltas == 0):
-            wn.warn('Flow velocity may be to high. Consider reducing t_delta.', stacklevel=2)
-            logger.warning('Flow velocity may be to high. Consider reducing t_delta.')
+        if np.isin(self.flow_t_deltas, (0, 1)).any():
+            message = 'Flow velocity may be to high. Consider reducing t_delta.'
+            wn.warn(message, stacklevel=2)
+            logger.warning(message)
 
     def _flow_on_device(self):
         return type(self).apply_flow is AcousticFlow2D.apply_flow
@@ -68,10 +68,18 @@ class AcousticFlow2D(acs.Acoustic2D):
     sim_step._on_device = True
 
     def apply_flow(self):
-        nx = self.x.samples
-        for component in [self.pressure, self.velocity_x, self.velocity_y]:
-            for n, f in enumerate(self.flow_t_deltas):
-                if self.step % f == 0:
-                    component.values[n * nx + 1: (n + 1) * nx] = \
-                        component.values[n * nx: (n + 1) * nx - 1]
-                    component.values[n * nx: n * nx + 1] = 0
+        """Host statement of the shift (``pyfds/acoustic_flow.py:49-57``): every row whose period
+        divides the current step moves one cell towards +x and gets a zero at x = 0. All due rows of a
+        component move in one fancy-indexed assignment (its right-hand side is a copy, so the order
+        of reads and writes is that of the reference's per-row slices)."""
+        periods = np.asarray(self.flow_t_deltas)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            due = np.mod(self.step, periods) == 0       # a period of 0 is due at every step
+        if not due.any():
+            return
+        for component in (self.pressure, self.velocity_x, self.velocity_y):
+            grid = component.values.reshape(self.y.samples, self.x.samples)
+            grid[due, 1:] = grid[due, :-1]
+            grid[due, 0] = 0
+            if not np.shares_memory(grid, component.values):
+                component.values = grid.reshape(-1)

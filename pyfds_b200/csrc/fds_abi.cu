@@ -122,6 +122,10 @@ struct fds_ctx {
         long long row_begin = 0, row_end = 0;
         int k = 0, n_tasks = 0;
         void *tasks = nullptr;
+        // ordering of consecutive sweeps over this table (TaskSync in fds_stream2d.cuh)
+        int *dep_ptr = nullptr, *dep_idx = nullptr;
+        unsigned *done = nullptr;
+        int n_edge[2] = {0, 0};   // tasks that own rows of the lower / upper edge band
     };
     std::vector<StreamPlan> plans;
     std::vector<int> strip_nonplain;   // [strip][block of kCensusBlockRows rows]
@@ -154,12 +158,19 @@ struct fds_ctx {
 
     // peer-memory halo path of the streaming kernel (multi-GPU): neighbours' buffers opened over IPC
     unsigned *flags = nullptr;           // [0],[1]: halo-arrival flags written by the lower / upper
-                                         // neighbour; [2],[3]: counters of finished band tasks
+                                         // neighbour; [2]: blocks of halo_push_kernel that are done;
+                                         // [4..7]: finished edge tasks by side and sweep parity;
+                                         // [8]: a device-side wait gave up
     void *peer_base[2][2][3] = {};       // [side][buffer][component] base pointers (IPC mappings)
     unsigned *peer_flags[2] = {nullptr, nullptr};
     long long peer_rows[2] = {0, 0};
     bool peer_open[2] = {false, false};
     unsigned launch_seq = 0;
+    // task table of the streaming launch that was enqueued last on `stream`, nothing else since
+    // (nullptr otherwise): the next launch over the same table may overlap it
+    const void *chain_tasks = nullptr;
+    bool overlap = true;       // programmatic dependent launches between sweeps (FDS_NO_OVERLAP=1: off)
+    bool halo_in_kernel = true;   // halo rows pushed / awaited inside the streaming kernels
     bool use_stream2d = false; // streaming multi-step kernel selected
     bool use_tile2d = false;   // shared-memory tile kernel selected (one step per launch)
     bool use_streamv = false;  // streaming kernel of the viscous / axisymmetric acoustic models
@@ -396,12 +407,15 @@ StepTables make_tables(fds_ctx *ctx) {
 // ---- kernel dispatch ----------------------------------------------------------------------------
 
 constexpr int kCounterPool = 4096;
+constexpr int kFlagWords = 16;      // fds_ctx::flags
+constexpr int kFlagEdgeDone = 4, kFlagError = 8;
 
 int *next_counter(fds_ctx *ctx) {
     if (ctx->next_counter == kCounterPool) {
         if (cudaMemsetAsync(ctx->task_counters, 0, sizeof(int) * kCounterPool, ctx->stream) !=
             cudaSuccess)
             return nullptr;
+        ctx->chain_tasks = nullptr;   // (the counters of a sweep that may still run must not be cleared)
         ctx->next_counter = 0;
     }
     return ctx->task_counters + ctx->next_counter++;
@@ -570,10 +584,15 @@ int strip_census(fds_ctx *ctx, int n_strips) {
 void invalidate_plans(fds_ctx *ctx) {
     if (!ctx->plans.empty()) {
         cudaStreamSynchronize(ctx->stream);
-        for (auto &p : ctx->plans)
+        for (auto &p : ctx->plans) {
             if (p.tasks) cudaFree(p.tasks);
+            if (p.dep_ptr) cudaFree(p.dep_ptr);
+            if (p.dep_idx) cudaFree(p.dep_idx);
+            if (p.done) cudaFree(p.done);
+        }
         ctx->plans.clear();
     }
+    ctx->chain_tasks = nullptr;
     ctx->census_valid = false;
 }
 
@@ -706,15 +725,75 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
             items.push_back({s, ys, ys + h, (double)h + overhead});
         }
     }
+    // Multi-GPU, whole slab: tasks that read halo rows wait for the neighbour's flag inside the kernel,
+    // tasks that own rows of an edge band push them to the neighbour when they finish (TaskSync). The
+    // edge tasks go first: their rows travel while the interior is computed, and by the time the
+    // neighbour's next sweep asks for them they have long arrived.
+    const bool whole_slab = plan.row_begin == 0 && plan.row_end == ctx->d.rows;
+    const bool has_side[2] = {ctx->world > 1 && ctx->rank > 0, ctx->world > 1 && ctx->rank < ctx->world - 1};
+    const long long band = ctx->d.halo_rows;
+    auto flags_of = [&](const Item &it) {
+        int f = 0;
+        if (!whole_slab) return f;
+        if (has_side[0]) {
+            if (it.ys - lag_rows < 0) f |= kTaskWaitLo;
+            if (it.ys < band) f |= kTaskPushLo;
+        }
+        if (has_side[1]) {
+            if (it.ye + lag_rows > rows) f |= kTaskWaitHi;
+            if (it.ye > rows - band) f |= kTaskPushHi;
+        }
+        return f;
+    };
+    if (whole_slab && (has_side[0] || has_side[1]))
+        std::stable_partition(items.begin(), items.end(),
+                              [&](const Item &it) { return flags_of(it) != 0; });
     std::vector<int4> tasks(items.size());
-    for (size_t i = 0; i < items.size(); ++i)
-        tasks[i] = make_int4(items[i].strip, (int)items[i].ys, (int)items[i].ye, 0);
+    plan.n_edge[0] = plan.n_edge[1] = 0;
+    for (size_t i = 0; i < items.size(); ++i) {
+        const int f = flags_of(items[i]);
+        if (f & kTaskPushLo) ++plan.n_edge[0];
+        if (f & kTaskPushHi) ++plan.n_edge[1];
+        tasks[i] = make_int4(items[i].strip, (int)items[i].ys, (int)items[i].ye, f);
+    }
+    // Dependency lists for overlapped sweeps: the tasks (of the same table, one sweep earlier) whose
+    // output a task reads -- strips s-1, s, s+1 (cyclic: the flat index wraps from one row into the
+    // next) and rows within `lag_rows` (+1 for that wrap) of its own. The same tasks are the ones that
+    // read what it overwrites, so one wait covers both hazards.
+    std::vector<int> dep_ptr(items.size() + 1, 0), dep_idx;
+    {
+        std::vector<std::vector<int>> by_strip((size_t)n_strips);
+        for (size_t i = 0; i < items.size(); ++i) by_strip[(size_t)items[i].strip].push_back((int)i);
+        const long long margin = lag_rows + 1;
+        for (size_t i = 0; i < items.size(); ++i) {
+            const Item &t = items[i];
+            int neighbours[3] = {(t.strip + n_strips - 1) % n_strips, t.strip, (t.strip + 1) % n_strips};
+            const int n_nb = n_strips >= 3 ? 3 : n_strips;   // fewer than 3 strips: no duplicates
+            for (int j = 0; j < n_nb; ++j) {
+                const int sj = n_strips >= 3 ? neighbours[j] : j;
+                for (int other : by_strip[(size_t)sj]) {
+                    const Item &o = items[(size_t)other];
+                    if (o.ys < t.ye + margin && o.ye > t.ys - margin) dep_idx.push_back(other);
+                }
+            }
+            dep_ptr[i + 1] = (int)dep_idx.size();
+        }
+    }
     void *dev = nullptr;
     if (dev_alloc(ctx, &dev, tasks.size() * sizeof(int4), false)) return 1;
+    plan.tasks = dev;
+    if (dev_alloc(ctx, (void **)&plan.dep_ptr, dep_ptr.size() * sizeof(int), false)) return 1;
+    if (dev_alloc(ctx, (void **)&plan.dep_idx, dep_idx.size() * sizeof(int), false)) return 1;
+    if (dev_alloc(ctx, (void **)&plan.done, tasks.size() * sizeof(unsigned), true)) return 1;
     FDS_CUDA(ctx, cudaMemcpyAsync(dev, tasks.data(), tasks.size() * sizeof(int4),
                                   cudaMemcpyHostToDevice, ctx->stream));
-    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // `tasks` is pageable host memory
-    plan.tasks = dev;
+    FDS_CUDA(ctx, cudaMemcpyAsync(plan.dep_ptr, dep_ptr.data(), dep_ptr.size() * sizeof(int),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    if (!dep_idx.empty())
+        FDS_CUDA(ctx, cudaMemcpyAsync(plan.dep_idx, dep_idx.data(), dep_idx.size() * sizeof(int),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the vectors are pageable host memory
+    ctx->chain_tasks = nullptr;
     plan.n_tasks = (int)tasks.size();
     plan.k = k;
     if (getenv("FDS_DEBUG_PLAN")) {
@@ -728,6 +807,25 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
     return 0;
 }
 
+// Launches a streaming kernel; `overlap`: with programmatic stream serialisation, i.e. its CTAs may
+// become resident while the previous kernel on the stream (the previous sweep over the same task
+// table) is still running -- the tasks order themselves (TaskSync).
+template <typename Kernel, typename Args>
+int launch_sweep(fds_ctx *ctx, Kernel kernel, long long ctas, int smem, const Args &args, bool overlap) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(kStreamWarps * 32);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap ? 1 : 0;
+    FDS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, args));
+    return 0;
+}
+
 template <int K, bool THERMAL, bool STATS, bool AXI>
 int launch_stream2d_as(fds_ctx *ctx, const Stream2DArgs &a) {
     auto kernel = stream2d_kernel<K, THERMAL, STATS, AXI>;
@@ -737,12 +835,10 @@ int launch_stream2d_as(fds_ctx *ctx, const Stream2DArgs &a) {
         FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    // persistent CTAs (4 per SM) pull tasks from a counter
+    // persistent CTAs pull tasks from a counter
     const long long want = (a.n_tasks + kStreamWarps - 1) / kStreamWarps;
     const long long ctas = std::min<long long>(want, 148 * kS2CtasPerSm);
-    kernel<<<(unsigned)ctas, kStreamWarps * 32, smem, ctx->stream>>>(a);
-    FDS_CUDA(ctx, cudaGetLastError());
-    return 0;
+    return launch_sweep(ctx, kernel, ctas, smem, a, a.sync.wait_deps != 0);
 }
 
 template <int K, bool THERMAL>
@@ -769,9 +865,7 @@ int launch_streamv(fds_ctx *ctx, const StreamVArgs &av) {
     }
     const long long want = (av.base.n_tasks + kStreamWarps - 1) / kStreamWarps;
     const long long ctas = std::min<long long>(want, 148 * CTAS);
-    kernel<<<(unsigned)ctas, kStreamWarps * 32, smem, ctx->stream>>>(av);
-    FDS_CUDA(ctx, cudaGetLastError());
-    return 0;
+    return launch_sweep(ctx, kernel, ctas, smem, av, av.base.sync.wait_deps != 0);
 }
 
 int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
@@ -798,6 +892,14 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     a.stats = ctx->stream_stats;
     a.task_counter = next_counter(ctx);
     if (!a.task_counter) return fail(ctx, "stream2d: counter reset failed");
+    // ordering against the previous sweep: a.sync.seq and the halo fields were set by the caller
+    a.sync.dep_ptr = plan->dep_ptr;
+    a.sync.dep_idx = plan->dep_idx;
+    a.sync.done = plan->done;
+    a.sync.wait_deps = ctx->overlap && ctx->chain_tasks == plan->tasks;
+    a.sync.n_edge_tasks[0] = plan->n_edge[0];
+    a.sync.n_edge_tasks[1] = plan->n_edge[1];
+    ctx->chain_tasks = plan->tasks;
     a.map = ctx->map + ctx->pad + ctx->halo;
     a.tab = ctx->tab;
     a.tables = ctx->d_tables;
@@ -963,7 +1065,6 @@ bool peers_ready(const fds_ctx *ctx) {
 // Before launch L: the neighbours' rows of launch L-1 must have landed in my halo rows. The first
 // launch of a call is covered by the host-driven exchange at the start of run_steps.
 int peer_wait(fds_ctx *ctx, bool wait) {
-    ++ctx->launch_seq;
     if (!wait) return 0;
     const unsigned *lo = ctx->rank > 0 ? ctx->flags + 0 : nullptr;
     const unsigned *hi = ctx->rank < ctx->world - 1 ? ctx->flags + 1 : nullptr;
@@ -1008,7 +1109,47 @@ int peer_push(fds_ctx *ctx, int which) {
     return 0;
 }
 
+// The same exchange from inside the streaming kernels (TaskSync in fds_stream2d.cuh): tasks that read
+// halo rows wait for flags >= wait_seq (0: nothing to wait for), tasks that own edge rows copy them into
+// the neighbours' buffer `which` and the last one releases the neighbours' flags with this sweep's number.
+void fill_halo_sync(fds_ctx *ctx, TaskSync &y, int which, unsigned wait_seq, bool push) {
+    const long long nx = ctx->d.nx, h = ctx->d.halo_rows;
+    const long long off = ctx->pad + ctx->halo;
+    y.halo_wait_seq = wait_seq;
+    y.halo_push = push ? 1 : 0;
+    y.ncomp = ctx->thermal ? 1 : 3;
+    y.halo_rows = (int)h;
+    y.rows = ctx->d.rows;
+    y.edge_done = ctx->flags + kFlagEdgeDone;
+    for (int side = 0; side < 2; ++side) {
+        const bool has = side == 0 ? ctx->rank > 0 : ctx->rank < ctx->world - 1;
+        y.flag_in[side] = has ? ctx->flags + side : nullptr;
+        y.flag_out[side] = has ? ctx->peer_flags[side] + (1 - side) : nullptr;
+        for (int c = 0; c < 3; ++c) {
+            y.peer_dst[side][c] = nullptr;
+            if (!has || c >= y.ncomp) continue;
+            double *theirs = (double *)ctx->peer_base[side][which][c] + off;
+            // my bottom rows -> the lower neighbour's upper halo; my top rows -> the upper one's lower halo
+            y.peer_dst[side][c] = side == 0 ? theirs + ctx->peer_rows[0] * nx : theirs - h * nx;
+        }
+    }
+}
+
 int exchange_halos(fds_ctx *ctx, int which);
+
+// After a synchronisation: did a device-side wait (neighbour flag, task of the previous sweep) give up?
+int check_device_waits(fds_ctx *ctx) {
+    unsigned err = 0;
+    FDS_CUDA(ctx, cudaMemcpyAsync(&err, ctx->flags + kFlagError, sizeof(err), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (err) {
+        cudaMemsetAsync(ctx->flags + kFlagError, 0, sizeof(unsigned), ctx->stream);
+        return fail(ctx, "a device-side wait timed out (neighbour slab or previous sweep never "
+                         "arrived): results of this call are invalid");
+    }
+    return 0;
+}
 
 // ---- medium flow ------------------------------------------------------------------------------------
 // True if some row moves after leapfrog step `step` (pyfds/acoustic_flow.py:54: step % period == 0).
@@ -1083,11 +1224,13 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
         FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
     }
     FDS_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    ctx->chain_tasks = nullptr;
     long long done = 0;
     long long chunk = 0;
     while (done < n_steps) {
         const long long chunk_steps = std::min(half, n_steps - done);
         const int h = (int)(chunk & 1);
+        ctx->chain_tasks = nullptr;   // events sit between the chunks
         if (drain && ctx->n_slots > 0 && chunk >= 2)  // the half must have been drained
             FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_drained[h], 0));
         long long in_chunk = 0;
@@ -1145,13 +1288,31 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 const bool shift = ctx->flow && flow_due(ctx, last);
                 // thermal fluxes are derived data: stored only by the launch that ends the call
                 a.write_vector = (s + k == n_steps);
-                if (multi && peers_ready(ctx)) {
-                    // one launch for the whole slab; halo rows travel over NVLink peer memory
+                a.sync.seq = ++ctx->launch_seq;
+                a.sync.error = ctx->flags + kFlagError;
+                if (multi && peers_ready(ctx) && ctx->halo_in_kernel) {
+                    // One launch for the whole slab; halo rows travel over NVLink peer memory, pushed
+                    // and awaited by the tasks themselves. Rows of a flowing medium move after the
+                    // sweep and before they travel: that launch pushes with a kernel of its own.
+                    const bool first = !(in_chunk > 0 || chunk > 0);
+                    fill_halo_sync(ctx, a.sync, ctx->cur ^ 1, first ? 0u : a.sync.seq - 1u, !shift);
+                    a.row_begin = 0; a.row_end = rows;
+                    if (dispatch_stream2d(ctx, a, k)) return 1;
+                    if (shift) {
+                        if (launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
+                        if (peer_push(ctx, ctx->cur ^ 1)) return 1;
+                        ctx->chain_tasks = nullptr;
+                    }
+                    ctx->last_launches += 1;
+                } else if (multi && peers_ready(ctx)) {
+                    // the same with a waiting and a pushing kernel either side of the sweep
                     if (peer_wait(ctx, in_chunk > 0 || chunk > 0)) return 1;
+                    ctx->chain_tasks = nullptr;
                     a.row_begin = 0; a.row_end = rows;
                     if (dispatch_stream2d(ctx, a, k)) return 1;
                     if (shift && launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
                     if (peer_push(ctx, ctx->cur ^ 1)) return 1;
+                    ctx->chain_tasks = nullptr;
                     ctx->last_launches += 1;
                 } else if (multi && shift) {
                     // the edge rows move before they travel: no overlap for this launch
@@ -1163,6 +1324,7 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                     if (exchange_halos(ctx, ctx->cur ^ 1)) return 1;
                     FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
                     FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+                    ctx->chain_tasks = nullptr;
                     ctx->last_launches += 1;
                 } else if (multi) {
                     // the k outermost rows of either side travel while the interior is computed
@@ -1178,11 +1340,15 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                     a.row_begin = band; a.row_end = std::max(band, rows - band);
                     if (dispatch_stream2d(ctx, a, k)) return 1;
                     FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+                    ctx->chain_tasks = nullptr;
                     ctx->last_launches += 3;
                 } else {
                     a.row_begin = 0; a.row_end = rows;
                     if (dispatch_stream2d(ctx, a, k)) return 1;
-                    if (shift && launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
+                    if (shift) {
+                        if (launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
+                        ctx->chain_tasks = nullptr;
+                    }
                     ctx->last_launches += 1;
                 }
                 advanced = k;
@@ -1211,6 +1377,7 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 const long long last = first_step + s;
                 const bool shift = ctx->flow && flow_due(ctx, last);
                 if (ctx->comm && ctx->world > 1 && peers_ready(ctx)) {
+                    ++ctx->launch_seq;
                     if (peer_wait(ctx, in_chunk > 0 || chunk > 0)) return 1;
                     a.row_begin = 0; a.row_end = rows;
                     if (dispatch_step2d(ctx, a, t)) return 1;
@@ -1409,6 +1576,8 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
     if (const char *env = getenv("FDS_TILE_ROWS")) ctx->tile_rows = atoi(env);
     if (const char *env = getenv("FDS_CHUNK_ROWS")) ctx->chunk_rows = atoi(env);
     if (const char *env = getenv("FDS_HALO_1D")) ctx->halo_1d = std::max(2, atoi(env) / 2 * 2);
+    if (getenv("FDS_NO_OVERLAP")) ctx->overlap = false;
+    if (getenv("FDS_HALO_KERNELS")) ctx->halo_in_kernel = false;
     if (const char *env = getenv("FDS_MAX_K"))
         ctx->max_k = std::max(1, std::min(kMaxStreamSteps, atoi(env)));
     // >= 9 rows + 4096 cells of padding, rounded so that the origin stays 512-byte aligned
@@ -1452,7 +1621,7 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
                           sizeof(double) * FDS_CTAB_COUNT * (d.n_materials + 1) * d.nx, true));
         FDS_TRY(dev_alloc(ctx, (void **)&ctx->cvec, sizeof(double) * FDS_CVEC_COUNT * d.nx, true));
     }
-    FDS_TRY(dev_alloc(ctx, (void **)&ctx->flags, 4 * sizeof(unsigned), true));
+    FDS_TRY(dev_alloc(ctx, (void **)&ctx->flags, kFlagWords * sizeof(unsigned), true));
     FDS_TRY(dev_alloc(ctx, (void **)&ctx->d_tables, sizeof(StepTables), true));
     FDS_TRY(dev_alloc(ctx, (void **)&ctx->task_counters, sizeof(int) * kCounterPool, true));
     if (getenv("FDS_STREAM_STATS"))
@@ -1766,7 +1935,7 @@ int fds_step(fds_ctx *ctx, int64_t first_step, int64_t n_steps, double *probes_o
     if (ctx->n_slots > 0 && n_steps > 0 && !probes_out)
         return fail(ctx, "fds_step: probes are configured but probes_out is NULL");
     if (run_steps(ctx, first_step, n_steps, true)) return 1;
-    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (check_device_waits(ctx)) return 1;
     FDS_CUDA(ctx, cudaStreamSynchronize(ctx->drain));
     FDS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
     if (ctx->n_slots > 0 && n_steps > 0) {
@@ -1799,7 +1968,7 @@ int fds_step_async(fds_ctx *ctx, int64_t first_step, int64_t n_steps) {
 int fds_sync(fds_ctx *ctx) {
     if (!ctx) return fail(ctx, "fds_sync: null context");
     FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
-    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (check_device_waits(ctx)) return 1;
     FDS_CUDA(ctx, cudaStreamSynchronize(ctx->drain));
     FDS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
     return 0;
@@ -1815,18 +1984,22 @@ int fds_set_flow(fds_ctx *ctx, const int64_t *periods, int64_t n) {
     }
     if (ctx->d.model != FDS_ACOUSTIC2D)
         return fail(ctx, "fds_set_flow: medium flow is defined for Acoustic2D only");
-    if (n != ctx->d.rows) return fail(ctx, "fds_set_flow: expected one period per owned row");
-    std::vector<long long> unique;
-    for (int64_t k = 0; k < n; ++k) {
+    // n = ny: the periods of ALL grid rows (every slab of a multi-GPU run passes the same array); the
+    // launches of all slabs must end at the same steps, so the schedule (`flow_unique`: where any row
+    // of the GRID is due) comes from all of them while the shift kernel only sees the owned rows.
+    // n = rows: the owned rows only (single slab).
+    if (n != ctx->d.rows && n != ctx->d.ny)
+        return fail(ctx, "fds_set_flow: expected one period per grid row (or per owned row)");
+    if (n != ctx->d.ny && ctx->d.rows != ctx->d.ny)
+        return fail(ctx, "fds_set_flow: a slab of a larger grid needs the periods of all grid rows");
+    for (int64_t k = 0; k < n; ++k)
         if (periods[k] < 0) return fail(ctx, "fds_set_flow: periods must not be negative");
-        bool seen = false;
-        for (long long u : unique) seen = seen || u == periods[k];
-        if (!seen) unique.push_back(periods[k]);
-        if (unique.size() > 4096)
-            return fail(ctx, "fds_set_flow: more than 4096 distinct shift periods");
-    }
+    std::vector<long long> unique(periods, periods + n);
+    std::sort(unique.begin(), unique.end());
+    unique.erase(std::unique(unique.begin(), unique.end()), unique.end());
     static_assert(sizeof(long long) == sizeof(int64_t), "period width");
-    if (dev_upload(ctx, ctx->flow_periods, periods, (size_t)n * 8)) return 1;
+    const int64_t *owned = n == ctx->d.ny ? periods + ctx->d.row0 : periods;
+    if (dev_upload(ctx, ctx->flow_periods, owned, (size_t)ctx->d.rows * 8)) return 1;
     ctx->flow_unique.swap(unique);
     ctx->flow = true;
     return 0;

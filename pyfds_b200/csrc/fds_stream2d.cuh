@@ -42,8 +42,142 @@
 
 namespace fds {
 
-constexpr int kStreamWarps = 4;      // warps per CTA
+#ifndef FDS_STREAM_WARPS
+#define FDS_STREAM_WARPS 4
+#endif
+constexpr int kStreamWarps = FDS_STREAM_WARPS;   // warps per CTA
 constexpr int kMaxStreamSteps = 4;   // K
+
+// ---- ordering between tasks: overlapped sweeps and the in-kernel halo exchange ------------------------
+// A launch (one "sweep" of K steps over the slab) no longer has to wait for the whole previous sweep:
+//   * launched with programmatic stream serialisation, its CTAs become resident as soon as CTAs of the
+//     previous sweep exit, and every task waits only for the tasks of the previous sweep whose output it
+//     reads (and which read what it is about to overwrite -- the same set): `dep_idx[dep_ptr[t] ..
+//     dep_ptr[t+1])`, host-built from the task table, checked against `done[]`, which every task
+//     releases with the sweep number when its rows are stored. The tail of one sweep (the slowest SMs,
+//     the last tasks) is filled with the head of the next one.
+//   * multi-GPU: tasks that read halo rows wait for the flag the neighbour slab releases when its edge
+//     rows of the previous sweep have landed in this slab's halo rows; tasks that own edge rows copy
+//     them straight into the neighbour's halo rows (peer memory over NVLink) when they finish, and the
+//     last one of a side releases the neighbour's flag. Edge tasks are handed out first, so the rows
+//     travel while the interior of the slab is still being computed.
+// Task flags (int4::w of the task table):
+constexpr int kTaskWaitLo = 1, kTaskWaitHi = 2;    // reads halo rows of the lower / upper neighbour
+constexpr int kTaskPushLo = 4, kTaskPushHi = 8;    // owns rows the lower / upper neighbour needs
+
+struct TaskSync {
+    unsigned seq;               // number of this sweep (> 0, counted per context)
+    int wait_deps;              // 1: the previous sweep used this task table and may still be running
+    const int *dep_ptr;         // CSR over the tasks of the table; nullptr: no dependency lists
+    const int *dep_idx;
+    unsigned *done;             // [n_tasks] last sweep each task finished; nullptr: not recorded
+    // in-kernel halo exchange (all null / 0 on a single GPU)
+    unsigned halo_wait_seq;     // flags must have reached this sweep number (0: nothing to wait for)
+    int halo_push;              // 1: edge tasks push their rows and release the neighbours' flags
+    const unsigned *flag_in[2]; // this slab's flags, written by the lower / upper neighbour
+    unsigned *flag_out[2];      // the neighbours' flags (peer memory)
+    double *peer_dst[2][3];     // [side][component]: where row 0 of the side's edge band goes
+    unsigned *edge_done;        // [side][sweep parity] counters of finished edge tasks
+    unsigned *error;            // set to 1 when a wait gave up
+    int n_edge_tasks[2];
+    int halo_rows;              // rows per edge band
+    int ncomp;                  // components that travel (thermal: 1)
+    long long rows;             // owned rows of the slab
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spins until *flag >= want (wrapping comparison); gives up after 20 s and raises *error.
+template <bool SYSTEM>
+__device__ __noinline__ void spin_until(const unsigned *flag, unsigned want, unsigned *error) {
+    unsigned seen;
+    unsigned long long t0 = 0;
+    for (unsigned spins = 0;; ++spins) {
+        if (SYSTEM)
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        else
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if ((int)(seen - want) >= 0) return;
+        if (spins > 64) __nanosleep(64);
+        if ((spins & 1023u) == 1023u) {
+            const unsigned long long now = global_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) {
+                if (error) atomicExch(error, 1u);
+                return;
+            }
+        }
+    }
+}
+
+// Before a task touches memory: wait for what it reads to be there and for what it overwrites to have
+// been read. Called by the whole warp; what follows (bulk loads issued by lane 0 through the async
+// proxy) is ordered behind the acquires by the proxy fence.
+__device__ __forceinline__ void task_acquire(const TaskSync &y, int task, int flags, int lane) {
+    bool waited = false;
+    if (y.halo_wait_seq && (flags & (kTaskWaitLo | kTaskWaitHi))) {
+        if (lane < 2 && (flags & (kTaskWaitLo << lane)) && y.flag_in[lane])
+            spin_until<true>(y.flag_in[lane], y.halo_wait_seq, y.error);
+        waited = true;
+    }
+    if (y.wait_deps && y.dep_ptr) {
+        const int end = __ldg(y.dep_ptr + task + 1);
+        for (int k = __ldg(y.dep_ptr + task) + lane; k < end; k += 32)
+            spin_until<false>(y.done + __ldg(y.dep_idx + k), y.seq - 1u, y.error);
+        waited = true;
+    }
+    if (waited) {
+        __syncwarp();
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+}
+
+// After the last row of a task has been stored (by all lanes of the warp).
+__device__ __noinline__ void task_release(const TaskSync &y, double *const *out, long long nx,
+                                          int task, int strip_first_col, int ys, int ye, int flags,
+                                          int lane) {
+    __syncwarp();
+    if (y.halo_push && (flags & (kTaskPushLo | kTaskPushHi))) {
+        // 56 owned cells of the strip = 28 16-byte words per row and component
+        const long long x = strip_first_col + 2 * lane;
+        const bool mine = lane < 28 && x < nx;
+        for (int side = 0; side < 2; ++side) {
+            if (!(flags & (kTaskPushLo << side)) || !y.flag_out[side]) continue;
+            const long long band0 = side ? y.rows - y.halo_rows : 0;   // first row of the edge band
+            const long long lo = ys > band0 ? ys : band0;
+            const long long hi = ye < band0 + y.halo_rows ? ye : band0 + y.halo_rows;
+            if (mine)
+                for (long long row = lo; row < hi; ++row)
+                    for (int c = 0; c < y.ncomp; ++c) {
+                        const double2 v =
+                            __ldcg(reinterpret_cast<const double2 *>(out[c] + row * nx + x));
+                        *reinterpret_cast<double2 *>(y.peer_dst[side][c] + (row - band0) * nx + x) = v;
+                    }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_system();
+                unsigned *counter = y.edge_done + 2 * side + (y.seq & 1u);
+                const unsigned before = atomicAdd(counter, 1u);
+                if (before == (unsigned)y.n_edge_tasks[side] - 1u) {
+                    atomicExch(counter, 0u);
+                    __threadfence_system();
+                    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(y.flag_out[side]),
+                                 "r"(y.seq)
+                                 : "memory");
+                }
+            }
+        }
+    }
+    if (y.done && lane == 0) {
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(y.done + task), "r"(y.seq)
+                     : "memory");
+    }
+}
 
 struct Stream2DArgs {
     const double *in[3];
@@ -70,6 +204,7 @@ struct Stream2DArgs {
     const double *ctab;    // [FDS_CTAB_COUNT][n_mat1][nx]
     const double *cvec;    // [FDS_CVEC_COUNT][nx]
     int n_mat1;
+    TaskSync sync;         // ordering between the tasks of consecutive sweeps and of neighbour slabs
 };
 
 __device__ __forceinline__ unsigned smem_addr(const void *p) {
@@ -130,7 +265,7 @@ constexpr int kS2StripHalo = 4;                                    // cells; K <
 constexpr int kS2HaloLanes = kS2StripHalo / kS2LaneCells;          // 2
 constexpr int kS2StripStride = kS2StripCells - 2 * kS2StripHalo;   // 56 owned cells per strip
 #ifndef FDS_S2_CTAS
-#define FDS_S2_CTAS 3
+#define FDS_S2_CTAS (12 / FDS_STREAM_WARPS)   // 12 warps per SM at 168 registers
 #endif
 #ifndef FDS_S2_RING
 #define FDS_S2_RING 6
@@ -141,7 +276,8 @@ constexpr int kS2MapWindowBytes = kS2StripCells * 2 + 16;
 constexpr int kS2FieldBytes = kS2StripCells * 8;                   // 512
 constexpr int kS2SlotBytes = 3 * kS2FieldBytes + kS2MapWindowBytes + 16;
 constexpr int kS2ScratchBytes = 32 * 2 * kS2LaneCells * 8;         // slow path: 2 components per lane
-constexpr int kS2WarpRingBytes = kS2RingDepth * kS2SlotBytes + kS2ScratchBytes + 64;   // + mbarriers
+constexpr int kS2WarpRingBytes = kS2RingDepth * kS2SlotBytes + kS2ScratchBytes + 64;   // + mbarriers, task stash
+static_assert(8 * (kS2RingDepth / 2) + 8 <= 64, "mbarriers and the task stash share 64 bytes");
 static_assert(kS2SlotBytes % 16 == 0, "bulk copies need 16-byte aligned slots");
 static_assert(kS2LaneCells == 2, "the 32-bit lane map word and the double2 row accesses assume 2");
 
@@ -325,6 +461,9 @@ stream2d_kernel(Stream2DArgs a) {
     for (int k = threadIdx.x; k < 4 * kMaxMaterials; k += blockDim.x) (&tabs[0][0])[k] = a.tab[k];
     stage_class_tables<K>(a, cls_alpha, cls_value);
     __syncthreads();
+    // the next sweep may move in as soon as CTAs of this one leave (its tasks order themselves
+    // against ours through a.sync); a no-op unless it was launched with programmatic serialisation
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nx = a.nx;
@@ -333,6 +472,8 @@ stream2d_kernel(Stream2DArgs a) {
         reinterpret_cast<double *>(ring + kS2RingDepth * kS2SlotBytes) + lane * 2 * C;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(
         ring + kS2RingDepth * kS2SlotBytes + kS2ScratchBytes);
+    // task number and flags wait here for the end of the task instead of occupying registers
+    int *stash = reinterpret_cast<int *>(bars + kS2RingDepth / 2);
     // rows travel in pairs: ring slots 2j and 2j+1 share mbarrier j (one wait, one refill per pair)
     static_assert(kS2RingDepth % 2 == 0, "the ring holds whole row pairs");
     unsigned phase_bits = 0;   // parity of every pair barrier (the barriers live across tasks)
@@ -353,6 +494,11 @@ stream2d_kernel(Stream2DArgs a) {
         const int ys = tk.y, ye = tk.z;
         const long long xs = (long long)tk.x * kS2StripStride - kS2StripHalo;   // column of lane 0
         const int r0 = ys - K, r1 = ye + K;                                     // rows streamed in
+        if (lane == 0) {
+            stash[0] = task;
+            stash[1] = tk.w;
+        }
+        task_acquire(a.sync, task, tk.w, lane);
 
         // rows r, r+1 (r - r0 even) into ring slots `slot`, `slot` + 1 (slot even), one barrier
         auto issue_pair = [&](int r, int slot) {
@@ -776,6 +922,7 @@ stream2d_kernel(Stream2DArgs a) {
             m0 = m1;
             m1 = fetch();
         }
+        task_release(a.sync, a.out, nx, stash[0], (int)xs + kS2StripHalo, ys, ye, stash[1], lane);
     }
 }
 

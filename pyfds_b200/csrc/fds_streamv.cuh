@@ -41,7 +41,7 @@ struct StreamVArgs {
     int n_mat1;
 };
 
-constexpr int kSVCtasPerSm = 3;             // resident CTAs per SM (register budget: 168)
+constexpr int kSVCtasPerSm = 12 / kStreamWarps;             // resident CTAs per SM (register budget: 168)
 constexpr int kMaxStreamVSteps = 2;         // K: bounded by the strip halo (see above)
 
 // Coefficients of this lane's cells on steady rows (the same for rows q, q-1, q-2: steady rows repeat
@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
         (&tabs[0][0])[k] = a.tab[k];
     stage_class_tables<K>(a, cls_alpha, cls_value);
     __syncthreads();
+    // sweep overlap: see TaskSync in fds_stream2d.cuh
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nx = a.nx;
@@ -162,6 +164,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
         reinterpret_cast<double *>(ring + kS2RingDepth * kS2SlotBytes) + lane * 2 * C;
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(
         ring + kS2RingDepth * kS2SlotBytes + kS2ScratchBytes);
+    int *stash = reinterpret_cast<int *>(bars + kS2RingDepth / 2);
     unsigned phase_bits = 0;   // parity of every pair barrier (the barriers live across tasks)
 
     if (lane == 0) {
@@ -179,6 +182,11 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
         const int ys = tk.y, ye = tk.z;
         const long long xs = (long long)tk.x * kS2StripStride - kS2StripHalo;   // column of lane 0
         const int r0 = ys - kLag, r1 = ye + kLag;                               // rows streamed in
+        if (lane == 0) {
+            stash[0] = task;
+            stash[1] = tk.w;
+        }
+        task_acquire(a.sync, task, tk.w, lane);
 
         // rows r, r+1 (r - r0 even) into ring slots `slot`, `slot` + 1 (slot even), one barrier
         auto issue_pair = [&](int r, int slot) {
@@ -623,6 +631,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
             m0 = m1;
             m1 = fetch();
         }
+        task_release(a.sync, a.out, nx, stash[0], (int)xs + kS2StripHalo, ys, ye, stash[1], lane);
     }
 }
 

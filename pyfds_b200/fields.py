@@ -139,9 +139,11 @@ class Field:
     def reset(self):
         """Zero every component and the step counter; boundaries, materials, outputs and recorded
         ``signals`` stay (``pyfds/fields.py:121-127``)."""
-        for name in dir(self):
-            if isinstance(getattr(self, name), FieldComponent):
-                getattr(self, name).values = np.zeros_like(getattr(self, name).values)
+        # instance attributes only: the lazy scipy operators of the device models are properties of
+        # the class, and touching them here would assemble (and cache) every one of them
+        for component in list(vars(self).values()):
+            if isinstance(component, FieldComponent):
+                component.values = np.zeros_like(component.values)
         self.step = 0
 
     # ---- the device handle must never be pickled or forked (gfx.py:72-86 pickles the Field) ------
@@ -149,6 +151,8 @@ class Field:
     def __getstate__(self):
         state = dict(self.__dict__)
         state.pop('_engine_state', None)
+        if '_operators' in state:       # lazy scipy views: rebuilt on demand, never shipped
+            state['_operators'] = {}
         return state
 
 

@@ -106,8 +106,11 @@ class SlabRun:
         if world > 1 and self.rows < self.halo_rows:
             raise ValueError('Slabs of {} rows are thinner than the {} halo rows needed.'.format(
                 self.rows, self.halo_rows))
+        # decided on the whole grid: a lossy material confined to one slab must not make the slabs
+        # pick different kernels (they would exchange halo rows at different cadences)
+        lossy = field._device_model.startswith('acoustic') and is_lossy(field)
         self.engine = _engine.prepare(field, device=device, row0=self.row0, rows=self.rows,
-                                      halo_rows=self.halo_rows, kernel=kernel)
+                                      halo_rows=self.halo_rows, kernel=kernel, lossy=lossy)
         if world > 1:
             if unique_id is None:
                 unique_id = _broadcast_unique_id(rank)

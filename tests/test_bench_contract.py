@@ -18,7 +18,7 @@ def _run(*args):
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    result = _run('--impl', 'reference', '--steps', '2', '--warmup', '3')
+    result = _run('--impl', 'reference', '--steps', '2', '--warmup', '3', '--size', '512')
     assert result.returncode == 0, result.stderr[-2000:]
     lines = [ln for ln in result.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, result.stdout
@@ -30,8 +30,11 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert line['value'] > 0 and line['ms_per_step'] > 0
     assert line['vs_baseline'] is None              # BASELINE.md publishes no number for this metric
     baseline = line['cpu_baseline']
-    assert baseline['kind'] == 'port' and baseline['cores'] == 1 and baseline['value'] == line['value']
-    assert 'sub-grid' in baseline['sample']
+    # the unmodified reference staged in baseline/_ref by build(); the CPU restatement without it
+    staged = os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', 'pyfds'))
+    assert baseline['kind'] == ('reference' if staged else 'port')
+    assert baseline['cores'] == 1 and baseline['value'] == line['value']
+    assert '512x512' in baseline['sample']
     e2e = line['e2e']
     assert e2e['value'] == line['value'] and e2e['h2d_bytes_per_step'] == 0
     assert e2e['d2h_bytes_per_step'] == 0
@@ -39,10 +42,25 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert 'workload' in line['config'] and 'model' not in line['config']
 
 
+def test_both_arms_describe_the_same_config():
+    """The driver compares the `config` of the two arms: it must not depend on the arm."""
+    sys.path.insert(0, ROOT)
+    import bench
+    product = bench.config_record(4096, 4096, 4096 * 2, 2)
+    result = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
+                             '--gpus', '2', '--steps', '1', '--warmup', '3', '--size', '256'],
+                            capture_output=True, text=True, cwd=ROOT, timeout=600,
+                            env=dict(os.environ, RANK='0', LOCAL_RANK='0', WORLD_SIZE='2'))
+    assert result.returncode == 0, result.stderr[-2000:]
+    line = json.loads(result.stdout.strip().splitlines()[-1])
+    assert line['config'] == bench.config_record(256, 256, 512, 2)
+    assert set(line['config']) == set(product)
+
+
 def test_reference_arm_runs_on_rank_zero_only():
     env = dict(os.environ, RANK='1', LOCAL_RANK='1', WORLD_SIZE='2')
     result = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference',
-                             '--gpus', '2', '--steps', '2', '--warmup', '3'],
+                             '--gpus', '2', '--steps', '2', '--warmup', '3', '--size', '512'],
                             capture_output=True, text=True, cwd=ROOT, timeout=600, env=env)
     assert result.returncode == 0 and result.stdout.strip() == ''
 

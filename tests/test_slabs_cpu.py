@@ -89,8 +89,19 @@ def _worker(rank, world, port, name, steps_per_exchange, queue):
     ('acoustic2d_boundaries', 2), ('thermal2d', 1), ('acoustic2d_lossy_wide', 2),
     ('acoustic3daxi_lossless_wide', 4), ('thermal3daxi_wide', 4), ('acoustic2d_signal_lines', 4)])
 def test_two_rank_halo_protocol_matches_single_domain(name, steps_per_exchange):
+    _check_halo_protocol(name, steps_per_exchange, 2)
+
+
+# interior slabs (two neighbours) from 3 ranks on
+@pytest.mark.parametrize('world', [3, 4])
+@pytest.mark.parametrize('name,steps_per_exchange', [
+    ('acoustic2d_wide', 4), ('acoustic2d_lossy_wide', 2), ('thermal2d', 1)])
+def test_interior_slab_halo_protocol_matches_single_domain(name, steps_per_exchange, world):
+    _check_halo_protocol(name, steps_per_exchange, world)
+
+
+def _check_halo_protocol(name, steps_per_exchange, world):
     import torch.multiprocessing as mp
-    world = 2
     ctx = mp.get_context('spawn')
     queue = ctx.Queue()
     port = _free_port()
