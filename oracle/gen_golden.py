@@ -54,6 +54,19 @@ def main():
         print('{:28s} steps {:4d}  {}'.format(
             name, steps, {k: v.shape for k, v in data.items() if k.startswith('values')}))
 
+    for name, builder in scenarios.COUPLED_SCENARIOS.items():
+        if only and name not in only:
+            continue
+        group, steps = builder(pyfds)
+        first = steps // 3
+        group.simulate(first)
+        group.simulate(steps - first)
+        data = scenarios.collect_group(group)
+        data['versions'] = np.asarray(versions)
+        np.savez_compressed(os.path.join(GOLDEN, 'coupled_' + name + '.npz'), **data)
+        print('{:28s} steps {:4d}  {}'.format(
+            name, steps, {k: v.shape for k, v in data.items() if '/values/' in k}))
+
     if only:
         return
     regions = {k: np.asarray(r.indices, dtype=np.int64)

@@ -25,6 +25,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler injects its library
+
 #include "fds_common.cuh"
 #include "fds_step1d.cuh"
 #include "fds_line1d.cuh"
@@ -36,6 +38,15 @@
 using namespace fds;
 
 namespace {
+
+// NVTX range for the duration of a scope (bake / upload / step / drain show up as
+// named ranges on an nsys or ncu --nvtx timeline).
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 std::mutex g_err_mutex;
 std::string g_create_error = "";
@@ -558,6 +569,7 @@ __global__ void strip_census_kernel(const map_t *map, long long nx, long long ro
 }
 
 int strip_census(fds_ctx *ctx, int n_strips) {
+    NvtxRange nvtx_range("fds:plan census");
     const int n_blocks = (int)((ctx->d.rows + kCensusBlockRows - 1) / kCensusBlockRows);
     const size_t n = (size_t)n_strips * (size_t)n_blocks;
     int *d_counts = nullptr;
@@ -607,6 +619,7 @@ void invalidate_plans(fds_ctx *ctx) {
 // accumulated cost crosses the multiples of their share. Tasks of the latter are handed out first,
 // the rest chunk-major (dynamic distribution absorbs what the model misses).
 int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int k, int lag_rows) {
+    NvtxRange nvtx_range("fds:plan tasks");
     const long long rows = plan.row_end - plan.row_begin;
     const double slots = 148.0 * (ctx->use_streamv ? kSVCtasPerSm : kS2CtasPerSm) * kStreamWarps;
     const double overhead = 2.0 * lag_rows + 4.0;
@@ -745,9 +758,31 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
         }
         return f;
     };
-    if (whole_slab && (has_side[0] || has_side[1]))
+    if (whole_slab && (has_side[0] || has_side[1])) {
+        // Short edge tasks: the rows a neighbour waits for are cut off the first / last task of every
+        // strip as tasks of their own (twice the band: a few dozen rows of work including the
+        // pipeline fill), so that they are stored, pushed and flagged within the first tenth of a
+        // sweep instead of at its end -- a neighbour may then lag or lead by most of a sweep before
+        // anybody waits.
+        const long long edge = std::min<long long>(std::max<long long>(2 * band, 8), rows);
+        std::vector<Item> cut;
+        cut.reserve(items.size() + 2 * (size_t)n_strips);
+        for (const Item &it : items) {
+            long long ys = it.ys, ye = it.ye;
+            if (has_side[0] && ys < edge && ye > edge + 4) {
+                cut.push_back({it.strip, ys, edge, (double)(edge - ys) + overhead});
+                ys = edge;
+            }
+            if (has_side[1] && ye > rows - edge && ys < rows - edge - 4) {
+                cut.push_back({it.strip, rows - edge, ye, (double)(ye - (rows - edge)) + overhead});
+                ye = rows - edge;
+            }
+            cut.push_back({it.strip, ys, ye, it.cost});
+        }
+        items.swap(cut);
         std::stable_partition(items.begin(), items.end(),
                               [&](const Item &it) { return flags_of(it) != 0; });
+    }
     std::vector<int4> tasks(items.size());
     plan.n_edge[0] = plan.n_edge[1] = 0;
     for (size_t i = 0; i < items.size(); ++i) {
@@ -1184,6 +1219,7 @@ int launch_flow(fds_ctx *ctx, int which, long long step) {
 
 // The time loop. `drain` = copy probe records to pinned host memory behind the computation.
 int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain) {
+    NvtxRange nvtx_range("fds:step enqueue");
     if (n_steps <= 0) return 0;
     if (!ctx->map_uploaded) return fail(ctx, "fds_step: material map not uploaded");
     if (ctx->n_signals > 0 &&
@@ -1691,6 +1727,7 @@ void fds_destroy(fds_ctx *ctx) {
 }
 
 int fds_upload_material_map(fds_ctx *ctx, const uint8_t *ids, int64_t n) {
+    NvtxRange nvtx_range("fds:bake material map h2d");
     if (!ctx || !ids) return fail(ctx, "fds_upload_material_map: null argument");
     if (n != ctx->owned + 2 * ctx->halo)
         return fail(ctx, "fds_upload_material_map: expected (rows + 2*halo_rows) * nx ids");
@@ -1758,6 +1795,7 @@ int fds_upload_column_vector(fds_ctx *ctx, int32_t vec, const double *values, in
 int fds_upload_boundaries(fds_ctx *ctx, int32_t component, const int64_t *cells,
                           const int32_t *offsets, int64_t n_cells, const double *alpha,
                           const double *value, const int32_t *signal, int64_t n_ops) {
+    NvtxRange nvtx_range("fds:bake boundary table h2d");
     if (!ctx) return fail(ctx, "fds_upload_boundaries: null context");
     if (component < 0 || component >= ctx->ncomp)
         return fail(ctx, "fds_upload_boundaries: bad component");
@@ -1844,6 +1882,7 @@ int fds_upload_boundaries(fds_ctx *ctx, int32_t component, const int64_t *cells,
 
 int fds_upload_signals(fds_ctx *ctx, const double *samples, int64_t n_signals, int64_t n_steps,
                        int64_t first_step) {
+    NvtxRange nvtx_range("fds:bake signals h2d");
     if (!ctx) return fail(ctx, "fds_upload_signals: null context");
     if (n_signals < 0 || n_steps < 0) return fail(ctx, "fds_upload_signals: bad sizes");
     if (n_signals > 0 && n_steps > 0 && !samples)
@@ -1858,6 +1897,7 @@ int fds_upload_signals(fds_ctx *ctx, const double *samples, int64_t n_signals, i
 
 int fds_upload_probes(fds_ctx *ctx, int32_t component, const int64_t *cells, const int32_t *slots,
                       int64_t n, int64_t n_slots_total) {
+    NvtxRange nvtx_range("fds:bake probe table h2d");
     if (!ctx) return fail(ctx, "fds_upload_probes: null context");
     if (component < 0 || component >= ctx->ncomp) return fail(ctx, "fds_upload_probes: bad component");
     if (n < 0 || n > 0x7fffffff || n_slots_total < 0 || n_slots_total > 0x7fffffff)
@@ -1882,6 +1922,7 @@ int fds_upload_probes(fds_ctx *ctx, int32_t component, const int64_t *cells, con
 }
 
 int fds_upload_state(fds_ctx *ctx, int32_t component, const double *values, int64_t n) {
+    NvtxRange nvtx_range("fds:state h2d");
     if (!ctx || !values) return fail(ctx, "fds_upload_state: null argument");
     if (component < 0 || component >= ctx->ncomp) return fail(ctx, "fds_upload_state: bad component");
     if (n != ctx->owned) return fail(ctx, "fds_upload_state: expected rows * nx values");
@@ -1891,6 +1932,7 @@ int fds_upload_state(fds_ctx *ctx, int32_t component, const double *values, int6
 }
 
 int fds_download_state(fds_ctx *ctx, int32_t component, double *values, int64_t n) {
+    NvtxRange nvtx_range("fds:state d2h");
     if (!ctx || !values) return fail(ctx, "fds_download_state: null argument");
     if (component < 0 || component >= ctx->ncomp)
         return fail(ctx, "fds_download_state: bad component");
@@ -1930,6 +1972,7 @@ int fds_reset_state(fds_ctx *ctx) {
 }
 
 int fds_step(fds_ctx *ctx, int64_t first_step, int64_t n_steps, double *probes_out) {
+    NvtxRange nvtx_range("fds:step + probe drain");
     if (!ctx) return fail(ctx, "fds_step: null context");
     if (n_steps < 0) return fail(ctx, "fds_step: negative step count");
     if (ctx->n_slots > 0 && n_steps > 0 && !probes_out)
@@ -1966,6 +2009,7 @@ int fds_step_async(fds_ctx *ctx, int64_t first_step, int64_t n_steps) {
 }
 
 int fds_sync(fds_ctx *ctx) {
+    NvtxRange nvtx_range("fds:sync");
     if (!ctx) return fail(ctx, "fds_sync: null context");
     FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
     if (check_device_waits(ctx)) return 1;
@@ -2013,6 +2057,7 @@ int fds_last_flow_shifts(fds_ctx *ctx, int64_t *shifts) {
 
 int fds_snapshot_async(fds_ctx *ctx, int32_t component, int32_t stride_x, int32_t stride_y,
                        int32_t slot) {
+    NvtxRange nvtx_range("fds:snapshot");
     if (!ctx) return fail(ctx, "fds_snapshot_async: null context");
     if (component < 0 || component >= ctx->ncomp)
         return fail(ctx, "fds_snapshot_async: bad component");

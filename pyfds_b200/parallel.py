@@ -160,12 +160,22 @@ class SlabRun:
     def simulate(self, num_steps, gather_probes=True):
         """Advances the slab ``num_steps`` steps. Probe signals are summed over ranks (every probe
         point is owned by exactly one slab) so that each rank ends up with complete ``signals``."""
+        import time
+        clock = time.perf_counter
         field, engine = self.field, self.engine
         first_step = field.step
+        t0 = clock()
         n_slots, layout = _engine.upload_run_tables(field, engine, first_step, num_steps)
+        t1 = clock()
         self.upload_state()
+        t2 = clock()
         records = engine.step(first_step, num_steps, n_slots)
+        t3 = clock()
         self.download_state()
+        t4 = clock()
+        field.__dict__['_last_run_profile'] = {
+            'prepare_and_tables_s': t1 - t0, 'upload_state_s': t2 - t1, 'step_s': t3 - t2,
+            'download_state_s': t4 - t3}
         if n_slots:
             if gather_probes and self.world > 1:
                 import torch
@@ -178,6 +188,7 @@ class SlabRun:
                 dist.all_reduce(tensor)
                 records = tensor.cpu().numpy()
             _engine._append_signals(layout, records)
+        field.__dict__['_last_run_profile']['probe_gather_s'] = clock() - t4
         field.step += num_steps
 
     def gather(self):

@@ -384,3 +384,132 @@ def region_cases(fds):
         'point_1d': g.get_point_region(4.9),
     }
     return cases
+
+
+# ---- coupled fields (pyfds/coupling.py, pyfds/coupled_fields.py) -----------------------------------
+# Builders return (group, n_steps); `collect_group` flattens every member field.
+
+def linear_transfer(fds, scale):
+    """``lambda values: scale * values`` -- as the object the drop-in recognises as a linear transfer
+    function where it offers one (``pyfds_b200.coupling.linear``), as the plain callable elsewhere."""
+    factory = getattr(getattr(fds, 'coupling', None), 'linear', None)
+    if factory is not None:
+        return factory(scale)
+    return lambda values: scale * values
+
+
+def _thermoacoustic(fds, stepping, steps=240, nx=300):
+    grp = fds.ThermoAcoustic1D(x_samples=nx, x_delta=1e-3, t_samples=steps, t_delta=1e-7,
+                               thermal_material=fds.ThermalMaterial(900, 2700, 200),
+                               acoustic_material=fds.AcousticMaterial(700, 0.01,
+                                                                     shear_viscosity=1e-3),
+                               stepping=stepping)
+    sound, heat = grp.fields
+    sound.add_material_region(sound.get_line_region((120e-3, 170e-3)),
+                              fds.AcousticMaterial(650, 0.012, bulk_viscosity=2e-3))
+    heat.add_material_region(heat.get_line_region((140e-3, 199e-3)),
+                             fds.ThermalMaterial(450, 7800, 50))
+    # The heating of one step is ~1e-25 K at these amplitudes (the reference's expression carries
+    # dt / dx twice): the temperature starts at exactly zero so that every bit of it is the coupling's.
+    _randomise(sound, ('pressure', 'velocity'), seed=31, scale=1.0)
+    sound.velocity.add_boundary(sound.get_point_region(0))
+    sound.pressure.add_boundary(sound.get_point_region((nx - 1) * 1e-3))
+    sound.pressure.add_boundary(sound.get_point_region(100e-3), value=_pulse(steps, 60, 20),
+                                additive=True)
+    heat.temperature.add_boundary(heat.get_point_region(0), value=0)
+    sound.pressure.add_output(sound.get_point_region(200e-3))
+    heat.temperature.add_output(heat.get_line_region((98e-3, 103e-3)))
+    heat.heat_flux.add_output(heat.get_point_region(150e-3))
+    return grp, steps
+
+
+def thermoacoustic1d(fds):
+    """The preset of pyfds/coupled_fields.py: viscous losses of the sound field heat the medium,
+    delivered after every step."""
+    return _thermoacoustic(fds, stepping=1)
+
+
+def thermoacoustic1d_stepping(fds):
+    """... accumulated over three steps between deliveries (accumulate = True)."""
+    return _thermoacoustic(fds, stepping=3)
+
+
+def _two_line_fields(fds, steps, nx=220):
+    sound = fds.Acoustic1D(t_delta=1e-7, t_samples=steps, x_delta=1e-3, x_samples=nx,
+                           material=fds.AcousticMaterial(700, 0.01, shear_viscosity=1e-3))
+    heat = fds.Thermal1D(t_delta=1e-3, t_samples=steps, x_delta=1e-3, x_samples=nx,
+                         material=fds.ThermalMaterial(900, 2700, 200))
+    heat.add_material_region(heat.get_line_region((60e-3, 99e-3)), fds.ThermalMaterial(450, 7800, 50))
+    _randomise(sound, ('pressure', 'velocity'), seed=33, scale=1e-2)
+    rng = np.random.default_rng(34)
+    heat.temperature.values = 20 + 3 * np.sin(np.arange(nx) / 17.0) + 0.1 * rng.standard_normal(nx)
+    sound.velocity.add_boundary(sound.get_point_region(0))
+    sound.pressure.add_boundary(sound.get_point_region(70e-3), value=_pulse(steps, 50, 18),
+                                additive=True)
+    heat.temperature.add_boundary(heat.get_point_region(0), value=40)
+    sound.pressure.add_output(sound.get_point_region(150e-3))
+    sound.velocity.add_output(sound.get_point_region(151e-3))
+    heat.temperature.add_output(heat.get_point_region(30e-3))
+    return sound, heat
+
+
+def boundary_coupling_linear(fds):
+    """Two BoundaryCouplings with linear transfer functions (pyfds/coupling.py:90-140): temperature
+    feeds the pressure additively after every step; the velocity REPLACES the heat flux every fourth
+    step with what accumulated in between."""
+    steps = 150
+    sound, heat = _two_line_fields(fds, steps)
+    a = fds.BoundaryCoupling(heat.temperature, sound.pressure, linear_transfer(fds, 1e-4))
+    b = fds.BoundaryCoupling(sound.velocity, heat.heat_flux, linear_transfer(fds, -2.5),
+                             additive=False, accumulate=True, stepping=4)
+    return fds.SynchronizedFields([sound, heat], [a, b]), steps
+
+
+def boundary_coupling_stepping(fds):
+    """additive with stepping 3 and no accumulation; non-additive after every step."""
+    steps = 100
+    sound, heat = _two_line_fields(fds, steps)
+    a = fds.BoundaryCoupling(heat.temperature, sound.velocity, linear_transfer(fds, 3e-6),
+                             additive=True, accumulate=False, stepping=3)
+    b = fds.BoundaryCoupling(sound.pressure, heat.heat_flux, linear_transfer(fds, 0.5),
+                             additive=False)
+    return fds.SynchronizedFields([sound, heat], [a, b]), steps
+
+
+def material_coupling_exponential(fds):
+    """MaterialCouplingExponential (pyfds/coupling.py:218-259): the smooth temperature profile scales
+    the sound velocity point by point -- every cell its own material -- re-assembled every 5th step."""
+    steps = 90
+    sound, heat = _two_line_fields(fds, steps)
+    law = fds.MaterialCouplingExponential(heat.temperature, sound, 'sound_velocity', a=0.8, b=-0.01,
+                                          stepping=5)
+    return fds.SynchronizedFields([sound, heat], [law]), steps
+
+
+def material_coupling_powerlaw(fds):
+    """MaterialCouplingPowerLaw (pyfds/coupling.py:262-300) on the density of the thermal field, driven
+    by the pressure, re-assembled only when the factors moved by more than 2 %."""
+    steps = 90
+    sound, heat = _two_line_fields(fds, steps)
+    law = fds.MaterialCouplingPowerLaw(sound.pressure, heat, 'density', power=2, factor=40.0,
+                                       rel_change_threshold=0.02)
+    return fds.SynchronizedFields([sound, heat], [law]), steps
+
+
+COUPLED_SCENARIOS = {
+    'thermoacoustic1d': thermoacoustic1d,
+    'thermoacoustic1d_stepping': thermoacoustic1d_stepping,
+    'boundary_coupling_linear': boundary_coupling_linear,
+    'boundary_coupling_stepping': boundary_coupling_stepping,
+    'material_coupling_exponential': material_coupling_exponential,
+    'material_coupling_powerlaw': material_coupling_powerlaw,
+}
+
+
+def collect_group(group):
+    """Final values and probe signals of every member of a ``SynchronizedFields`` group."""
+    out = {}
+    for f, field in enumerate(group.fields):
+        for key, value in collect(field).items():
+            out['field{}/{}'.format(f, key)] = value
+    return out

@@ -261,3 +261,72 @@ def test_subclass_sim_step_override_is_called_per_step():         # acoustic_flo
     assert calls == [0, 1, 2] and fld.step == 3
     fld.simulate()          # falsy -> t.samples steps (fields.py:74-75)
     assert fld.step == 8
+
+
+# ---- is_stable (pyfds/acoustics.py:54-63, 130-139, 227-236) ------------------------------------------
+
+def _stability_cases():
+    """(class name, constructor kwargs, extra region or None, expected) -- expected values follow from
+    the reference statement ``all(c < 0.99 * min(dx, dy) / dt)``: strict inequality, 1 % headroom."""
+    water = dict(sound_velocity=1500, density=1000)
+    line = dict(x_samples=40, x_delta=1e-3, t_samples=10)
+    grid = dict(x_samples=24, x_delta=1e-3, y_samples=20, y_delta=2e-3, t_samples=10)
+    yield 'Acoustic1D', dict(line, t_delta=6e-7), water, None, True        # limit 1650
+    yield 'Acoustic1D', dict(line, t_delta=6.7e-7), water, None, False     # limit 1477.6
+    # exactly on the limit: `<` is strict
+    limit = 0.99 * 1e-3 / 5e-7
+    yield 'Acoustic1D', dict(line, t_delta=5e-7), dict(sound_velocity=limit, density=1000), None, False
+    yield 'Acoustic1D', dict(line, t_delta=5e-7), \
+        dict(sound_velocity=np.nextafter(limit, 0), density=1000), None, True
+    # the finer of the two increments decides in 2-D (dx = 1e-3 < dy = 2e-3)
+    yield 'Acoustic2D', dict(grid, t_delta=6e-7), water, None, True
+    yield 'Acoustic2D', dict(grid, t_delta=6.7e-7), water, None, False
+    yield 'Acoustic3DAxi', dict(grid, t_delta=6e-7), water, None, True
+    yield 'Acoustic3DAxi', dict(grid, t_delta=6.7e-7), water, None, False
+    # one fast inclusion is enough
+    yield 'Acoustic2D', dict(grid, t_delta=6e-7), water, ('rect', 5900), False
+    yield 'Acoustic2D', dict(grid, t_delta=6e-7), water, ('rect', 1600), True
+    # ... unless a later region paints all of it over (the test is on the painted vector)
+    yield 'Acoustic2D', dict(grid, t_delta=6e-7), water, ('hidden', 5900), True
+
+
+def _stability_field(package, name, kwargs, material, extra):
+    fld_ = getattr(package, name)(material=package.AcousticMaterial(**material), **kwargs)
+    if extra is not None:
+        kind, speed = extra
+        region = fld_.get_rect_region((3e-3, 4e-3, 5e-3, 6e-3))
+        fld_.add_material_region(region, package.AcousticMaterial(speed, 2000))
+        if kind == 'hidden':
+            fld_.add_material_region(fld_.get_rect_region((2e-3, 2e-3, 8e-3, 12e-3)),
+                                     package.AcousticMaterial(1400, 900))
+    return fld_
+
+
+@pytest.mark.parametrize('name,kwargs,material,extra,expected', list(_stability_cases()))
+def test_is_stable_known_answers(name, kwargs, material, extra, expected):
+    field = _stability_field(fds, name, kwargs, material, extra)
+    assert bool(field.is_stable()) is expected
+    # the statement of the reference on the painted vector
+    dx = min(field.x.increment, field.y.increment) if hasattr(field, 'y') else field.x.increment
+    assert bool(np.all(field.material_vector('sound_velocity')
+                       < 0.99 * dx / field.t.increment)) is expected
+
+
+def test_is_stable_equals_the_reference_where_it_is_installed():
+    import os
+    import sys
+    import types
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    staged = os.path.join(root, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(staged, 'pyfds')):
+        pytest.skip('reference not staged (baseline/_ref)')
+    for mod in ('matplotlib', 'matplotlib.patches', 'matplotlib.pyplot', 'matplotlib.animation'):
+        sys.modules.setdefault(mod, types.ModuleType(mod))
+    sys.path.insert(0, staged)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        import pyfds
+        for name, kwargs, material, extra, expected in _stability_cases():
+            reference = _stability_field(pyfds, name, kwargs, material, extra)
+            assert bool(reference.is_stable()) is expected, (name, kwargs, extra)
