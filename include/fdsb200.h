@@ -113,6 +113,11 @@ int fds_upload_table(fds_ctx *ctx, int32_t table, const double *values, int64_t 
 int fds_upload_column_table(fds_ctx *ctx, int32_t table, const double *values, int64_t n);
 /* One per-column vector: n = nx doubles. */
 int fds_upload_column_vector(fds_ctx *ctx, int32_t vec, const double *values, int64_t n);
+/* 1-D models whose material parameters differ from cell to cell (what `MaterialCoupling` produces by
+ * scaling a parameter with another field's values, pyfds/coupling.py:182-197): one per-CELL coefficient
+ * array, n = nx doubles, used instead of the per-material table of the same id. All tables the model
+ * reads must be uploaded this way; values == NULL switches back to the per-material tables. */
+int fds_upload_cell_table(fds_ctx *ctx, int32_t table, const double *values, int64_t n);
 
 /* --- boundaries and sources: `FieldComponent.apply_bounds` + `Boundary.apply`
  *     (pyfds/fields.py:591-600, pyfds/regions.py:125-145) -------------------------------------- */
@@ -176,6 +181,53 @@ int fds_sync(fds_ctx *ctx);
 int fds_set_flow(fds_ctx *ctx, const int64_t *periods, int64_t n);
 /* Number of row-shift passes the last fds_step / fds_step_async call launched. */
 int fds_last_flow_shifts(fds_ctx *ctx, int64_t *shifts);
+
+/* --- the caller above the hot path: coupled fields --------------------------- */
+
+/* `SynchronizedFields.sim_step` (pyfds/coupling.py:81-87) for 1-D member fields on one device: per
+ * common step every member advances one step (in list order), then the interactions run (in the order
+ * they were added) -- all as kernels on one stream, so the state of the group stays in HBM for the
+ * whole call. Interactions are the reference's own ones whose transfer function is built in or
+ * linear; arbitrary Python transfer functions stay with the host-side session of the Python layer. */
+typedef struct fds_group fds_group;
+int fds_group_create(fds_ctx *const *members, int32_t n_members, fds_group **out);
+void fds_group_destroy(fds_group *group);
+const char *fds_group_last_error(const fds_group *group);
+/* `BoundaryCoupling` (pyfds/coupling.py:90-140) with transfer function  values -> scale * values:
+ * target (+)= scale * source every `stepping`-th step; with `accumulate` the products are summed after
+ * every step and the sum is delivered. accumulated: the coupling's `accumulated_transfer` carried over
+ * from an earlier call (n doubles) or NULL for 0. */
+int fds_group_add_linear(fds_group *group, int32_t src_member, int32_t src_component,
+                         int32_t dst_member, int32_t dst_component, double scale, int32_t additive,
+                         int32_t accumulate, int64_t stepping, const double *accumulated);
+/* `ThermoAcoustic1D._loss_coupling` (pyfds/coupled_fields.py:45-65): temperature +=
+ * gain * (a_v_p . (velocity * density))^2 * dt, with per-cell density, gradient_factor (the factors
+ * dt/dx/density of a_v_p, pyfds/acoustics.py:31) and gain = absorption_coef / density_thermal /
+ * heat_capacity, n doubles each, evaluated by the host with the reference's expressions. */
+int fds_group_add_viscous_heating(fds_group *group, int32_t sound_member, int32_t heat_member,
+                                  const double *density, const double *gradient_factor,
+                                  const double *gain, double dt, int32_t accumulate,
+                                  int64_t stepping, const double *accumulated);
+/* `MaterialCouplingExponential` (law 0: a = p0, b = p1) / `MaterialCouplingPowerLaw` (law 1:
+ * factor = p0, power = p1), pyfds/coupling.py:218-300: every `stepping`-th step the factors of the
+ * source component are evaluated and -- if they moved by more than `threshold` relative to the ones
+ * last used, or always without a threshold -- the target member's per-cell coefficients are
+ * re-assembled from  statics[parameter] * factors  (pyfds/coupling.py:193-215). statics: the three
+ * static parameter vectors of the target in the order the model lists them ([3][n] doubles: acoustic
+ * sound_velocity, density, absorption_coef; thermal density, heat_capacity, thermal_conductivity_x);
+ * last: `last_used_factors` of an earlier call or NULL; scalars: dt/dx, dt/dx**2, 1/dx as the host
+ * evaluates them. The target needs per-cell coefficient tables (fds_upload_cell_table). */
+int fds_group_add_material_law(fds_group *group, int32_t src_member, int32_t src_component,
+                               int32_t dst_member, int32_t parameter, int32_t law, double p0,
+                               double p1, int32_t has_threshold, double threshold,
+                               int64_t stepping, const double *statics, const double *last,
+                               const double *scalars);
+/* n_steps common steps; probes_out[m] receives member m's records [n_steps][n_slots] (may be NULL for
+ * members without probes). Synchronous. */
+int fds_group_step(fds_group *group, int64_t first_step, int64_t n_steps, double *const *probes_out);
+/* State an interaction carries between calls: the accumulated transfer of a boundary coupling, or the
+ * factors last used by a material law (n doubles) and how often it re-assembled so far. */
+int fds_group_read(fds_group *group, int32_t interaction, double *values, int64_t *reassemblies);
 
 /* --- the output side: field snapshots --------------------------------------- */
 

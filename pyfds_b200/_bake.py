@@ -63,6 +63,12 @@ class DenseSnapshot:
                         for p in self.params}
 
 
+def distinct_combinations(snapshot):
+    """Number of distinct per-point parameter combinations of a ``DenseSnapshot``."""
+    stacked = np.stack([snapshot.vectors[p] for p in snapshot.params], axis=1)
+    return len(np.unique(stacked, axis=0))
+
+
 def _dense_material_ids(snapshot, num_points, cell_lo, cell_hi):
     lo, hi = max(cell_lo, 0), min(cell_hi, num_points)
     ids = np.zeros(cell_hi - cell_lo, dtype=np.uint8)

@@ -71,6 +71,7 @@ def load_library():
         'fds_device_count': (ct.c_int, []),
         'fds_upload_material_map': (ct.c_int, [p, p, i64]),
         'fds_upload_table': (ct.c_int, [p, i32, p, i64]),
+        'fds_upload_cell_table': (ct.c_int, [p, i32, p, i64]),
         'fds_upload_column_table': (ct.c_int, [p, i32, p, i64]),
         'fds_upload_column_vector': (ct.c_int, [p, i32, p, i64]),
         'fds_upload_boundaries': (ct.c_int, [p, i32, p, p, i64, p, p, p, i64]),
@@ -96,6 +97,15 @@ def load_library():
         'fds_last_launch_info': (ct.c_int, [p, ct.POINTER(i64), ct.POINTER(i64),
                                             ct.POINTER(ct.c_char_p)]),
         'fds_device_bytes': (i64, [p]),
+        'fds_group_create': (ct.c_int, [ct.POINTER(p), i32, ct.POINTER(p)]),
+        'fds_group_destroy': (None, [p]),
+        'fds_group_last_error': (ct.c_char_p, [p]),
+        'fds_group_add_linear': (ct.c_int, [p, i32, i32, i32, i32, ct.c_double, i32, i32, i64, p]),
+        'fds_group_add_viscous_heating': (ct.c_int, [p, i32, i32, p, p, p, ct.c_double, i32, i64, p]),
+        'fds_group_add_material_law': (ct.c_int, [p, i32, i32, i32, i32, i32, ct.c_double,
+                                                   ct.c_double, i32, ct.c_double, i64, p, p, p]),
+        'fds_group_step': (ct.c_int, [p, i64, i64, ct.POINTER(p)]),
+        'fds_group_read': (ct.c_int, [p, i32, p, ct.POINTER(i64)]),
         'fds_stream_stats': (ct.c_int, [p, ct.POINTER(i64)]),
     }
     for name, (restype, argtypes) in sigs.items():
@@ -162,6 +172,14 @@ class Engine:
     def upload_table(self, which, values):
         values = _c(values, np.float64)
         self._check(self.lib.fds_upload_table(self.handle, which, _ptr(values), values.size))
+
+    def upload_cell_table(self, which, values):
+        """Per-cell coefficients of a 1-D field (``None``: back to the per-material tables)."""
+        if values is None:
+            self._check(self.lib.fds_upload_cell_table(self.handle, 0, None, 0))
+            return
+        values = _c(values, np.float64)
+        self._check(self.lib.fds_upload_cell_table(self.handle, which, _ptr(values), values.size))
 
     def upload_column_table(self, which, values):
         values = _c(values, np.float64)
@@ -277,6 +295,83 @@ class Engine:
         self._check(self.lib.fds_comm_init(self.handle, buf, rank, world))
 
 
+class Group:
+    """Device form of a ``SynchronizedFields`` group of 1-D fields (``fds_group_*``): the members step
+    in lock-step on one stream and the built-in interactions run as kernels in between."""
+
+    def __init__(self, engines):
+        self.lib = load_library()
+        self.engines = list(engines)
+        handles = (ct.c_void_p * len(self.engines))(*[e.handle for e in self.engines])
+        handle = ct.c_void_p()
+        if self.lib.fds_group_create(handles, len(self.engines), ct.byref(handle)) != 0:
+            raise EngineError(self.lib.fds_group_last_error(None).decode())
+        self.handle = handle
+        self.n = self.engines[0].nx
+        self.count = 0
+        self._finalizer = weakref.finalize(self, self.lib.fds_group_destroy, handle)
+
+    def close(self):
+        self._finalizer()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise EngineError(self.lib.fds_group_last_error(self.handle).decode())
+
+    @staticmethod
+    def _optional(values, n):
+        """Array of n doubles, or NULL for the integer 0 the reference starts its sums with."""
+        if np.ndim(values) == 0:
+            return None, None
+        array = _c(np.broadcast_to(np.asarray(values, dtype=np.float64), (n,)), np.float64)
+        return array, _ptr(array)
+
+    def add_linear(self, source, target, scale, additive, accumulate, stepping, accumulated=0):
+        keep, pointer = self._optional(accumulated, self.n)
+        self._check(self.lib.fds_group_add_linear(
+            self.handle, source[0], source[1], target[0], target[1], float(scale), int(additive),
+            int(accumulate), int(stepping), pointer))
+        self.count += 1
+        return self.count - 1
+
+    def add_viscous_heating(self, sound, heat, density, gradient_factor, gain, dt, accumulate,
+                            stepping, accumulated=0):
+        arrays = [_c(a, np.float64) for a in (density, gradient_factor, gain)]
+        keep, pointer = self._optional(accumulated, self.n)
+        self._check(self.lib.fds_group_add_viscous_heating(
+            self.handle, sound, heat, _ptr(arrays[0]), _ptr(arrays[1]), _ptr(arrays[2]), float(dt),
+            int(accumulate), int(stepping), pointer))
+        self.count += 1
+        return self.count - 1
+
+    def add_material_law(self, source, target, parameter, law, p0, p1, threshold, stepping, statics,
+                         last, scalars):
+        statics = _c(statics, np.float64)
+        scalars = _c(scalars, np.float64)
+        keep, pointer = self._optional(last, self.n)
+        self._check(self.lib.fds_group_add_material_law(
+            self.handle, source[0], source[1], target, int(parameter), int(law), float(p0),
+            float(p1), int(threshold is not None), float(threshold or 0.0), int(stepping),
+            _ptr(statics), pointer, _ptr(scalars)))
+        self.count += 1
+        return self.count - 1
+
+    def step(self, first_step, n_steps, slots):
+        """``n_steps`` common steps; returns the probe records of every member."""
+        records = [np.zeros((n_steps, n), dtype=np.float64) for n in slots]
+        pointers = (ct.c_void_p * len(records))(
+            *[r.ctypes.data if r.size else None for r in records])
+        self._check(self.lib.fds_group_step(self.handle, first_step, n_steps, pointers))
+        return records
+
+    def read(self, interaction):
+        values = np.zeros(self.n, dtype=np.float64)
+        count = ct.c_int64()
+        self._check(self.lib.fds_group_read(self.handle, interaction, _ptr(values),
+                                            ct.byref(count)))
+        return values, count.value
+
+
 def comm_unique_id():
     lib = load_library()
     buf = (ct.c_uint8 * 128)()
@@ -346,14 +441,18 @@ def halo_rows_for(field, world):
     return 2 if field._baked['lossy'] else 1
 
 
-def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None, lossy=None):
+def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None, lossy=None,
+            per_cell=False):
     """Creates (or reuses) the device context of ``field`` and uploads what ``assemble_matrices``
     froze: the material map and the coefficient tables. Returns the ``Engine``.
 
     ``kernel``: 0 automatic, 1 one-step kernel, 2 streaming multi-step kernel (``fds_desc.kernel``);
     defaults to the field attribute ``device_kernel`` (0 if absent). ``lossy``: True if ANY cell of the
     grid is lossy -- every slab of a multi-GPU run must pick the same kernel and the same number of
-    steps per launch, whatever materials its own rows hold (default: decided from this window)."""
+    steps per launch, whatever materials its own rows hold (default: decided from this window).
+    ``per_cell``: give a 1-D field with per-point material vectors per-cell coefficient arrays even if
+    its distinct value combinations would fit the material table (targets of a device-side material
+    law, whose coefficients are rewritten cell by cell)."""
     if kernel is None:
         kernel = getattr(field, 'device_kernel', 0)
     state = field.__dict__.get('_engine_state')
@@ -362,15 +461,29 @@ def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None, lossy=
     baked = field._baked
     nx, ny = _grid(field)
     rows = ny if rows is None else rows
-    key = (field._device_model, nx, ny, row0, rows, halo_rows, device, kernel)
+    key = (field._device_model, nx, ny, row0, rows, halo_rows, device, kernel, bool(per_cell))
     if state.engine is not None and state.epoch == baked['epoch'] and state.key == key:
         return state.engine
 
     snapshot = baked['snapshot']
     lo, hi = (row0 - halo_rows) * nx, (row0 + rows + halo_rows) * nx
-    ids, values = _bake.material_ids(snapshot, field.num_points, nx, lo, hi)
-    tables = field._coefficient_tables(values)
-    n_materials = len(next(iter(values.values()))) - 1
+    one_d = not hasattr(field, 'y')
+    cells = None
+    if isinstance(snapshot, _bake.DenseSnapshot) and one_d and \
+            (per_cell or _bake.distinct_combinations(snapshot) > _bake.MAX_MATERIALS):
+        # materials that differ from cell to cell (MaterialCoupling on a smooth source): the 1-D kernels
+        # read per-cell coefficient arrays, evaluated here by the same expressions on the per-point
+        # parameter vectors themselves
+        values = {p: np.concatenate(([0.0], snapshot.vectors[p])) for p in snapshot.params}
+        cells = field._coefficient_tables(values)
+        ids = np.ones(field.num_points, dtype=np.uint8)
+        tables = {'tables': {name: np.zeros(1) for name in cells['tables']},
+                  'lossy': cells.get('lossy', False)}
+        n_materials = 1
+    else:
+        ids, values = _bake.material_ids(snapshot, field.num_points, nx, lo, hi)
+        tables = field._coefficient_tables(values)
+        n_materials = len(next(iter(values.values()))) - 1
     lossy = bool(tables.get('lossy', False)) or bool(lossy)
     baked['lossy'] = lossy
 
@@ -388,6 +501,11 @@ def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None, lossy=
         engine.upload_column_table(CTAB[name], np.vstack((np.zeros((1, nx)), matrix)))
     for name, vector in tables.get('column_vectors', {}).items():
         engine.upload_column_vector(CVEC[name], vector)
+    if one_d:
+        engine.upload_cell_table(0, None)
+        if cells is not None:
+            for name, column in cells['tables'].items():
+                engine.upload_cell_table(TAB[name], column)
     state.engine, state.epoch, state.key = engine, baked['epoch'], key
     return engine
 

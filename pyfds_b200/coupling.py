@@ -28,6 +28,19 @@ __all__ = [
     'MaterialCouplingPowerLaw',
 ]
 
+
+class linear:
+    """Transfer function ``values -> scale * values`` for a ``BoundaryCoupling``. Behaves like the
+    lambda it replaces; being an object, it lets ``SynchronizedFields.simulate`` see what the coupling
+    computes and run it on the device (an extension: the reference takes any callable, and so does this
+    package -- an opaque callable is simply evaluated on the host)."""
+
+    def __init__(self, scale):
+        self.scale = scale
+
+    def __call__(self, values):
+        return self.scale * values
+
 logger = lo.getLogger('pyfds')
 
 
@@ -112,12 +125,160 @@ class SynchronizedFields(fld.Field):
             plan.append((interaction, source, target))
         return plan
 
+    def _group_plan(self):
+        """What the device needs to run every interaction itself (``fds_group_*``): a list of
+        ``(kind, interaction, ...)`` if all members are 1-D device fields and every interaction is one
+        the engine knows -- a ``BoundaryCoupling`` with a ``linear`` transfer function, the viscous
+        heating of ``ThermoAcoustic1D``, or one of the two built-in material laws -- else ``None``."""
+        if not self.device_session or type(self).sim_step is not SynchronizedFields.sim_step:
+            return None
+        owners = {}
+        for f, field in enumerate(self.fields):
+            if getattr(field, '_device_model', None) not in ('acoustic1d', 'thermal1d') or \
+                    not field._uses_device() or getattr(field, 'device_kernel', 0) == 1:
+                return None
+            for c, name in enumerate(field._device_components):
+                owners[id(getattr(field, name))] = (f, c)
+        if len({field.num_points for field in self.fields}) != 1:
+            return None
+        from . import coupled_fields
+        plan, law_targets, heated = [], set(), set()
+        for interaction in self.interactions:
+            kind = type(interaction)
+            if kind is BoundaryCoupling:
+                source = owners.get(id(interaction.source_component))
+                target = owners.get(id(interaction.target_component))
+                if source is None or target is None or int(interaction.stepping) < 1 or \
+                        interaction.additive not in (True, False) or \
+                        interaction.accumulate not in (True, False):
+                    return None
+                function = interaction.transfer_function
+                if isinstance(function, linear) and np.ndim(function.scale) == 0:
+                    plan.append(('linear', interaction, source, target))
+                elif getattr(function, '__func__', None) is \
+                        coupled_fields.ThermoAcoustic1D._viscous_heating and \
+                        function.__self__ is self and source == (0, 1) and target == (1, 0):
+                    plan.append(('heating', interaction, source, target))
+                    heated.add(0)
+                else:
+                    return None
+            elif kind in (MaterialCouplingExponential, MaterialCouplingPowerLaw) and \
+                    getattr(interaction.transfer_function, '__func__', None) is \
+                    kind.transfer_function:
+                source = owners.get(id(interaction.source_component))
+                targets = [f for f, field in enumerate(self.fields)
+                           if field is interaction.target_field]
+                if source is None or not targets or targets[0] in law_targets or \
+                        int(interaction.stepping) < 1:
+                    return None
+                field = self.fields[targets[0]]
+                if interaction.target_parameter not in field._material_params or \
+                        vars(field).get('material_vector') != interaction._material_vector:
+                    return None          # somebody else shadows material_vector as well
+                law_targets.add(targets[0])
+                plan.append(('law', interaction, source, targets[0]))
+            else:
+                return None
+        if law_targets & heated:
+            return None      # the heating term reads the operators of a field that is re-assembled
+        return plan
+
+    def _simulate_on_group(self, plan, num_steps, progress_logger=None):
+        """``num_steps`` x ``sim_step`` entirely on the device: members and interactions as kernels on
+        one stream (``fds_group_step``), values and probe records cross the bus once per call."""
+        from . import _bake, _engine
+        first_step = self.step
+        law_targets = {entry[3]: entry[1] for entry in plan if entry[0] == 'law'}
+        engines, layouts = [], []
+        for f, field in enumerate(self.fields):
+            if not field.matrices_assembled:
+                field.assemble_matrices()
+            law = law_targets.get(f)
+            lossy = law is not None and law.target_parameter == 'absorption_coef'
+            engine = _engine.prepare(field, device=int(getattr(field, 'device_index', 0)),
+                                     per_cell=law is not None, lossy=lossy or None)
+            engines.append(engine)
+            layouts.append(_engine.upload_run_tables(field, engine, first_step, num_steps))
+            _engine.upload_values(field, engine)
+        group = _engine.Group(engines)
+        try:
+            for kind, interaction, source, target in plan:
+                if kind == 'linear':
+                    group.add_linear(source, target, interaction.transfer_function.scale,
+                                     interaction.additive, interaction.accumulate,
+                                     interaction.stepping, interaction.accumulated_transfer)
+                elif kind == 'heating':
+                    sound, heat = self.fields
+                    density = sound.material_vector('density')
+                    _, gradient_factor, _ = sound._factors(
+                        sound.material_vector('sound_velocity'), density,
+                        sound.material_vector('absorption_coef'))
+                    gain = sound.material_vector('absorption_coef') / \
+                        heat.material_vector('density') / heat.material_vector('heat_capacity')
+                    group.add_viscous_heating(0, 1, density, gradient_factor, gain, self.t.increment,
+                                              interaction.accumulate, interaction.stepping,
+                                              interaction.accumulated_transfer)
+                else:
+                    field = self.fields[target]
+                    statics = np.stack([np.asarray(field.static_material_vector(p), dtype=np.float64)
+                                        for p in field._material_params])
+                    dt, dx = field.t.increment, field.x.increment
+                    if type(interaction) is MaterialCouplingExponential:
+                        law, p0, p1 = 0, interaction.a, interaction.b
+                    else:
+                        law, p0, p1 = 1, interaction.factor, interaction.power
+                    group.add_material_law(
+                        source, target, field._material_params.index(interaction.target_parameter),
+                        law, p0, p1, interaction.rel_change_threshold, interaction.stepping, statics,
+                        interaction.last_used_factors, [dt / dx, dt / dx ** 2, 1 / dx])
+            slots = [n_slots for n_slots, _ in layouts]
+            chunk = num_steps if progress_logger is None else max(1, -(-num_steps // 20))
+            done = 0
+            while done < num_steps:
+                count = min(chunk, num_steps - done)
+                for (n_slots, layout), records in zip(
+                        layouts, group.step(first_step + done, count, slots)):
+                    if n_slots:
+                        _engine._append_signals(layout, records)
+                if progress_logger is not None:
+                    for s in range(first_step + done, first_step + done + count):
+                        progress_logger.log(s)
+                done += count
+            for field, engine in zip(self.fields, engines):
+                _engine.download_values(field, engine)
+            # what the interactions carry from one call to the next
+            for number, (kind, interaction, source, target) in enumerate(plan):
+                values, count = group.read(number)
+                if kind == 'law':
+                    if count:
+                        field = self.fields[target]
+                        interaction.last_used_factors = values
+                        snapshot = field._baked['snapshot']
+                        if isinstance(snapshot, _bake.DenseSnapshot):
+                            name = interaction.target_parameter
+                            snapshot.vectors[name] = np.asarray(
+                                field.static_material_vector(name), dtype=np.float64) * values
+                        field._baked['epoch'] += 1
+                        field._operators = {}
+                elif interaction.accumulate is True:
+                    interaction.accumulated_transfer = values if values.any() else 0
+        finally:
+            group.close()
+        self.step = first_step + num_steps
+        return True
+
     def _simulate_on_device(self, num_steps, progress_logger=None):
         """``num_steps`` x ``sim_step`` with the state of all fields resident on the device; returns
-        ``False`` (and does nothing) if the session does not apply."""
+        ``False`` (and does nothing) if no device session applies."""
+        group_plan = self._group_plan()
+        if group_plan is not None:
+            self._last_session = 'device'
+            return self._simulate_on_group(group_plan, num_steps, progress_logger)
         plan = self._session_plan()
         if plan is None:
+            self._last_session = 'per step'
             return False
+        self._last_session = 'host interactions'
         from . import _engine
         first_step = self.step
         engines, tables, components = [], [], []

@@ -34,6 +34,7 @@
 #include "fds_stream2d.cuh"
 #include "fds_streamv.cuh"
 #include "fds_aux.cuh"
+#include "fds_couple.cuh"
 
 using namespace fds;
 
@@ -112,6 +113,7 @@ struct fds_ctx {
     map_t *map = nullptr;
     bool map_uploaded = false;
     double *tab = nullptr;
+    double *cell_tab = nullptr;   // 1-D: per-cell coefficients [FDS_TAB_COUNT][nx] (fds_upload_cell_table)
     double *ctab = nullptr;
     double *cvec = nullptr;
     int cur = 0;
@@ -389,6 +391,8 @@ StepTables make_tables(fds_ctx *ctx) {
     t.tab = ctx->tab;
     t.ctab = ctx->ctab;
     t.cvec = ctx->cvec;
+    t.cell_tab = ctx->cell_tab;
+    t.cell_n = ctx->d.nx;
     for (int c = 0; c < 3; ++c) {
         t.bound[c].cells = (const long long *)ctx->bcells[c].ptr;
         t.bound[c].offsets = (const int *)ctx->boffsets[c].ptr;
@@ -999,6 +1003,8 @@ Plan1D plan_1d(const fds_ctx *ctx, long long steps_left) {
             // and tail) but leaves fewer owned cells per warp; short lines can afford it
             p.halo = n <= 592 * 64 ? 96 : n <= 1184 * 128 ? 64 : 32;
             if (ctx->halo_1d > 0) p.halo = std::min(112, (ctx->halo_1d + 7) / 8 * 8);
+            // a launch that can only advance a few steps (coupled fields: one) needs no wider halo
+            p.halo = (int)std::min<long long>(p.halo, (2 * steps_left + 7) / 8 * 8);
             p.tile = kLineWidth - 2 * p.halo;
             p.ctas = (n + p.tile - 1) / p.tile;
             p.steps = (int)std::min<long long>(steps_left, p.halo / 2);
@@ -1501,6 +1507,133 @@ int exchange_halos(fds_ctx *ctx, int which) {
 
 }  // namespace
 
+
+// =================================================================================================
+// coupled fields (SynchronizedFields with built-in interactions)
+// =================================================================================================
+
+struct fds_group {
+    struct Interaction {
+        int kind = 0;                 // 0 linear boundary coupling, 1 viscous heating, 2 material law
+        int src_member = 0, src_comp = 0, dst_member = 0, dst_comp = 0;
+        int additive = 1, accumulate = 0;
+        long long stepping = 1;
+        double scale = 0.0;
+        double *acc = nullptr;        // [n] sum since the last delivery (accumulate)
+        double *aux = nullptr;        // viscous heating: density | g | gain, [3][n]
+        double dt = 0.0;
+        fds::LawArgs law{};           // material law (device pointers filled in)
+        double *law_buffers = nullptr;   // statics [3][n] | last [n] | factors [n]
+        unsigned long long *law_max = nullptr;
+        int *law_count = nullptr;
+    };
+    std::vector<fds_ctx *> members;
+    std::vector<Interaction> interactions;
+    long long n = 0;
+    std::string err;
+};
+
+namespace {
+
+int gfail(fds_group *g, const std::string &msg) {
+    if (g) g->err = msg;
+    else {
+        std::lock_guard<std::mutex> lock(g_err_mutex);
+        g_create_error = msg;
+    }
+    return 1;
+}
+
+#define FDS_GCUDA(g, call)                                                               \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return gfail(g, std::string(#call) + ": " + cudaGetErrorString(e_));         \
+    } while (0)
+
+int group_alloc(fds_group *g, void **p, size_t bytes, const void *host) {
+    FDS_GCUDA(g, cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    if (host) FDS_GCUDA(g, cudaMemcpy(*p, host, bytes, cudaMemcpyHostToDevice));
+    else FDS_GCUDA(g, cudaMemset(*p, 0, std::max<size_t>(bytes, 16)));
+    return 0;
+}
+
+bool group_member_ok(const fds_group *g, int member, int comp) {
+    return member >= 0 && member < (int)g->members.size() && comp >= 0 && comp < 2;
+}
+
+// One 1-D step of one member on `stream`, recording probes into ring row `ring_row`.
+int group_member_step(fds_ctx *ctx, const StepTables &t, long long sig_index, long long ring_row) {
+    Plan1D p = plan_1d(ctx, 1);
+    Step1DArgs a{};
+    a.in[0] = origin(ctx, ctx->cur, 0);
+    a.in[1] = origin(ctx, ctx->cur, 1);
+    a.out[0] = origin(ctx, ctx->cur ^ 1, 0);
+    a.out[1] = origin(ctx, ctx->cur ^ 1, 1);
+    a.n = ctx->d.nx;
+    a.tile = p.tile;
+    a.halo = p.halo;
+    a.n_steps = 1;
+    a.sig_index = sig_index;
+    a.ring_row = ring_row;
+    int rc;
+    if (ctx->thermal) rc = launch_step1d<true, false>(ctx, a, t, p);
+    else if (ctx->d.lossy) rc = launch_step1d<false, true>(ctx, a, t, p);
+    else rc = launch_step1d<false, false>(ctx, a, t, p);
+    if (rc) return 1;
+    ctx->cur ^= 1;
+    ctx->last_kernel = p.per == 0 ? (ctx->thermal ? "line1d_kernel<thermal>"
+                                     : ctx->d.lossy ? "line1d_kernel<acoustic,lossy>"
+                                                    : "line1d_kernel<acoustic,lossless>")
+                                  : "step1d_kernel";
+    ctx->last_steps_per_launch = 1;
+    ctx->last_launches += 1;
+    return 0;
+}
+
+int group_apply(fds_group *g, fds_group::Interaction &it, long long step, cudaStream_t stream) {
+    const long long n = g->n;
+    const unsigned blocks = (unsigned)((n + kCoupleThreads - 1) / kCoupleThreads);
+    const bool due = it.stepping <= 1 || step % it.stepping == 0;
+    if (it.kind == 2) {
+        if (!due) return 0;
+        fds_ctx *src = g->members[(size_t)it.src_member];
+        LawArgs a = it.law;
+        a.source = origin(src, src->cur, it.src_comp);
+        a.cell_tab = g->members[(size_t)it.dst_member]->cell_tab;
+        if (a.has_threshold)
+            FDS_GCUDA(g, cudaMemsetAsync(a.max_bits, 0, sizeof(unsigned long long), stream));
+        couple_law_factors_kernel<<<blocks, kCoupleThreads, 0, stream>>>(a);
+        couple_law_assemble_kernel<<<blocks, kCoupleThreads, 0, stream>>>(a);
+        FDS_GCUDA(g, cudaGetLastError());
+        return 0;
+    }
+    if (!due && !it.accumulate) return 0;
+    fds_ctx *src = g->members[(size_t)it.src_member], *dst = g->members[(size_t)it.dst_member];
+    DeliverArgs d{};
+    d.target = origin(dst, dst->cur, it.dst_comp);
+    d.acc = it.accumulate ? it.acc : nullptr;
+    d.n = n;
+    d.additive = it.additive;
+    d.deliver = due ? 1 : 0;
+    if (it.kind == 0) {
+        couple_linear_kernel<<<blocks, kCoupleThreads, 0, stream>>>(
+            d, origin(src, src->cur, it.src_comp), it.scale);
+    } else {
+        HeatingArgs h{};
+        h.velocity = origin(src, src->cur, it.src_comp);
+        h.density = it.aux;
+        h.g = it.aux + n;
+        h.gain = it.aux + 2 * n;
+        h.dt = it.dt;
+        couple_viscous_heating_kernel<<<blocks, kCoupleThreads, 0, stream>>>(d, h);
+    }
+    FDS_GCUDA(g, cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
 // =================================================================================================
 // exported entry points
 // =================================================================================================
@@ -1683,6 +1816,7 @@ void fds_destroy(fds_ctx *ctx) {
             if (ctx->buf[b][c]) cudaFree(ctx->buf[b][c]);
     if (ctx->map) cudaFree(ctx->map);
     if (ctx->tab) cudaFree(ctx->tab);
+    if (ctx->cell_tab) cudaFree(ctx->cell_tab);
     if (ctx->ctab) cudaFree(ctx->ctab);
     if (ctx->cvec) cudaFree(ctx->cvec);
     for (int side = 0; side < 2; ++side) {
@@ -1762,6 +1896,34 @@ int fds_upload_table(fds_ctx *ctx, int32_t table, const double *values, int64_t 
     FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
     FDS_CUDA(ctx, cudaMemcpyAsync(ctx->tab + (size_t)table * kMaxMaterials, values, (size_t)n * 8,
                                   cudaMemcpyHostToDevice, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int fds_upload_cell_table(fds_ctx *ctx, int32_t table, const double *values, int64_t n) {
+    if (!ctx) return fail(ctx, "fds_upload_cell_table: null context");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    if (!values) {   // back to the per-material table
+        if (ctx->cell_tab) {
+            FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->cell_tab);
+            ctx->device_bytes -= (long long)sizeof(double) * FDS_TAB_COUNT * ctx->d.nx;
+            ctx->cell_tab = nullptr;
+        }
+        return 0;
+    }
+    if (ctx->dims != 1)
+        return fail(ctx, "fds_upload_cell_table: per-cell coefficients are supported for 1-D models");
+    if (ctx->d.kernel == 1)
+        return fail(ctx, "fds_upload_cell_table: the shared-memory 1-D kernel reads the material table "
+                         "only (use kernel 0)");
+    if (table < 0 || table >= FDS_TAB_COUNT) return fail(ctx, "fds_upload_cell_table: bad table id");
+    if (n != ctx->d.nx) return fail(ctx, "fds_upload_cell_table: expected nx values");
+    if (!ctx->cell_tab)
+        if (dev_alloc(ctx, (void **)&ctx->cell_tab, sizeof(double) * FDS_TAB_COUNT * (size_t)n, true))
+            return 1;
+    FDS_CUDA(ctx, cudaMemcpyAsync(ctx->cell_tab + (size_t)table * (size_t)n, values,
+                                  sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -2187,6 +2349,228 @@ int fds_peer_import(fds_ctx *ctx, int32_t side, const uint8_t *handles, int64_t 
     ctx->peer_flags[side] = (unsigned *)flags;
     ctx->peer_rows[side] = neighbour_rows;
     ctx->peer_open[side] = true;
+    return 0;
+}
+
+// ---- coupled fields ---------------------------------------------------------------------------------
+
+int fds_group_create(fds_ctx *const *members, int32_t n_members, fds_group **out) {
+    if (!members || !out || n_members < 1) return gfail(nullptr, "fds_group_create: bad arguments");
+    *out = nullptr;
+    for (int m = 0; m < n_members; ++m) {
+        if (!members[m]) return gfail(nullptr, "fds_group_create: null member");
+        if (members[m]->dims != 1)
+            return gfail(nullptr, "fds_group_create: device groups are built from 1-D fields");
+        if (members[m]->d.device != members[0]->d.device || members[m]->d.nx != members[0]->d.nx)
+            return gfail(nullptr, "fds_group_create: members must share the device and the line");
+        if (members[m]->d.kernel == 1)
+            return gfail(nullptr, "fds_group_create: members must use the default 1-D kernel");
+    }
+    fds_group *g = new fds_group();
+    g->members.assign(members, members + n_members);
+    g->n = members[0]->d.nx;
+    *out = g;
+    return 0;
+}
+
+void fds_group_destroy(fds_group *g) {
+    if (!g) return;
+    if (!g->members.empty()) {
+        cudaSetDevice(g->members[0]->d.device);
+        cudaStreamSynchronize(g->members[0]->stream);
+    }
+    for (auto &it : g->interactions) {
+        if (it.acc) cudaFree(it.acc);
+        if (it.aux) cudaFree(it.aux);
+        if (it.law_buffers) cudaFree(it.law_buffers);
+        if (it.law_max) cudaFree(it.law_max);
+        if (it.law_count) cudaFree(it.law_count);
+    }
+    delete g;
+}
+
+const char *fds_group_last_error(const fds_group *g) {
+    return g ? g->err.c_str() : g_create_error.c_str();
+}
+
+int fds_group_add_linear(fds_group *g, int32_t src_member, int32_t src_component,
+                         int32_t dst_member, int32_t dst_component, double scale, int32_t additive,
+                         int32_t accumulate, int64_t stepping, const double *accumulated) {
+    if (!g) return gfail(g, "fds_group_add_linear: null group");
+    if (!group_member_ok(g, src_member, src_component) ||
+        !group_member_ok(g, dst_member, dst_component) || stepping < 1)
+        return gfail(g, "fds_group_add_linear: bad member, component or stepping");
+    FDS_GCUDA(g, cudaSetDevice(g->members[0]->d.device));
+    fds_group::Interaction it;
+    it.kind = 0;
+    it.src_member = src_member; it.src_comp = src_component;
+    it.dst_member = dst_member; it.dst_comp = dst_component;
+    it.scale = scale;
+    it.additive = additive ? 1 : 0;
+    it.accumulate = accumulate ? 1 : 0;
+    it.stepping = stepping;
+    if (it.accumulate && group_alloc(g, (void **)&it.acc, sizeof(double) * (size_t)g->n, accumulated))
+        return 1;
+    g->interactions.push_back(it);
+    return 0;
+}
+
+int fds_group_add_viscous_heating(fds_group *g, int32_t sound_member, int32_t heat_member,
+                                  const double *density, const double *gradient_factor,
+                                  const double *gain, double dt, int32_t accumulate,
+                                  int64_t stepping, const double *accumulated) {
+    if (!g || !density || !gradient_factor || !gain)
+        return gfail(g, "fds_group_add_viscous_heating: null argument");
+    if (!group_member_ok(g, sound_member, 1) || !group_member_ok(g, heat_member, 0) || stepping < 1)
+        return gfail(g, "fds_group_add_viscous_heating: bad member or stepping");
+    if (g->members[(size_t)sound_member]->thermal || !g->members[(size_t)heat_member]->thermal)
+        return gfail(g, "fds_group_add_viscous_heating: needs an acoustic source and a thermal target");
+    FDS_GCUDA(g, cudaSetDevice(g->members[0]->d.device));
+    fds_group::Interaction it;
+    it.kind = 1;
+    it.src_member = sound_member; it.src_comp = 1;     // velocity
+    it.dst_member = heat_member; it.dst_comp = 0;      // temperature
+    it.additive = 1;
+    it.accumulate = accumulate ? 1 : 0;
+    it.stepping = stepping;
+    it.dt = dt;
+    const size_t n = (size_t)g->n;
+    std::vector<double> packed(3 * n);
+    memcpy(packed.data(), density, n * 8);
+    memcpy(packed.data() + n, gradient_factor, n * 8);
+    memcpy(packed.data() + 2 * n, gain, n * 8);
+    if (group_alloc(g, (void **)&it.aux, sizeof(double) * 3 * n, packed.data())) return 1;
+    if (it.accumulate && group_alloc(g, (void **)&it.acc, sizeof(double) * n, accumulated)) return 1;
+    g->interactions.push_back(it);
+    return 0;
+}
+
+int fds_group_add_material_law(fds_group *g, int32_t src_member, int32_t src_component,
+                               int32_t dst_member, int32_t parameter, int32_t law, double p0,
+                               double p1, int32_t has_threshold, double threshold,
+                               int64_t stepping, const double *statics, const double *last,
+                               const double *scalars) {
+    if (!g || !statics || !scalars) return gfail(g, "fds_group_add_material_law: null argument");
+    if (!group_member_ok(g, src_member, src_component) || !group_member_ok(g, dst_member, 0) ||
+        parameter < 0 || parameter > 2 || stepping < 1 || (law != kLawExponential && law != kLawPower))
+        return gfail(g, "fds_group_add_material_law: bad member, parameter, law or stepping");
+    fds_ctx *target = g->members[(size_t)dst_member];
+    if (!target->cell_tab)
+        return gfail(g, "fds_group_add_material_law: the target field needs per-cell coefficients "
+                        "(fds_upload_cell_table)");
+    FDS_GCUDA(g, cudaSetDevice(g->members[0]->d.device));
+    fds_group::Interaction it;
+    it.kind = 2;
+    it.src_member = src_member; it.src_comp = src_component;
+    it.dst_member = dst_member;
+    it.stepping = stepping;
+    const size_t n = (size_t)g->n;
+    std::vector<double> packed(5 * n, 0.0);
+    memcpy(packed.data(), statics, 3 * n * 8);
+    if (last) memcpy(packed.data() + 3 * n, last, n * 8);
+    if (group_alloc(g, (void **)&it.law_buffers, sizeof(double) * 5 * n, packed.data())) return 1;
+    if (group_alloc(g, (void **)&it.law_max, sizeof(unsigned long long), nullptr)) return 1;
+    if (group_alloc(g, (void **)&it.law_count, sizeof(int), nullptr)) return 1;
+    LawArgs &a = it.law;
+    a.statics = it.law_buffers;
+    a.last = it.law_buffers + 3 * n;
+    a.factors = it.law_buffers + 4 * n;
+    a.max_bits = it.law_max;
+    a.reassemblies = it.law_count;
+    a.n = g->n;
+    a.law = law;
+    a.p0 = p0;
+    a.p1 = p1;
+    a.p2 = 1.0 - p0;                // exponential: (1 - a), as Python evaluates it
+    a.has_threshold = has_threshold ? 1 : 0;
+    a.threshold = threshold;
+    a.target_model = target->thermal ? kTargetThermal1D : kTargetAcoustic1D;
+    a.parameter = parameter;
+    a.k_dtdx = scalars[0];
+    a.k_dtdx2 = scalars[1];
+    a.k_inv_dx = scalars[2];
+    g->interactions.push_back(it);
+    return 0;
+}
+
+int fds_group_read(fds_group *g, int32_t interaction, double *values, int64_t *reassemblies) {
+    if (!g || interaction < 0 || interaction >= (int)g->interactions.size())
+        return gfail(g, "fds_group_read: bad interaction");
+    FDS_GCUDA(g, cudaSetDevice(g->members[0]->d.device));
+    FDS_GCUDA(g, cudaStreamSynchronize(g->members[0]->stream));
+    const fds_group::Interaction &it = g->interactions[(size_t)interaction];
+    const size_t bytes = sizeof(double) * (size_t)g->n;
+    if (reassemblies) *reassemblies = 0;
+    if (it.kind == 2) {
+        if (values) FDS_GCUDA(g, cudaMemcpy(values, it.law.last, bytes, cudaMemcpyDeviceToHost));
+        int count = 0;
+        FDS_GCUDA(g, cudaMemcpy(&count, it.law_count, sizeof(int), cudaMemcpyDeviceToHost));
+        if (reassemblies) *reassemblies = count;
+    } else if (values) {
+        if (it.acc) FDS_GCUDA(g, cudaMemcpy(values, it.acc, bytes, cudaMemcpyDeviceToHost));
+        else memset(values, 0, bytes);
+    }
+    return 0;
+}
+
+int fds_group_step(fds_group *g, int64_t first_step, int64_t n_steps, double *const *probes_out) {
+    if (!g) return gfail(g, "fds_group_step: null group");
+    if (n_steps <= 0) return 0;
+    NvtxRange nvtx_range("fds:group step");
+    const size_t nm = g->members.size();
+    FDS_GCUDA(g, cudaSetDevice(g->members[0]->d.device));
+    cudaStream_t stream = g->members[0]->stream;
+    std::vector<StepTables> tables(nm);
+    std::vector<cudaStream_t> own(nm);
+    long long chunk = n_steps;
+    auto member_fail = [&](fds_ctx *ctx) { return gfail(g, "fds_group_step: " + ctx->err); };
+    for (size_t m = 0; m < nm; ++m) {
+        fds_ctx *ctx = g->members[m];
+        if (!ctx->map_uploaded) return gfail(g, "fds_group_step: material map not uploaded");
+        if (ctx->n_signals > 0 && (first_step < ctx->sig_first ||
+                                   first_step + n_steps > ctx->sig_first + ctx->sig_steps))
+            return gfail(g, "fds_group_step: step range outside the uploaded signal window");
+        if (ctx->n_slots > 0 && (!probes_out || !probes_out[m]))
+            return gfail(g, "fds_group_step: probes are configured but probes_out is NULL");
+        if (refresh_flags(ctx) || ensure_ring(ctx, n_steps)) return member_fail(ctx);
+        FDS_GCUDA(g, cudaStreamSynchronize(ctx->stream));   // everything runs on the first stream
+        if (ctx->n_slots > 0) chunk = std::min(chunk, ctx->ring_half);
+        ctx->last_launches = 0;
+    }
+    // the members' launches go to one stream: their order on it is the order of sim_step
+    for (size_t m = 0; m < nm; ++m) {
+        own[m] = g->members[m]->stream;
+        g->members[m]->stream = stream;
+        tables[m] = make_tables(g->members[m]);
+    }
+    int rc = 0;
+    cudaError_t e = cudaEventRecord(g->members[0]->ev_t0, stream);
+    for (long long done = 0; done < n_steps && !rc && e == cudaSuccess; done += chunk) {
+        const long long count = std::min(chunk, n_steps - done);
+        for (long long s = 0; s < count && !rc; ++s) {
+            const long long step = first_step + done + s;
+            for (size_t m = 0; m < nm && !rc; ++m) {
+                fds_ctx *ctx = g->members[m];
+                rc = group_member_step(ctx, tables[m], step - ctx->sig_first, s);
+                if (rc) g->err = "fds_group_step: " + ctx->err;
+            }
+            for (auto &it : g->interactions)
+                if (!rc) rc = group_apply(g, it, step, stream);
+        }
+        for (size_t m = 0; m < nm && !rc; ++m) {
+            fds_ctx *ctx = g->members[m];
+            if (ctx->n_slots == 0) continue;
+            e = cudaMemcpyAsync(probes_out[m] + done * ctx->n_slots, ctx->ring.ptr,
+                                (size_t)count * ctx->n_slots * 8, cudaMemcpyDeviceToHost, stream);
+            if (e != cudaSuccess) break;
+        }
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(g->members[0]->ev_t1, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    for (size_t m = 0; m < nm; ++m) g->members[m]->stream = own[m];
+    g->members[0]->timed = true;
+    if (rc) return 1;
+    if (e != cudaSuccess) return gfail(g, std::string("fds_group_step: ") + cudaGetErrorString(e));
     return 0;
 }
 

@@ -1,6 +1,6 @@
 // Passes that sit either side of the leapfrog step: the medium-flow row shift of
-// AcousticFlow2D, decimated field snapshots for visualisation, and the device form of the built-in
-// boundary couplings. All pure data movement or element-wise fp64 with the reference's operation order.
+// AcousticFlow2D and decimated field snapshots for visualisation: pure data movement. (The interactions
+// of coupled fields live in fds_couple.cuh.)
 #pragma once
 
 #include "fds_common.cuh"
@@ -62,26 +62,6 @@ __global__ void snapshot_kernel(SnapshotArgs a) {
          k += (long long)gridDim.x * blockDim.x) {
         const long long y = k / a.fx, x = k - y * a.fx;
         a.frame[k] = __ldg(a.state + y * a.stride_y * a.nx + x * a.stride_x);
-    }
-}
-
-// ---- BoundaryCoupling.apply with a linear transfer function (pyfds/coupling.py:118-140) -------------
-// target (+)= scale * source  between two contexts on the same device (e.g. two fields of a
-// SynchronizedFields). One multiply and, if additive, one add per cell, IEEE RN, never fused -- what
-// NumPy computes for `target.values += scale * source.values`.
-struct CoupleArgs {
-    const double *source;
-    double *target;
-    long long n;
-    double scale;
-    int additive;
-};
-
-__global__ void couple_linear_kernel(CoupleArgs a) {
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < a.n;
-         k += (long long)gridDim.x * blockDim.x) {
-        const double t = mul(a.scale, a.source[k]);
-        a.target[k] = a.additive ? add(a.target[k], t) : t;
     }
 }
 

@@ -65,6 +65,10 @@ struct StepTables {
     const double *tab;         // [FDS_TAB_COUNT][kMaxMaterials]
     const double *ctab;        // [FDS_CTAB_COUNT][n_materials + 1][nx]   (axisymmetric only)
     const double *cvec;        // [FDS_CVEC_COUNT][nx]                    (axisymmetric only)
+    // 1-D fields whose materials vary from cell to cell (MaterialCoupling, pyfds/coupling.py:143-215):
+    // per-cell coefficients [FDS_TAB_COUNT][cell_n] instead of the per-material table (null otherwise)
+    const double *cell_tab;
+    long long cell_n;
     BoundTable bound[3];
     ProbeTable probe[3];
     const double *signals;     // [n_signals][sig_steps]

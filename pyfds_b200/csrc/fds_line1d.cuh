@@ -144,12 +144,19 @@ __global__ void __launch_bounds__(32 * kLineWarps, 1) line1d_kernel(Step1DArgs a
         u[c] = THERMAL ? 0.0 : a.in[1][g];
         id[c] = t.map[g];
         const int m = id[c] & kIdMask;
-        gx[c] = __ldg(t.tab + FDS_TAB_GX * kMaxMaterials + m);
-        fx[c] = __ldg(t.tab + FDS_TAB_FX * kMaxMaterials + m);
+        // coefficients by material, or by cell where the materials vary from cell to cell (cells
+        // outside the line are void: all coefficients zero). The per-cell arrays are rewritten between
+        // launches by the material couplings: plain loads, not the read-only path.
+        auto coefficient = [&](int table) {
+            if (t.cell_tab) return m ? t.cell_tab[(long long)table * t.cell_n + g] : 0.0;
+            return __ldg(t.tab + table * kMaxMaterials + m);
+        };
+        gx[c] = coefficient(FDS_TAB_GX);
+        fx[c] = coefficient(FDS_TAB_FX);
         if (LOSSY) {
-            v0[c] = __ldg(t.tab + FDS_TAB_V0 * kMaxMaterials + m);
-            vm1[c] = __ldg(t.tab + FDS_TAB_VM1 * kMaxMaterials + m);
-            vp1[c] = __ldg(t.tab + FDS_TAB_VP1 * kMaxMaterials + m);
+            v0[c] = coefficient(FDS_TAB_V0);
+            vm1[c] = coefficient(FDS_TAB_VM1);
+            vp1[c] = coefficient(FDS_TAB_VP1);
         }
         if (id[c] & (kFlagBound | kFlagProbe | kClassMask)) special |= 1u << c;
         if (m) real |= 1u << c;
