@@ -105,7 +105,7 @@ def frames(size, steps, steps_per_frame=20, decimate=(4, 4)):
         'frame_bytes': int(frame.nbytes)}), flush=True)
 
 
-def coupled(nx=10000, steps=2000):
+def coupled(nx=10000, steps=20000):
     def build():
         f = fds.ThermoAcoustic1D(x_samples=nx, x_delta=1e-3, t_samples=steps + 50, t_delta=1e-7,
                                  thermal_material=fds.ThermalMaterial(900, 2700, 200),
@@ -115,7 +115,7 @@ def coupled(nx=10000, steps=2000):
                                           value=np.sin(0.05 * np.arange(steps + 50)), additive=True)
         f.fields[1].temperature.add_output(f.fields[1].get_point_region(1001 * 1e-3))
         return f
-    rates = {}
+    rates, sessions = {}, {}
     for mode in ('session', 'per_step'):
         f = build()
         f.device_session = mode == 'session'
@@ -124,11 +124,12 @@ def coupled(nx=10000, steps=2000):
         t0 = time.perf_counter()
         f.simulate(n)
         rates[mode] = n / (time.perf_counter() - t0)
+        sessions[mode] = getattr(f, '_last_session', None)
     print(json.dumps({
         'row': 'coupled', 'workload': 'ThermoAcoustic1D {} cells, viscous loss -> temperature every '
                                       'step'.format(nx),
         'value': rates['session'], 'unit': 'steps/s', 'per_step_seam_steps_per_s': rates['per_step'],
-        'steps': steps}), flush=True)
+        'session': sessions['session'], 'steps': steps}), flush=True)
 
 
 def main():

@@ -168,6 +168,19 @@ int fds_step(fds_ctx *ctx, int64_t first_step, int64_t n_steps, double *probes_o
 int fds_step_async(fds_ctx *ctx, int64_t first_step, int64_t n_steps);
 int fds_sync(fds_ctx *ctx);
 
+/* `Field.simulate(n)` of a field that lives in host arrays (pyfds/fields.py:67-95) in ONE call:
+ * values_in[c] -> device, n_steps steps, device -> values_out[c] (c < 2 for 1-D, 3 for 2-D models; owned
+ * cells each; in and out may be the same arrays), probe records to probes_out as fds_step does. For
+ * short calls on large 2-D grids the three phases are overlapped by row bands: band j is uploaded while
+ * the steps advance the rows uploaded so far as far as their dependency cone allows and finished rows
+ * are downloaded -- the call then takes about as long as the slower PCIe direction instead of the sum of
+ * both. Results are bit-identical to upload + fds_step + download. Page-lock the arrays
+ * (fds_host_register) for the copies to run asynchronously. Single-slab contexts. */
+int fds_simulate(fds_ctx *ctx, int64_t first_step, int64_t n_steps, const double *const *values_in,
+                 double *const *values_out, double *probes_out);
+/* Row bands the last fds_simulate call was cut into (0: it ran the three phases back to back). */
+int fds_last_pipeline_bands(fds_ctx *ctx, int64_t *bands);
+
 /* --- the step after the hot path: medium flow ------------------------------- */
 
 /* `AcousticFlow2D.apply_flow` (pyfds/acoustic_flow.py:49-57) on the device: after leapfrog step s every

@@ -84,6 +84,8 @@ def load_library():
         'fds_reset_state': (ct.c_int, [p]),
         'fds_step': (ct.c_int, [p, i64, i64, p]),
         'fds_step_async': (ct.c_int, [p, i64, i64]),
+        'fds_simulate': (ct.c_int, [p, i64, i64, ct.POINTER(p), ct.POINTER(p), p]),
+        'fds_last_pipeline_bands': (ct.c_int, [p, ct.POINTER(i64)]),
         'fds_sync': (ct.c_int, [p]),
         'fds_set_flow': (ct.c_int, [p, p, i64]),
         'fds_last_flow_shifts': (ct.c_int, [p, ct.POINTER(i64)]),
@@ -228,6 +230,21 @@ class Engine:
         self._check(self.lib.fds_step(self.handle, first_step, n_steps,
                                       _ptr(probes) if n_slots else None))
         return probes
+
+    def simulate(self, first_step, n_steps, values_in, values_out, n_slots):
+        """Upload, ``n_steps`` steps and download in one call (``fds_simulate``: overlapped by row
+        bands where that pays); returns the probe records [n_steps][n_slots]."""
+        probes = np.zeros((n_steps, n_slots), dtype=np.float64)
+        ins = (ct.c_void_p * len(values_in))(*[a.ctypes.data for a in values_in])
+        outs = (ct.c_void_p * len(values_out))(*[a.ctypes.data for a in values_out])
+        self._check(self.lib.fds_simulate(self.handle, first_step, n_steps, ins, outs,
+                                          _ptr(probes) if n_slots else None))
+        return probes
+
+    def last_pipeline_bands(self):
+        bands = ct.c_int64()
+        self._check(self.lib.fds_last_pipeline_bands(self.handle, ct.byref(bands)))
+        return bands.value
 
     def step_async(self, first_step, n_steps):
         self._check(self.lib.fds_step_async(self.handle, first_step, n_steps))
@@ -519,12 +536,18 @@ def upload_run_tables(field, engine, first_step, n_steps):
     # all grid rows: every slab derives the same launch schedule from them (fds_set_flow)
     engine.set_flow(periods)
     signals = []
+    sent = engine.__dict__.setdefault('_sent_tables', {})
     for c, component in enumerate(_components(field)):
         table = _bake.boundary_table(component.boundaries, first_step, n_steps, engine.cell_lo,
                                      engine.cell_hi, signals)
         # the device addresses cells relative to the first *owned* cell
         table.cells = table.cells - engine.halo_rows * nx
-        engine.upload_boundaries(c, table)
+        # Unchanged since the last call (an animator calling simulate(20) again and again): nothing to
+        # send -- an upload marks the cell flags dirty and with them the task tables of the kernels.
+        mark = _fingerprint(table.cells, table.offsets, table.alpha, table.value, table.signal)
+        if sent.get(('bounds', c)) != mark:
+            engine.upload_boundaries(c, table)
+            sent[('bounds', c)] = mark
     engine.upload_signals(np.array(signals, dtype=np.float64).reshape(len(signals), n_steps)
                           if signals else np.zeros((0, 0)), first_step)
 
@@ -541,8 +564,21 @@ def upload_run_tables(field, engine, first_step, n_steps):
         cells, slots, _ = _bake.probe_table(component.outputs, base, own_lo, own_hi)
         tables.append((c, cells, slots))
     for c, cells, slots in tables:
-        engine.upload_probes(c, cells, slots, slot)
+        mark = _fingerprint(cells, slots, np.asarray([slot]))
+        if sent.get(('probes', c)) != mark:
+            engine.upload_probes(c, cells, slots, slot)
+            sent[('probes', c)] = mark
     return slot, layout
+
+
+def _fingerprint(*arrays):
+    import hashlib
+    digest = hashlib.blake2b(digest_size=16)
+    for array in arrays:
+        array = np.ascontiguousarray(array)
+        digest.update(str((array.dtype.str, array.shape)).encode())
+        digest.update(array.tobytes())
+    return digest.digest()
 
 
 def _append_signals(layout, records):
@@ -612,14 +648,46 @@ def run(field, n_steps, progress_logger=None, advance=True):
     first_step = field.step
     n_slots, layout = upload_run_tables(field, engine, first_step, n_steps)
     t1 = clock()
-    lock_s, upload_s = upload_values(field, engine)
-    t2 = clock()
 
     chunk = n_steps
     if n_slots:
         chunk = max(1, min(chunk, MAX_PROBE_BYTES // (8 * n_slots)))
     if progress_logger is not None:
         chunk = max(1, min(chunk, -(-n_steps // 20)))
+    if chunk == n_steps and getattr(field, 'device_single_call', True):
+        # the whole call in one engine call: values up, steps, values down (fds_simulate)
+        state = field.__dict__['_engine_state']
+        components = _components(field)
+        ins, outs = [], []
+        for c, component in enumerate(components):
+            values = _host_values(component, field.num_points)
+            own = component.values
+            in_place = isinstance(own, np.ndarray) and own.ctypes.data == values.ctypes.data and \
+                own.nbytes == values.nbytes and own.flags.writeable
+            if in_place:
+                state.pin(engine.lib, c, own)
+            ins.append(values)
+            outs.append(values if in_place else np.empty(field.num_points, dtype=np.float64))
+        t2 = clock()
+        records = engine.simulate(first_step, n_steps, ins, outs, n_slots)
+        for component, result in zip(components, outs):
+            if component.values is not result:
+                component.values = result
+        t3 = clock()
+        if n_slots:
+            _append_signals(layout, records)
+        if progress_logger is not None:
+            for s in range(first_step, first_step + n_steps):
+                progress_logger.log(s)
+        field.__dict__['_last_run_profile'] = {
+            'prepare_and_tables_s': t1 - t0, 'page_lock_s': t2 - t1, 'simulate_call_s': t3 - t2,
+            'signals_s': clock() - t3, 'pipeline_bands': engine.last_pipeline_bands()}
+        if advance:
+            field.step += n_steps
+        return
+
+    lock_s, upload_s = upload_values(field, engine)
+    t2 = clock()
     done = 0
     while done < n_steps:
         count = min(chunk, n_steps - done)

@@ -210,6 +210,10 @@ struct fds_ctx {
     long long frame_n[2] = {0, 0};
     cudaEvent_t ev_frame_ready[2] = {nullptr, nullptr}, ev_frame_done[2] = {nullptr, nullptr};
 
+    // fds_simulate: per row band one event "uploaded" and one "final rows stored"
+    std::vector<cudaEvent_t> band_events;
+    long long last_bands = 0;          // bands the last fds_simulate call was cut into (0: not pipelined)
+
     std::string err;
 };
 
@@ -1508,6 +1512,155 @@ int exchange_halos(fds_ctx *ctx, int which) {
 }  // namespace
 
 
+namespace {
+
+// ---- Field.simulate in one call: upload, steps and download overlapped by row bands ---------------
+// A call that advances few steps is bound by the two PCIe transfers of the state (4096^2: 7 ms up,
+// 1 ms of stepping, 7 ms down). The grid is cut into bands of rows; band j is uploaded on one stream
+// while the compute stream advances what the rows uploaded so far allow -- launch l (k_l steps, S_l
+// steps done after it) may produce the rows below  r1_j - reach * S_l  once band j (rows below r1_j)
+// has arrived, the dependency cone of a step being `reach` rows -- and a third stream downloads the
+// rows that have reached the final level. PCIe is full duplex, so the call takes about as long as the
+// slower of the two transfers instead of their sum. Launches run over row ranges of the same
+// ping-pong buffers: launch l reads buffer (cur + l) & 1 and writes the other one; a short first
+// launch (n_steps not a multiple of the kernel's steps per launch) keeps k_l non-decreasing, which is
+// what keeps the rows a launch overwrites clear of the rows an earlier launch of the NEXT band still
+// has to read.
+bool pipeline_applies(const fds_ctx *ctx, long long n_steps) {
+    if (getenv("FDS_NO_PIPELINE")) return false;
+    if (ctx->dims != 2 || !(ctx->use_stream2d || ctx->use_streamv)) return false;
+    if ((ctx->comm && ctx->world > 1) || ctx->flow) return false;
+    const int k = std::min(ctx->max_k, stream_max_steps(ctx));
+    const long long launches = (n_steps + k - 1) / k;
+    if (launches > 16) return false;                   // long runs: the transfers do not matter
+    const long long reach = ctx->d.lossy ? 2 : 1;
+    // worth it from ~100 MB per component and as long as bands stay much taller than what a call's
+    // steps eat off their upper end
+    return ctx->d.rows >= 8 * (reach * n_steps + 64) && ctx->owned >= (8ll << 20);
+}
+
+int simulate_pipelined(fds_ctx *ctx, long long first_step, long long n_steps,
+                       const double *const *in, double *const *out) {
+    NvtxRange nvtx_range("fds:simulate pipelined");
+    const long long rows = ctx->d.rows, nx = ctx->d.nx;
+    const long long reach = ctx->d.lossy ? 2 : 1;
+    const int kmax = std::min(ctx->max_k, stream_max_steps(ctx));
+    std::vector<int> ks;                                // steps per launch, shortest first
+    if (n_steps % kmax) ks.push_back((int)(n_steps % kmax));
+    for (long long l = 0; l < n_steps / kmax; ++l) ks.push_back(kmax);
+    const int L = (int)ks.size();
+    std::vector<long long> done_after(L);               // S_l
+    for (int l = 0, acc = 0; l < L; ++l) done_after[l] = (acc += ks[l]);
+
+    long long bands = 8;
+    if (const char *env = getenv("FDS_PIPELINE_BANDS")) bands = std::max(2, atoi(env));
+    const long long band_rows = std::max<long long>((rows + bands - 1) / bands, reach * n_steps + 64);
+    bands = (rows + band_rows - 1) / band_rows;
+    while ((long long)ctx->band_events.size() < 2 * bands) {
+        cudaEvent_t ev;
+        FDS_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->band_events.push_back(ev);
+    }
+    ctx->last_bands = bands;
+
+    if (refresh_flags(ctx)) return 1;
+    if (ensure_ring(ctx, n_steps)) return 1;
+    if (ctx->n_slots > 0 && ctx->ring_half < n_steps)
+        return fail(ctx, "fds_simulate: probe ring too small");   // (callers chunk long runs)
+    if (ctx->n_slots > 0) {
+        const size_t need = (size_t)n_steps * ctx->n_slots * 8;
+        if (ctx->pinned_bytes < need) {
+            if (ctx->pinned) cudaFreeHost(ctx->pinned);
+            ctx->pinned = nullptr;
+            ctx->pinned_bytes = 0;
+            const size_t alloc_bytes = std::max<size_t>(need, 1u << 20);
+            FDS_CUDA(ctx, cudaHostAlloc(&ctx->pinned, alloc_bytes, cudaHostAllocPortable));
+            ctx->pinned_bytes = alloc_bytes;
+        }
+    }
+    StepTables t = make_tables(ctx);
+    FDS_CUDA(ctx, cudaMemcpyAsync(ctx->d_tables, &t, sizeof(StepTables), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    cudaStream_t up = ctx->comm_stream, down = ctx->drain;
+    // nothing of an earlier call may still be in flight on the side streams
+    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
+    FDS_CUDA(ctx, cudaStreamWaitEvent(up, ctx->ev_edge, 0));
+    FDS_CUDA(ctx, cudaStreamWaitEvent(down, ctx->ev_edge, 0));
+
+    const int cur = ctx->cur;
+    const int n_up = ctx->thermal ? 1 : 3;    // thermal fluxes are derived: never read
+    for (long long j = 0; j < bands; ++j) {
+        const long long r0 = j * band_rows, r1 = std::min(rows, r0 + band_rows);
+        for (int c = 0; c < n_up; ++c)
+            FDS_CUDA(ctx, cudaMemcpyAsync(origin(ctx, cur, c) + r0 * nx, in[c] + r0 * nx,
+                                          (size_t)((r1 - r0) * nx) * 8, cudaMemcpyHostToDevice, up));
+        FDS_CUDA(ctx, cudaEventRecord(ctx->band_events[(size_t)(2 * j)], up));
+    }
+    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    ctx->last_launches = 0;
+    ctx->last_steps_per_launch = kmax;
+    ctx->flow_shifts = 0;
+    ctx->chain_tasks = nullptr;
+    const long long sig0 = first_step - ctx->sig_first;
+    std::vector<long long> produced(L, 0);              // rows [0, produced[l]) exist at level S_l
+    long long downloaded = 0;
+    const int final_buffer = (cur + L) & 1;
+    for (long long j = 0; j < bands; ++j) {
+        const long long r1 = std::min(rows, (j + 1) * band_rows);
+        FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->band_events[(size_t)(2 * j)], 0));
+        for (int l = 0; l < L; ++l) {
+            const long long hi = j == bands - 1 ? rows : r1 - reach * done_after[l];
+            const long long lo = produced[l];
+            if (hi <= lo) continue;
+            Stream2DArgs a{};
+            for (int c = 0; c < 3; ++c) {
+                a.in[c] = origin(ctx, (cur + l) & 1, c);
+                a.out[c] = origin(ctx, (cur + l + 1) & 1, c);
+            }
+            a.nx = nx;
+            const long long before = l ? done_after[l - 1] : 0;
+            a.sig_index = sig0 + before;
+            a.ring_row = before;
+            a.write_vector = l == L - 1;
+            a.sync.seq = ++ctx->launch_seq;
+            a.sync.error = ctx->flags + kFlagError;
+            a.row_begin = lo;
+            a.row_end = hi;
+            ctx->chain_tasks = nullptr;                 // every launch has a task table of its own
+            if (dispatch_stream2d(ctx, a, ks[l])) return 1;
+            ctx->last_launches += 1;
+            produced[l] = hi;
+        }
+        const long long fin = produced[L - 1];
+        if (fin > downloaded) {
+            FDS_CUDA(ctx, cudaEventRecord(ctx->band_events[(size_t)(2 * j + 1)], ctx->stream));
+            FDS_CUDA(ctx, cudaStreamWaitEvent(down, ctx->band_events[(size_t)(2 * j + 1)], 0));
+            for (int c = 0; c < 3; ++c)
+                FDS_CUDA(ctx, cudaMemcpyAsync(out[c] + downloaded * nx,
+                                              origin(ctx, final_buffer, c) + downloaded * nx,
+                                              (size_t)((fin - downloaded) * nx) * 8,
+                                              cudaMemcpyDeviceToHost, down));
+            downloaded = fin;
+        }
+    }
+    ctx->chain_tasks = nullptr;
+    FDS_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+    ctx->timed = true;
+    ctx->cur = final_buffer;
+    ctx->last_kernel = ctx->use_streamv
+                           ? (ctx->d.model == FDS_ACOUSTIC3DAXI ? "streamv_kernel<acoustic3daxi,lossy>"
+                                                                : "streamv_kernel<acoustic2d,lossy>")
+                       : ctx->axi ? (ctx->thermal ? "stream2d_kernel<thermal3daxi>"
+                                                  : "stream2d_kernel<acoustic3daxi,lossless>")
+                                  : (ctx->thermal ? "stream2d_kernel<thermal2d>"
+                                                  : "stream2d_kernel<acoustic2d,lossless>");
+    if (ctx->n_slots > 0)   // all records exist once the last launch is done (stream order)
+        FDS_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, ctx->ring.ptr, (size_t)n_steps * ctx->n_slots * 8,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    return 0;
+}
+}  // namespace
+
 // =================================================================================================
 // coupled fields (SynchronizedFields with built-in interactions)
 // =================================================================================================
@@ -1850,6 +2003,7 @@ void fds_destroy(fds_ctx *ctx) {
         if (ctx->ev_frame_done[slot]) cudaEventDestroy(ctx->ev_frame_done[slot]);
     }
 
+    for (cudaEvent_t ev : ctx->band_events) cudaEventDestroy(ev);
     cudaEvent_t events[] = {ctx->ev_half[0], ctx->ev_half[1], ctx->ev_drained[0], ctx->ev_drained[1],
                             ctx->ev_t0, ctx->ev_t1, ctx->ev_edge, ctx->ev_comm};
     for (cudaEvent_t ev : events)
@@ -2161,6 +2315,53 @@ int fds_step(fds_ctx *ctx, int64_t first_step, int64_t n_steps, double *probes_o
                     if (mine[(size_t)k]) probes_out[s * ctx->n_slots + k] = src[s * ctx->n_slots + k];
         }
     }
+    return 0;
+}
+
+int fds_simulate(fds_ctx *ctx, int64_t first_step, int64_t n_steps, const double *const *values_in,
+                 double *const *values_out, double *probes_out) {
+    NvtxRange nvtx_range("fds:simulate");
+    if (!ctx || !values_in || !values_out) return fail(ctx, "fds_simulate: null argument");
+    if (n_steps <= 0) return fail(ctx, "fds_simulate: needs at least one step");
+    for (int c = 0; c < ctx->ncomp; ++c)
+        if (!values_in[c] || !values_out[c]) return fail(ctx, "fds_simulate: null component array");
+    if (ctx->n_slots > 0 && !probes_out)
+        return fail(ctx, "fds_simulate: probes are configured but probes_out is NULL");
+    if (!ctx->map_uploaded) return fail(ctx, "fds_simulate: material map not uploaded");
+    if (ctx->n_signals > 0 &&
+        (first_step < ctx->sig_first || first_step + n_steps > ctx->sig_first + ctx->sig_steps))
+        return fail(ctx, "fds_simulate: step range outside the uploaded signal window");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    ctx->last_bands = 0;
+    bool pipelined = pipeline_applies(ctx, n_steps);
+    if (pipelined && ctx->n_slots > 0) {
+        // all probe records of the call must fit the device ring (they are drained at the end)
+        const long long budget = (32ll << 20) / (ctx->n_slots * 8);
+        if (n_steps > std::max<long long>(budget, 64)) pipelined = false;
+    }
+    if (pipelined) {
+        if (simulate_pipelined(ctx, first_step, n_steps, values_in, values_out)) return 1;
+    } else {
+        // the same three phases back to back: copies of all components enqueued together, one wait
+        for (int c = 0; c < ctx->ncomp; ++c)
+            FDS_CUDA(ctx, cudaMemcpyAsync(origin(ctx, ctx->cur, c), values_in[c],
+                                          (size_t)ctx->owned * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (run_steps(ctx, first_step, n_steps, true)) return 1;
+        for (int c = 0; c < ctx->ncomp; ++c)
+            FDS_CUDA(ctx, cudaMemcpyAsync(values_out[c], origin(ctx, ctx->cur, c),
+                                          (size_t)ctx->owned * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (check_device_waits(ctx)) return 1;
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->drain));
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
+    if (ctx->n_slots > 0)
+        memcpy(probes_out, ctx->pinned, (size_t)n_steps * ctx->n_slots * 8);
+    return 0;
+}
+
+int fds_last_pipeline_bands(fds_ctx *ctx, int64_t *bands) {
+    if (!ctx || !bands) return fail(ctx, "fds_last_pipeline_bands: null argument");
+    *bands = ctx->last_bands;
     return 0;
 }
 
