@@ -141,6 +141,14 @@ struct fds_ctx {
         int n_edge[2] = {0, 0};   // tasks that own rows of the lower / upper edge band
     };
     std::vector<StreamPlan> plans;
+    // Task tables live in an arena (device memory + page-locked staging of the same size): building one
+    // costs neither a cudaMalloc nor a synchronisation, which matters when fds_simulate builds dozens
+    // of them between launches while copies are in flight.
+    struct PlanChunk {
+        char *dev = nullptr, *host = nullptr;
+        size_t capacity = 0, used = 0;
+    };
+    std::vector<PlanChunk> plan_chunks;
     std::vector<int> strip_nonplain;   // [strip][block of kCensusBlockRows rows]
     int census_blocks = 0;
     bool census_valid = false;
@@ -604,13 +612,8 @@ int strip_census(fds_ctx *ctx, int n_strips) {
 void invalidate_plans(fds_ctx *ctx) {
     if (!ctx->plans.empty()) {
         cudaStreamSynchronize(ctx->stream);
-        for (auto &p : ctx->plans) {
-            if (p.tasks) cudaFree(p.tasks);
-            if (p.dep_ptr) cudaFree(p.dep_ptr);
-            if (p.dep_idx) cudaFree(p.dep_idx);
-            if (p.done) cudaFree(p.done);
-        }
         ctx->plans.clear();
+        for (auto &chunk : ctx->plan_chunks) chunk.used = 0;   // the memory is kept for the next tables
     }
     ctx->chain_tasks = nullptr;
     ctx->census_valid = false;
@@ -822,20 +825,39 @@ int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int
             dep_ptr[i + 1] = (int)dep_idx.size();
         }
     }
-    void *dev = nullptr;
-    if (dev_alloc(ctx, &dev, tasks.size() * sizeof(int4), false)) return 1;
+    // one block in the arena: tasks | dep_ptr | dep_idx | done (zero), staged in page-locked memory and
+    // sent with one asynchronous copy ahead of the launches that read it (same stream)
+    auto align16 = [](size_t b) { return (b + 15) / 16 * 16; };
+    const size_t off_ptr = align16(tasks.size() * sizeof(int4));
+    const size_t off_idx = off_ptr + align16(dep_ptr.size() * sizeof(int));
+    const size_t off_done = off_idx + align16(dep_idx.size() * sizeof(int));
+    const size_t bytes = off_done + align16(tasks.size() * sizeof(unsigned));
+    fds_ctx::PlanChunk *chunk = nullptr;
+    for (auto &c : ctx->plan_chunks)
+        if (c.capacity - c.used >= bytes) { chunk = &c; break; }
+    if (!chunk) {
+        fds_ctx::PlanChunk fresh;
+        fresh.capacity = std::max<size_t>(bytes, 8u << 20);
+        FDS_CUDA(ctx, cudaMalloc((void **)&fresh.dev, fresh.capacity));
+        if (cudaHostAlloc((void **)&fresh.host, fresh.capacity, cudaHostAllocPortable) != cudaSuccess) {
+            cudaFree(fresh.dev);
+            return fail(ctx, "build_stream_plan: cudaHostAlloc failed");
+        }
+        ctx->device_bytes += (long long)fresh.capacity;
+        ctx->plan_chunks.push_back(fresh);
+        chunk = &ctx->plan_chunks.back();
+    }
+    char *host = chunk->host + chunk->used, *dev = chunk->dev + chunk->used;
+    chunk->used += bytes;
+    memset(host, 0, bytes);
+    memcpy(host, tasks.data(), tasks.size() * sizeof(int4));
+    memcpy(host + off_ptr, dep_ptr.data(), dep_ptr.size() * sizeof(int));
+    if (!dep_idx.empty()) memcpy(host + off_idx, dep_idx.data(), dep_idx.size() * sizeof(int));
+    FDS_CUDA(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     plan.tasks = dev;
-    if (dev_alloc(ctx, (void **)&plan.dep_ptr, dep_ptr.size() * sizeof(int), false)) return 1;
-    if (dev_alloc(ctx, (void **)&plan.dep_idx, dep_idx.size() * sizeof(int), false)) return 1;
-    if (dev_alloc(ctx, (void **)&plan.done, tasks.size() * sizeof(unsigned), true)) return 1;
-    FDS_CUDA(ctx, cudaMemcpyAsync(dev, tasks.data(), tasks.size() * sizeof(int4),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    FDS_CUDA(ctx, cudaMemcpyAsync(plan.dep_ptr, dep_ptr.data(), dep_ptr.size() * sizeof(int),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    if (!dep_idx.empty())
-        FDS_CUDA(ctx, cudaMemcpyAsync(plan.dep_idx, dep_idx.data(), dep_idx.size() * sizeof(int),
-                                      cudaMemcpyHostToDevice, ctx->stream));
-    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the vectors are pageable host memory
+    plan.dep_ptr = (int *)(dev + off_ptr);
+    plan.dep_idx = (int *)(dev + off_idx);
+    plan.done = (unsigned *)(dev + off_done);
     ctx->chain_tasks = nullptr;
     plan.n_tasks = (int)tasks.size();
     plan.k = k;
@@ -1683,6 +1705,7 @@ struct fds_group {
     std::vector<fds_ctx *> members;
     std::vector<Interaction> interactions;
     long long n = 0;
+    StepTables *d_tables = nullptr;   // two members: their tables, for the one-launch pair kernel
     std::string err;
 };
 
@@ -1742,6 +1765,56 @@ int group_member_step(fds_ctx *ctx, const StepTables &t, long long sig_index, lo
     ctx->last_steps_per_launch = 1;
     ctx->last_launches += 1;
     return 0;
+}
+
+// Both members of a two-field group in one launch (line1d_pair_kernel).
+int member_kind(const fds_ctx *ctx) { return ctx->thermal ? 2 : ctx->d.lossy ? 1 : 0; }
+
+template <int K0, int K1>
+int launch_pair(fds_group *g, const LinePairArgs &p, unsigned ctas, cudaStream_t stream) {
+    auto kernel = line1d_pair_kernel<K0, K1>;
+    const int smem = (int)(kLineWarps * sizeof(LineShared));
+    static bool configured = false;
+    if (!configured) {
+        FDS_GCUDA(g, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    kernel<<<dim3(ctas, 2), 32 * kLineWarps, smem, stream>>>(p, g->d_tables);
+    FDS_GCUDA(g, cudaGetLastError());
+    return 0;
+}
+
+int group_pair_step(fds_group *g, long long step, long long ring_row, cudaStream_t stream) {
+    LinePairArgs p{};
+    unsigned ctas = 1;
+    for (int m = 0; m < 2; ++m) {
+        fds_ctx *ctx = g->members[(size_t)m];
+        const Plan1D plan = plan_1d(ctx, 1);
+        Step1DArgs &a = p.a[m];
+        a.in[0] = origin(ctx, ctx->cur, 0);
+        a.in[1] = origin(ctx, ctx->cur, 1);
+        a.out[0] = origin(ctx, ctx->cur ^ 1, 0);
+        a.out[1] = origin(ctx, ctx->cur ^ 1, 1);
+        a.n = ctx->d.nx;
+        a.tile = plan.tile;
+        a.halo = plan.halo;
+        a.n_steps = 1;
+        a.sig_index = step - ctx->sig_first;
+        a.ring_row = ring_row;
+        p.n_tiles[m] = (int)plan.ctas;
+        ctas = std::max(ctas, (unsigned)((plan.ctas + kLineWarps - 1) / kLineWarps));
+        ctx->cur ^= 1;
+        ctx->last_kernel = "line1d_pair_kernel";
+        ctx->last_steps_per_launch = 1;
+        ctx->last_launches += 1;
+    }
+    const int k0 = member_kind(g->members[0]), k1 = member_kind(g->members[1]);
+#define FDS_PAIR(A, B) if (k0 == A && k1 == B) return launch_pair<A, B>(g, p, ctas, stream);
+    FDS_PAIR(0, 0) FDS_PAIR(0, 1) FDS_PAIR(0, 2)
+    FDS_PAIR(1, 0) FDS_PAIR(1, 1) FDS_PAIR(1, 2)
+    FDS_PAIR(2, 0) FDS_PAIR(2, 1) FDS_PAIR(2, 2)
+#undef FDS_PAIR
+    return gfail(g, "fds_group_step: unknown member kinds");
 }
 
 int group_apply(fds_group *g, fds_group::Interaction &it, long long step, cudaStream_t stream) {
@@ -1992,6 +2065,11 @@ void fds_destroy(fds_ctx *ctx) {
     }
     if (ctx->flagged.ptr) cudaFree(ctx->flagged.ptr);
     invalidate_plans(ctx);
+    for (auto &chunk : ctx->plan_chunks) {
+        if (chunk.dev) cudaFree(chunk.dev);
+        if (chunk.host) cudaFreeHost(chunk.host);
+    }
+    ctx->plan_chunks.clear();
     if (ctx->signals.ptr) cudaFree(ctx->signals.ptr);
     if (ctx->ring.ptr) cudaFree(ctx->ring.ptr);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -2580,6 +2658,7 @@ void fds_group_destroy(fds_group *g) {
         cudaSetDevice(g->members[0]->d.device);
         cudaStreamSynchronize(g->members[0]->stream);
     }
+    if (g->d_tables) cudaFree(g->d_tables);
     for (auto &it : g->interactions) {
         if (it.acc) cudaFree(it.acc);
         if (it.aux) cudaFree(it.aux);
@@ -2745,12 +2824,22 @@ int fds_group_step(fds_group *g, int64_t first_step, int64_t n_steps, double *co
         tables[m] = make_tables(g->members[m]);
     }
     int rc = 0;
+    const bool pair = nm == 2 && !getenv("FDS_NO_PAIR_KERNEL");
+    if (pair) {
+        if (!g->d_tables && group_alloc(g, (void **)&g->d_tables, 2 * sizeof(StepTables), nullptr))
+            rc = 1;
+        if (!rc && cudaMemcpyAsync(g->d_tables, tables.data(), 2 * sizeof(StepTables),
+                                   cudaMemcpyHostToDevice, stream) != cudaSuccess)
+            rc = gfail(g, "fds_group_step: table upload failed");
+        if (!rc) cudaStreamSynchronize(stream);      // `tables` is pageable host memory
+    }
     cudaError_t e = cudaEventRecord(g->members[0]->ev_t0, stream);
     for (long long done = 0; done < n_steps && !rc && e == cudaSuccess; done += chunk) {
         const long long count = std::min(chunk, n_steps - done);
         for (long long s = 0; s < count && !rc; ++s) {
             const long long step = first_step + done + s;
-            for (size_t m = 0; m < nm && !rc; ++m) {
+            if (pair) rc = group_pair_step(g, step, s, stream);
+            for (size_t m = 0; m < nm && !rc && !pair; ++m) {
                 fds_ctx *ctx = g->members[m];
                 rc = group_member_step(ctx, tables[m], step - ctx->sig_first, s);
                 if (rc) g->err = "fds_group_step: " + ctx->err;

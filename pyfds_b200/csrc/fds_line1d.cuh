@@ -121,8 +121,7 @@ __device__ __noinline__ double line_special(const LineShared *sh, int comp, int 
 constexpr int kLineWarps = 4;        // warps (= tiles) per CTA: one per SM sub-partition
 
 template <bool THERMAL, bool LOSSY>
-__global__ void __launch_bounds__(32 * kLineWarps, 1) line1d_kernel(Step1DArgs a, StepTables t,
-                                                                    int n_tiles) {
+__device__ __forceinline__ void line1d_body(const Step1DArgs &a, const StepTables &t, int n_tiles) {
     constexpr int C = kLineCells;
     extern __shared__ __align__(16) unsigned char line_smem[];
     const int lane = threadIdx.x & 31;
@@ -329,6 +328,35 @@ __global__ void __launch_bounds__(32 * kLineWarps, 1) line1d_kernel(Step1DArgs a
             }
         }
     }
+}
+
+template <bool THERMAL, bool LOSSY>
+__global__ void __launch_bounds__(32 * kLineWarps, 1) line1d_kernel(Step1DArgs a, StepTables t,
+                                                                    int n_tiles) {
+    line1d_body<THERMAL, LOSSY>(a, t, n_tiles);
+}
+
+// Two member fields of a SynchronizedFields group in ONE launch: within a common step the members do
+// not depend on each other (only the interactions that follow couple them, pyfds/coupling.py:81-87),
+// so blockIdx.y picks the field and both lines advance side by side. KIND: 0 acoustic lossless,
+// 1 acoustic lossy, 2 thermal.
+struct LinePairArgs {
+    Step1DArgs a[2];
+    int n_tiles[2];
+};
+
+template <int KIND>
+__device__ __forceinline__ void line1d_member(const Step1DArgs &a, const StepTables &t, int n_tiles) {
+    if (KIND == 2) line1d_body<true, false>(a, t, n_tiles);
+    else if (KIND == 1) line1d_body<false, true>(a, t, n_tiles);
+    else line1d_body<false, false>(a, t, n_tiles);
+}
+
+template <int KIND0, int KIND1>
+__global__ void __launch_bounds__(32 * kLineWarps, 1)
+line1d_pair_kernel(LinePairArgs p, const StepTables *__restrict__ tables) {
+    if (blockIdx.y == 0) line1d_member<KIND0>(p.a[0], tables[0], p.n_tiles[0]);
+    else line1d_member<KIND1>(p.a[1], tables[1], p.n_tiles[1]);
 }
 
 }  // namespace fds
