@@ -164,6 +164,11 @@ struct fds_ctx {
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
     std::vector<int> host_pslots[3];   // host copies of the probe slot lists
+    // 1-D: host copies of the lookup tables and what refresh_flags resolves from them (LineResolved)
+    std::vector<int> host_boffsets[3], host_bsignal[3];
+    std::vector<double> host_balpha[3], host_bvalue[3];
+    std::vector<long long> host_pcells[3];
+    DevArray line_index, line_entries;
 
     cudaStream_t stream = nullptr, drain = nullptr, comm_stream = nullptr;
     cudaEvent_t ev_half[2] = {nullptr, nullptr}, ev_drained[2] = {nullptr, nullptr};
@@ -328,6 +333,53 @@ int upload_row_ptr(fds_ctx *ctx, DevArray &dst, const long long *cells, int64_t 
 // Rebuilds the per-cell flag bits from the boundary and probe tables.
 void invalidate_plans(fds_ctx *ctx);
 
+// 1-D: per flagged cell and component the position of its operations and probes in the tables
+// (LineResolved), so that the kernels do not search them launch after launch.
+int resolve_line_entries(fds_ctx *ctx) {
+    const long long n = ctx->d.nx;
+    std::vector<int> index((size_t)n, -1);
+    std::vector<LineResolved> entries;
+    auto entry_of = [&](long long cell) -> LineResolved * {
+        int &number = index[(size_t)cell];
+        if (number < 0) {
+            number = (int)(entries.size() / 2);
+            LineResolved blank{1.0, 0.0, -1, 0, 0, 0, 0, 0};
+            entries.push_back(blank);
+            entries.push_back(blank);
+        }
+        return &entries[(size_t)(2 * number)];
+    };
+    for (int c = 0; c < 2; ++c) {
+        const auto &cells = ctx->host_bcells[c];
+        for (size_t k = 0; k < cells.size(); ++k) {
+            if (cells[k] < 0 || cells[k] >= n) continue;
+            LineResolved &e = entry_of(cells[k])[c];
+            e.o0 = ctx->host_boffsets[c][k];
+            e.n_ops = ctx->host_boffsets[c][k + 1] - e.o0;
+            if (e.n_ops > 0) {
+                e.alpha = ctx->host_balpha[c][(size_t)e.o0];
+                e.value = ctx->host_bvalue[c][(size_t)e.o0];
+                e.signal = ctx->host_bsignal[c][(size_t)e.o0];
+            }
+        }
+        const auto &probes = ctx->host_pcells[c];
+        for (size_t k = 0; k < probes.size();) {
+            size_t end = k;
+            while (end < probes.size() && probes[end] == probes[k]) ++end;
+            if (probes[k] >= 0 && probes[k] < n) {
+                LineResolved &e = entry_of(probes[k])[c];
+                e.p0 = (int)k;
+                e.p1 = (int)end;
+            }
+            k = end;
+        }
+    }
+    if (dev_upload(ctx, ctx->line_index, index.data(), index.size() * sizeof(int))) return 1;
+    if (dev_upload(ctx, ctx->line_entries, entries.data(), entries.size() * sizeof(LineResolved)))
+        return 1;
+    return 0;
+}
+
 int refresh_flags(fds_ctx *ctx) {
     if (!ctx->flags_dirty) return 0;
     invalidate_plans(ctx);   // the strip census reads the flag and class bits
@@ -376,6 +428,7 @@ int refresh_flags(fds_ctx *ctx) {
     }
     ctx->n_flagged = total;
     ctx->flags_dirty = false;
+    if (ctx->dims == 1 && resolve_line_entries(ctx)) return 1;
     return 0;
 }
 
@@ -405,6 +458,8 @@ StepTables make_tables(fds_ctx *ctx) {
     t.cvec = ctx->cvec;
     t.cell_tab = ctx->cell_tab;
     t.cell_n = ctx->d.nx;
+    t.line_index = (const int *)ctx->line_index.ptr;
+    t.line_entries = (const LineResolved *)ctx->line_entries.ptr;
     for (int c = 0; c < 3; ++c) {
         t.bound[c].cells = (const long long *)ctx->bcells[c].ptr;
         t.bound[c].offsets = (const int *)ctx->boffsets[c].ptr;
@@ -1767,6 +1822,23 @@ int group_member_step(fds_ctx *ctx, const StepTables &t, long long sig_index, lo
     return 0;
 }
 
+// Launch with programmatic stream serialisation (the kernels wait for their predecessor themselves).
+template <typename Kernel, typename... Args>
+cudaError_t launch_chained(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                           Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = getenv("FDS_NO_OVERLAP") ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // Both members of a two-field group in one launch (line1d_pair_kernel).
 int member_kind(const fds_ctx *ctx) { return ctx->thermal ? 2 : ctx->d.lossy ? 1 : 0; }
 
@@ -1779,8 +1851,8 @@ int launch_pair(fds_group *g, const LinePairArgs &p, unsigned ctas, cudaStream_t
         FDS_GCUDA(g, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    kernel<<<dim3(ctas, 2), 32 * kLineWarps, smem, stream>>>(p, g->d_tables);
-    FDS_GCUDA(g, cudaGetLastError());
+    FDS_GCUDA(g, launch_chained(kernel, dim3(ctas, 2), dim3(32 * kLineWarps), (size_t)smem, stream, p,
+                                (const StepTables *)g->d_tables));
     return 0;
 }
 
@@ -1829,9 +1901,10 @@ int group_apply(fds_group *g, fds_group::Interaction &it, long long step, cudaSt
         a.cell_tab = g->members[(size_t)it.dst_member]->cell_tab;
         if (a.has_threshold)
             FDS_GCUDA(g, cudaMemsetAsync(a.max_bits, 0, sizeof(unsigned long long), stream));
-        couple_law_factors_kernel<<<blocks, kCoupleThreads, 0, stream>>>(a);
-        couple_law_assemble_kernel<<<blocks, kCoupleThreads, 0, stream>>>(a);
-        FDS_GCUDA(g, cudaGetLastError());
+        FDS_GCUDA(g, launch_chained(couple_law_factors_kernel, dim3(blocks), dim3(kCoupleThreads), 0,
+                                    stream, a));
+        FDS_GCUDA(g, launch_chained(couple_law_assemble_kernel, dim3(blocks), dim3(kCoupleThreads), 0,
+                                    stream, a));
         return 0;
     }
     if (!due && !it.accumulate) return 0;
@@ -1843,8 +1916,8 @@ int group_apply(fds_group *g, fds_group::Interaction &it, long long step, cudaSt
     d.additive = it.additive;
     d.deliver = due ? 1 : 0;
     if (it.kind == 0) {
-        couple_linear_kernel<<<blocks, kCoupleThreads, 0, stream>>>(
-            d, origin(src, src->cur, it.src_comp), it.scale);
+        FDS_GCUDA(g, launch_chained(couple_linear_kernel, dim3(blocks), dim3(kCoupleThreads), 0, stream,
+                                    d, (const double *)origin(src, src->cur, it.src_comp), it.scale));
     } else {
         HeatingArgs h{};
         h.velocity = origin(src, src->cur, it.src_comp);
@@ -1852,9 +1925,9 @@ int group_apply(fds_group *g, fds_group::Interaction &it, long long step, cudaSt
         h.g = it.aux + n;
         h.gain = it.aux + 2 * n;
         h.dt = it.dt;
-        couple_viscous_heating_kernel<<<blocks, kCoupleThreads, 0, stream>>>(d, h);
+        FDS_GCUDA(g, launch_chained(couple_viscous_heating_kernel, dim3(blocks), dim3(kCoupleThreads), 0,
+                                    stream, d, h));
     }
-    FDS_GCUDA(g, cudaGetLastError());
     return 0;
 }
 
@@ -2064,6 +2137,8 @@ void fds_destroy(fds_ctx *ctx) {
             if (a->ptr) cudaFree(a->ptr);
     }
     if (ctx->flagged.ptr) cudaFree(ctx->flagged.ptr);
+    if (ctx->line_index.ptr) cudaFree(ctx->line_index.ptr);
+    if (ctx->line_entries.ptr) cudaFree(ctx->line_entries.ptr);
     invalidate_plans(ctx);
     for (auto &chunk : ctx->plan_chunks) {
         if (chunk.dev) cudaFree(chunk.dev);
@@ -2267,6 +2342,12 @@ int fds_upload_boundaries(fds_ctx *ctx, int32_t component, const int64_t *cells,
     if (dev_upload(ctx, ctx->cclass[c], class_ids.data(), nc * 4)) return 1;
     ctx->host_bcells[c] = slow_cells;
     ctx->host_ccells[c] = class_cells;
+    if (ctx->dims == 1) {
+        ctx->host_boffsets[c] = slow_offsets;
+        ctx->host_balpha[c] = slow_alpha;
+        ctx->host_bvalue[c] = slow_value;
+        ctx->host_bsignal[c] = slow_signal;
+    }
     invalidate_plans(ctx);
     ctx->n_bcells[c] = (long long)ns;
     ctx->n_ccells[c] = (long long)nc;
@@ -2309,6 +2390,7 @@ int fds_upload_probes(fds_ctx *ctx, int32_t component, const int64_t *cells, con
     if (dev_upload(ctx, ctx->pslots[component], slots, (size_t)n * 4)) return 1;
     if (upload_row_ptr(ctx, ctx->prowptr[component], (const long long *)cells, n)) return 1;
     ctx->host_pslots[component].assign(slots, slots + n);
+    if (ctx->dims == 1) ctx->host_pcells[component].assign(cells, cells + n);
     ctx->n_probes[component] = n;
     ctx->n_slots = n_slots_total;
     ctx->flags_dirty = true;

@@ -53,6 +53,18 @@ struct ProbeTable {
     int n;
 };
 
+// 1-D fields: what the boundary and probe tables hold for one flagged cell and component, resolved on
+// the host when the tables change, so that a launch reads it with two loads instead of walking the
+// tables (binary searches = a chain of dependent global loads per flagged cell and launch, which is what
+// a one-step launch of a coupled group used to spend most of its time on).
+struct LineResolved {
+    double alpha, value;   // first operation: v = alpha * v + (signal sample or value)
+    int signal;            // signal of the first operation, -1 = scalar value
+    int o0, n_ops;         // all operations: o0 .. o0 + n_ops - 1 of the component's table
+    int p0, p1;            // probe entries p0 .. p1 - 1 of the component's table
+    int pad;
+};
+
 // Geometry needed to find the row of a cell on the slow path.
 struct RowIndex {
     long long nx;
@@ -69,6 +81,9 @@ struct StepTables {
     // per-cell coefficients [FDS_TAB_COUNT][cell_n] instead of the per-material table (null otherwise)
     const double *cell_tab;
     long long cell_n;
+    // 1-D: entry number of every cell (-1: none) and the entries [number][component]
+    const int *line_index;
+    const LineResolved *line_entries;
     BoundTable bound[3];
     ProbeTable probe[3];
     const double *signals;     // [n_signals][sig_steps]

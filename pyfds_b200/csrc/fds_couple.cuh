@@ -12,6 +12,14 @@ namespace fds {
 
 constexpr int kCoupleThreads = 256;
 
+// The kernels of a group are launched with programmatic stream serialisation: each grid is scheduled
+// while its predecessor still runs and waits for it here (launch latency off the critical path of a
+// step that consists of two or three tiny dependent launches).
+__device__ __forceinline__ void couple_grid_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // BoundaryCoupling.apply (pyfds/coupling.py:118-140) for a transfer function f given per cell by `Fn`:
 //   if accumulate: acc += f(src)                      (acc starts as the integer 0: 0 + x)
 //   if step % stepping == 0:
@@ -45,6 +53,7 @@ __device__ __forceinline__ void deliver_cell(const DeliverArgs &d, long long k, 
 
 // transfer function  values -> scale * values
 __global__ void couple_linear_kernel(DeliverArgs d, const double *__restrict__ source, double scale) {
+    couple_grid_sync();
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= d.n) return;
     deliver_cell(d, k, [&](long long i) { return mul(scale, source[i]); });
@@ -62,6 +71,7 @@ struct HeatingArgs {
 };
 
 __global__ void couple_viscous_heating_kernel(DeliverArgs d, HeatingArgs h) {
+    couple_grid_sync();
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= d.n) return;
     deliver_cell(d, k, [&](long long i) {
@@ -114,6 +124,7 @@ __device__ __forceinline__ double law_factor(const LawArgs &a, double q) {
 }
 
 __global__ void couple_law_factors_kernel(LawArgs a) {
+    couple_grid_sync();
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double change = 0.0;
     if (k < a.n) {
@@ -138,6 +149,7 @@ __global__ void couple_law_factors_kernel(LawArgs a) {
 }
 
 __global__ void couple_law_assemble_kernel(LawArgs a) {
+    couple_grid_sync();
     if (a.has_threshold) {
         const double change = __longlong_as_double((long long)*a.max_bits);
         if (!(change > a.threshold)) return;

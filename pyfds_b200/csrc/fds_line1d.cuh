@@ -55,34 +55,30 @@ struct LineShared {
     long long sig_steps;
 };
 
-__device__ __noinline__ void line_resolve(LineShared *sh, int comp, int c, int lane,
-                                          const BoundTable b, const ProbeTable p,
-                                          const RowIndex ri, long long cell, double cls_alpha,
-                                          double cls_value, int has_cls) {
-    LineEntry e{1.0, 0.0, cls_alpha, cls_value, -1, 0, 0, 0, 0, -1, has_cls};
-    const long long row = (cell + ri.halo_cells) / ri.nx;
-    if (b.n_cells > 0) {
-        const int hi = __ldg(b.row_ptr + row + 1);
-        const int k = lower_bound_cell(b.cells, __ldg(b.row_ptr + row), hi, cell);
-        if (k < hi && __ldg(b.cells + k) == cell) {
-            e.o0 = __ldg(b.offsets + k);
-            e.n_ops = __ldg(b.offsets + k + 1) - e.o0;
-            if (e.n_ops > 0) {
-                const int sidx = __ldg(b.signal + e.o0);
-                e.alpha = __ldg(b.alpha + e.o0);
-                e.value = __ldg(b.value + e.o0);
-                e.sigoff = sidx >= 0 ? (long long)sidx * sh->sig_steps : -1;
-            }
+// Entries of one flagged cell (both components) from the host-resolved table.
+__device__ __noinline__ void line_resolve(LineShared *sh, int c, int lane,
+                                          const int *__restrict__ line_index,
+                                          const LineResolved *__restrict__ line_entries,
+                                          long long cell, double cls_alpha0, double cls_value0,
+                                          int has_cls0, double cls_alpha1, double cls_value1,
+                                          int has_cls1) {
+    const int number = __ldg(line_index + cell);
+#pragma unroll
+    for (int comp = 0; comp < 2; ++comp) {
+        LineEntry e{1.0, 0.0, comp ? cls_alpha1 : cls_alpha0, comp ? cls_value1 : cls_value0,
+                    -1, 0, 0, 0, 0, -1, comp ? has_cls1 : has_cls0};
+        if (number >= 0) {
+            const LineResolved r = line_entries[2 * number + comp];
+            e.alpha = r.alpha;
+            e.value = r.value;
+            e.sigoff = r.signal >= 0 ? (long long)r.signal * sh->sig_steps : -1;
+            e.o0 = r.o0;
+            e.n_ops = r.n_ops;
+            e.p0 = r.p0;
+            e.p1 = r.p1;
         }
+        sh->entries[comp][c][lane] = e;
     }
-    if (p.n > 0) {
-        const int hi = __ldg(p.row_ptr + row + 1);
-        int k = lower_bound_cell(p.cells, __ldg(p.row_ptr + row), hi, cell);
-        e.p0 = k;
-        while (k < hi && __ldg(p.cells + k) == cell) ++k;
-        e.p1 = k;
-    }
-    sh->entries[comp][c][lane] = e;
 }
 
 // Stages the samples of the next `count` steps of all cached signals; the whole warp copies.
@@ -124,6 +120,11 @@ template <bool THERMAL, bool LOSSY>
 __device__ __forceinline__ void line1d_body(const Step1DArgs &a, const StepTables &t, int n_tiles) {
     constexpr int C = kLineCells;
     extern __shared__ __align__(16) unsigned char line_smem[];
+    // Launched with programmatic stream serialisation (the one-step launches of a coupled group), the
+    // grid is scheduled while its predecessor still runs and waits here for it to complete; both
+    // instructions are no-ops in an ordinary launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * kLineWarps + (threadIdx.x >> 5);
     if (tile >= n_tiles) return;         // warps are independent: no block-level barrier anywhere
@@ -188,13 +189,13 @@ __device__ __forceinline__ void line1d_body(const Step1DArgs &a, const StepTable
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             if (!(special >> c & 1u)) continue;
+            const unsigned k0 = (id[c] >> class_shift(0)) & (kMaxClasses - 1);
+            const unsigned k1 = (id[c] >> class_shift(1)) & (kMaxClasses - 1);
+            line_resolve(&sh, c, lane, t.line_index, t.line_entries, g0 + c, t.cls_alpha[0][k0],
+                         t.cls_value[0][k0], k0 != 0, t.cls_alpha[1][k1], t.cls_value[1][k1], k1 != 0);
 #pragma unroll
-            for (int comp = 0; comp < 2; ++comp) {
-                const unsigned k = (id[c] >> class_shift(comp)) & (kMaxClasses - 1);
-                line_resolve(&sh, comp, c, lane, t.bound[comp], t.probe[comp], t.rows, g0 + c,
-                             t.cls_alpha[comp][k], t.cls_value[comp][k], k != 0);
+            for (int comp = 0; comp < 2; ++comp)
                 if (sh.entries[comp][c][lane].sigoff >= 0) ++n_cached;
-            }
         }
     }
     // rows of the signal window: exclusive prefix sum of the lanes' demands
