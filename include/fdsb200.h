@@ -113,10 +113,12 @@ int fds_upload_table(fds_ctx *ctx, int32_t table, const double *values, int64_t 
 int fds_upload_column_table(fds_ctx *ctx, int32_t table, const double *values, int64_t n);
 /* One per-column vector: n = nx doubles. */
 int fds_upload_column_vector(fds_ctx *ctx, int32_t vec, const double *values, int64_t n);
-/* 1-D models whose material parameters differ from cell to cell (what `MaterialCoupling` produces by
+/* Fields whose material parameters differ from cell to cell (what `MaterialCoupling` produces by
  * scaling a parameter with another field's values, pyfds/coupling.py:182-197): one per-CELL coefficient
- * array, n = nx doubles, used instead of the per-material table of the same id. All tables the model
- * reads must be uploaded this way; values == NULL switches back to the per-material tables. */
+ * array, n = owned cells, used instead of the per-material table of the same id. All tables the model
+ * reads must be uploaded this way; values == NULL switches back to the per-material tables. 1-D models
+ * keep their kernel; plain 2-D models (single slab, not axisymmetric) run on the one-thread-per-cell
+ * kernel, one step per launch, while per-cell coefficients are on. */
 int fds_upload_cell_table(fds_ctx *ctx, int32_t table, const double *values, int64_t n);
 
 /* --- boundaries and sources: `FieldComponent.apply_bounds` + `Boundary.apply`

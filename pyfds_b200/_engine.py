@@ -485,12 +485,15 @@ def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None, lossy=
     snapshot = baked['snapshot']
     lo, hi = (row0 - halo_rows) * nx, (row0 + rows + halo_rows) * nx
     one_d = not hasattr(field, 'y')
+    # per-cell coefficients: 1-D models, and plain 2-D models on a single slab
+    cells_possible = one_d or (field._device_model in ('acoustic2d', 'thermal2d') and
+                               row0 == 0 and rows == ny and halo_rows == 0)
     cells = None
-    if isinstance(snapshot, _bake.DenseSnapshot) and one_d and \
+    if isinstance(snapshot, _bake.DenseSnapshot) and cells_possible and \
             (per_cell or _bake.distinct_combinations(snapshot) > _bake.MAX_MATERIALS):
-        # materials that differ from cell to cell (MaterialCoupling on a smooth source): the 1-D kernels
+        # materials that differ from cell to cell (MaterialCoupling on a smooth source): the kernels
         # read per-cell coefficient arrays, evaluated here by the same expressions on the per-point
-        # parameter vectors themselves
+        # parameter vectors themselves (2-D: the one-thread-per-cell kernel, one step per launch)
         values = {p: np.concatenate(([0.0], snapshot.vectors[p])) for p in snapshot.params}
         cells = field._coefficient_tables(values)
         ids = np.ones(field.num_points, dtype=np.uint8)
@@ -518,7 +521,7 @@ def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None, lossy=
         engine.upload_column_table(CTAB[name], np.vstack((np.zeros((1, nx)), matrix)))
     for name, vector in tables.get('column_vectors', {}).items():
         engine.upload_column_vector(CVEC[name], vector)
-    if one_d:
+    if cells_possible:
         engine.upload_cell_table(0, None)
         if cells is not None:
             for name, column in cells['tables'].items():

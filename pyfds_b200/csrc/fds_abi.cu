@@ -197,6 +197,8 @@ struct fds_ctx {
     const void *chain_tasks = nullptr;
     bool overlap = true;       // programmatic dependent launches between sweeps (FDS_NO_OVERLAP=1: off)
     bool halo_in_kernel = true;   // halo rows pushed / awaited inside the streaming kernels
+    bool kernels_before_cells[3] = {false, false, false};   // use_stream2d / use_streamv / use_tile2d
+                                                            // while 2-D per-cell coefficients are on
     bool use_stream2d = false; // streaming multi-step kernel selected
     bool use_tile2d = false;   // shared-memory tile kernel selected (one step per launch)
     bool use_streamv = false;  // streaming kernel of the viscous / axisymmetric acoustic models
@@ -457,7 +459,7 @@ StepTables make_tables(fds_ctx *ctx) {
     t.ctab = ctx->ctab;
     t.cvec = ctx->cvec;
     t.cell_tab = ctx->cell_tab;
-    t.cell_n = ctx->d.nx;
+    t.cell_n = ctx->owned;
     t.line_index = (const int *)ctx->line_index.ptr;
     t.line_entries = (const LineResolved *)ctx->line_entries.ptr;
     for (int c = 0; c < 3; ++c) {
@@ -533,7 +535,14 @@ int launch_step2d(fds_ctx *ctx, const Step2DArgs &a, const StepTables &t) {
         return 0;
     }
     dim3 grid((unsigned)rows, (unsigned)((a.nx + 255) / 256));
-    step2d_kernel<MODEL, LOSSY><<<grid, 256, 0, ctx->stream>>>(a, t, ctx->d.n_materials + 1);
+    if (ctx->cell_tab) {
+        constexpr bool axi = (MODEL == FDS_ACOUSTIC3DAXI || MODEL == FDS_THERMAL3DAXI);
+        if (axi) return fail(ctx, "per-cell coefficients are not supported for axisymmetric models");
+        step2d_kernel<axi ? FDS_ACOUSTIC2D : MODEL, LOSSY, true>
+            <<<grid, 256, 0, ctx->stream>>>(a, t, ctx->d.n_materials + 1);
+    } else {
+        step2d_kernel<MODEL, LOSSY><<<grid, 256, 0, ctx->stream>>>(a, t, ctx->d.n_materials + 1);
+    }
     FDS_CUDA(ctx, cudaGetLastError());
     return 0;
 }
@@ -2214,21 +2223,37 @@ int fds_upload_cell_table(fds_ctx *ctx, int32_t table, const double *values, int
         if (ctx->cell_tab) {
             FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             cudaFree(ctx->cell_tab);
-            ctx->device_bytes -= (long long)sizeof(double) * FDS_TAB_COUNT * ctx->d.nx;
+            ctx->device_bytes -= (long long)sizeof(double) * FDS_TAB_COUNT * ctx->owned;
             ctx->cell_tab = nullptr;
+            if (ctx->dims == 2) {   // back to the kernels chosen at creation
+                ctx->use_stream2d = ctx->kernels_before_cells[0];
+                ctx->use_streamv = ctx->kernels_before_cells[1];
+                ctx->use_tile2d = ctx->kernels_before_cells[2];
+                invalidate_plans(ctx);
+            }
         }
         return 0;
     }
-    if (ctx->dims != 1)
-        return fail(ctx, "fds_upload_cell_table: per-cell coefficients are supported for 1-D models");
-    if (ctx->d.kernel == 1)
+    if (ctx->dims == 1 && ctx->d.kernel == 1)
         return fail(ctx, "fds_upload_cell_table: the shared-memory 1-D kernel reads the material table "
                          "only (use kernel 0)");
+    if (ctx->dims == 2 && (ctx->axi || ctx->d.halo_rows != 0 || ctx->d.rows != ctx->d.ny))
+        return fail(ctx, "fds_upload_cell_table: 2-D per-cell coefficients need a plain (not "
+                         "axisymmetric) model on a single slab");
     if (table < 0 || table >= FDS_TAB_COUNT) return fail(ctx, "fds_upload_cell_table: bad table id");
-    if (n != ctx->d.nx) return fail(ctx, "fds_upload_cell_table: expected nx values");
-    if (!ctx->cell_tab)
+    if (n != ctx->owned) return fail(ctx, "fds_upload_cell_table: expected one value per cell");
+    if (!ctx->cell_tab) {
         if (dev_alloc(ctx, (void **)&ctx->cell_tab, sizeof(double) * FDS_TAB_COUNT * (size_t)n, true))
             return 1;
+        if (ctx->dims == 2) {
+            // only the one-thread-per-cell kernel reads per-cell coefficients (one step per launch)
+            ctx->kernels_before_cells[0] = ctx->use_stream2d;
+            ctx->kernels_before_cells[1] = ctx->use_streamv;
+            ctx->kernels_before_cells[2] = ctx->use_tile2d;
+            ctx->use_stream2d = ctx->use_streamv = ctx->use_tile2d = false;
+            invalidate_plans(ctx);
+        }
+    }
     FDS_CUDA(ctx, cudaMemcpyAsync(ctx->cell_tab + (size_t)table * (size_t)n, values,
                                   sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -56,7 +56,7 @@ struct Tile2DArgs {
 // components and the map whose rows are `pitch` elements apart (global memory: pitch = nx; the
 // shared-memory tile: pitch = kTilePitch); x is the cell's column, i its local flat index (for the
 // boundary/probe tables and the output).
-template <int MODEL, bool LOSSY, bool FLAGS>
+template <int MODEL, bool LOSSY, bool FLAGS, bool PERCELL = false>
 __device__ __forceinline__ void cell_body(const Step2DArgs &a, const StepTables &t, int n_mat1,
                                             long long i, long long x, long long pitch,
                                             const double *__restrict__ sp,
@@ -96,7 +96,13 @@ __device__ __forceinline__ void cell_body(const Step2DArgs &a, const StepTables 
         myl = mp[pitch - 1]; my2 = mp[2 * pitch];
     }
 
-    auto tab = [&](int which, unsigned m) { return tabs[which][m & kIdMask]; };
+    // coefficient of the cell `off` places from cell i whose map entry is m: by material, or -- where
+    // the materials differ from cell to cell (PERCELL, MaterialCoupling on a smooth source) -- from the
+    // per-cell arrays; cells outside the grid are void (all coefficients zero) either way
+    auto tab = [&](int which, unsigned m, long long off) {
+        if (PERCELL) return (m & kIdMask) ? t.cell_tab[(long long)which * t.cell_n + i + off] : 0.0;
+        return tabs[which][m & kIdMask];
+    };
     auto ctab = [&](int which, unsigned m, long long col) {
         return __ldg(t.ctab + ((long long)which * n_mat1 + (m & kIdMask)) * nx + col);
     };
@@ -132,7 +138,7 @@ __device__ __forceinline__ void cell_body(const Step2DArgs &a, const StepTables 
         const unsigned mj = k ? mxp : m0, mjm = k ? m0 : mxm;
         const double sj = k ? sxp : s0, sjm = k ? s0 : sxm;
         // A_vx_p p  |  A_qx_t T : backward difference, offsets [-1, 0]
-        const double d = diff2(tab(FDS_TAB_GX, mjm), sjm, tab(FDS_TAB_GX, mj), sj);
+        const double d = diff2(tab(FDS_TAB_GX, mjm, k - 1), sjm, tab(FDS_TAB_GX, mj, k), sj);
         double v;
         if (kThermal) {
             v = -d;
@@ -147,19 +153,19 @@ __device__ __forceinline__ void cell_body(const Step2DArgs &a, const StepTables 
                     cm1 = ctab(FDS_CTAB_VM1, mjm, wrap_col(col - 1, nx));
                     cp1 = ctab(FDS_CTAB_VP1, mc, wrap_col(col + 1, nx));
                 } else {
-                    cm1 = tab(FDS_TAB_VM1, mjm);
-                    cp1 = tab(FDS_TAB_VP1, mc);
+                    cm1 = tab(FDS_TAB_VM1, mjm, k - 1);
+                    cp1 = tab(FDS_TAB_VP1, mc, k + 1);
                 }
                 // V u: five diagonals in offset order [-nx, -1, 0, +1, +nx]
-                double vis = acc0(mul(tab(FDS_TAB_VMN, mxa[k]), ua[k]));
+                double vis = acc0(mul(tab(FDS_TAB_VMN, mxa[k], k - nx), ua[k]));
                 vis = add(vis, mul(cm1, um));
-                vis = add(vis, mul(tab(FDS_TAB_V0, mj), old));
+                vis = add(vis, mul(tab(FDS_TAB_V0, mj, k), old));
                 vis = add(vis, mul(cp1, up));
-                vis = add(vis, mul(tab(FDS_TAB_VPN, mxb[k]), ub[k]));
+                vis = add(vis, mul(tab(FDS_TAB_VPN, mxb[k], k + nx), ub[k]));
                 double rhs = sub(d, vis);
                 if (kAxi) {
                     // + dt*mu/rho * vx / r**2   (pyfds/acoustics.py:213-215)
-                    const double e = mul(tab(FDS_TAB_EB, mj), old) /
+                    const double e = mul(tab(FDS_TAB_EB, mj, k), old) /
                                      __ldg(t.cvec + FDS_CVEC_RR * nx + col);
                     rhs = add(rhs, e);
                 }
@@ -182,7 +188,7 @@ __device__ __forceinline__ void cell_body(const Step2DArgs &a, const StepTables 
         const long long j = i + k * nx;
         const unsigned mj = k ? myp : m0, mjm = k ? m0 : mym;
         const double sj = k ? syp : s0, sjm = k ? s0 : sym;
-        const double d = diff2(tab(FDS_TAB_GY, mjm), sjm, tab(FDS_TAB_GY, mj), sj);
+        const double d = diff2(tab(FDS_TAB_GY, mjm, (k - 1) * nx), sjm, tab(FDS_TAB_GY, mj, k * nx), sj);
         double v;
         if (kThermal) {
             v = -d;
@@ -198,14 +204,14 @@ __device__ __forceinline__ void cell_body(const Step2DArgs &a, const StepTables 
                     cm1 = ctab(FDS_CTAB_VM1, ml, wrap_col(x - 1, nx));
                     cp1 = ctab(FDS_CTAB_VP1, mr, wrap_col(x + 1, nx));
                 } else {
-                    cm1 = tab(FDS_TAB_VM1, ml);
-                    cp1 = tab(FDS_TAB_VP1, mr);
+                    cm1 = tab(FDS_TAB_VM1, ml, k * nx - 1);
+                    cp1 = tab(FDS_TAB_VP1, mr, k * nx + 1);
                 }
-                double vis = acc0(mul(tab(FDS_TAB_VMN, ma), below));
+                double vis = acc0(mul(tab(FDS_TAB_VMN, ma, (k - 1) * nx), below));
                 vis = add(vis, mul(cm1, wl[k]));
-                vis = add(vis, mul(tab(FDS_TAB_V0, mj), old));
+                vis = add(vis, mul(tab(FDS_TAB_V0, mj, k * nx), old));
                 vis = add(vis, mul(cp1, wr[k]));
-                vis = add(vis, mul(tab(FDS_TAB_VPN, mb), above));
+                vis = add(vis, mul(tab(FDS_TAB_VPN, mb, (k + 1) * nx), above));
                 v = sub(old, sub(d, vis));
             } else {
                 v = sub(old, d);
@@ -225,11 +231,11 @@ __device__ __forceinline__ void cell_body(const Step2DArgs &a, const StepTables 
         f0 = mul(f0, __ldg(t.cvec + FDS_CVEC_R * nx + x));
         f1 = mul(f1, __ldg(t.cvec + FDS_CVEC_R * nx + col1));
     } else {
-        fx0 = tab(FDS_TAB_FX, m0);
-        fx1 = tab(FDS_TAB_FX, mxp);
+        fx0 = tab(FDS_TAB_FX, m0, 0);
+        fx1 = tab(FDS_TAB_FX, mxp, 1);
     }
     const double divx = diff2(fx0, f0, fx1, f1);
-    const double divy = diff2(tab(FDS_TAB_FY, m0), uy[0], tab(FDS_TAB_FY, myp), uy[1]);
+    const double divy = diff2(tab(FDS_TAB_FY, m0, 0), uy[0], tab(FDS_TAB_FY, myp, nx), uy[1]);
     a.out[0][i] = sub(s0, add(divx, divy));
     if (!kThermal || a.write_vector) {
         a.out[1][i] = ux[0];
@@ -239,7 +245,7 @@ __device__ __forceinline__ void cell_body(const Step2DArgs &a, const StepTables 
 
 // Cells whose 5-point neighbourhood carries no boundary operation, class or probe (almost all) take a
 // body with every flag test compiled out.
-template <int MODEL, bool LOSSY>
+template <int MODEL, bool LOSSY, bool PERCELL = false>
 __device__ __forceinline__ void cell_update(const Step2DArgs &a, const StepTables &t, int n_mat1,
                                             long long i, long long x, long long pitch,
                                             const double *__restrict__ sp,
@@ -249,13 +255,14 @@ __device__ __forceinline__ void cell_update(const Step2DArgs &a, const StepTable
                                             const double (*__restrict__ tabs)[kMaxMaterials]) {
     const unsigned any = mp[0] | mp[-1] | mp[1] | mp[-pitch] | mp[pitch];
     if (any & (kFlagBound | kFlagProbe | kClassMask))
-        cell_body<MODEL, LOSSY, true>(a, t, n_mat1, i, x, pitch, sp, up, wp, mp, tabs);
+        cell_body<MODEL, LOSSY, true, PERCELL>(a, t, n_mat1, i, x, pitch, sp, up, wp, mp, tabs);
     else
-        cell_body<MODEL, LOSSY, false>(a, t, n_mat1, i, x, pitch, sp, up, wp, mp, tabs);
+        cell_body<MODEL, LOSSY, false, PERCELL>(a, t, n_mat1, i, x, pitch, sp, up, wp, mp, tabs);
 }
 
 // One thread per cell, operands straight from global memory (L1/L2 provide the neighbour reuse).
-template <int MODEL, bool LOSSY>
+// PERCELL: coefficients from per-cell arrays (StepTables::cell_tab) instead of the material table.
+template <int MODEL, bool LOSSY, bool PERCELL = false>
 __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t, int n_mat1) {
     __shared__ double tabs[FDS_TAB_COUNT][kMaxMaterials];
     for (int k = threadIdx.x; k < FDS_TAB_COUNT * n_mat1; k += blockDim.x)
@@ -264,8 +271,8 @@ __global__ void __launch_bounds__(256) step2d_kernel(Step2DArgs a, StepTables t,
     const long long x = (long long)blockIdx.y * blockDim.x + threadIdx.x;
     if (x >= a.nx) return;
     const long long i = (a.row_begin + blockIdx.x) * a.nx + x;
-    cell_update<MODEL, LOSSY>(a, t, n_mat1, i, x, a.nx, a.in[0] + i, a.in[1] + i, a.in[2] + i,
-                              t.map + i, tabs);
+    cell_update<MODEL, LOSSY, PERCELL>(a, t, n_mat1, i, x, a.nx, a.in[0] + i, a.in[1] + i,
+                                       a.in[2] + i, t.map + i, tabs);
 }
 
 __device__ __forceinline__ unsigned tile_smem_addr(const void *p) {

@@ -496,7 +496,33 @@ def material_coupling_powerlaw(fds):
     return fds.SynchronizedFields([sound, heat], [law]), steps
 
 
+def material_coupling_2d(fds):
+    """A 2-D target: the smooth temperature field of a Thermal2D scales the sound velocity of an
+    Acoustic2D cell by cell (thousands of distinct materials), re-assembled every 4th step; a lossy
+    main material, so that the 5-diagonal operator is per-cell as well."""
+    steps, nx, ny = 30, 136, 44
+    axes = dict(t_samples=steps, x_delta=1e-3, x_samples=nx, y_delta=1e-3, y_samples=ny)
+    sound = fds.Acoustic2D(t_delta=1e-7, material=fds.AcousticMaterial(1500, 1000,
+                                                                      shear_viscosity=1e-3), **axes)
+    heat = fds.Thermal2D(t_delta=1e-3, material=fds.ThermalMaterial(900, 2700, 200), **axes)
+    sound.add_material_region(sound.get_rect_region((30e-3, 10e-3, 40e-3, 20e-3)),
+                              fds.AcousticMaterial(1200, 900, absorption_coef=7.7))
+    _randomise(sound, ('pressure', 'velocity_x', 'velocity_y'), seed=35)
+    yy, xx = np.mgrid[0:ny, 0:nx]
+    heat.temperature.values = (20 + 5 * np.sin(xx / 9.0) * np.cos(yy / 7.0)).reshape(-1)
+    sound.pressure.add_boundary(sound.get_point_region((68e-3, 22e-3)), value=_pulse(steps, 12, 5),
+                                additive=True)
+    sound.velocity_x.add_boundary(sound.get_line_region((0, 0, 0, (ny - 1) * 1e-3)))
+    heat.temperature.add_boundary(heat.get_line_region((0, 0, 0, (ny - 1) * 1e-3)), value=40)
+    sound.pressure.add_output(sound.get_point_region((100e-3, 30e-3)))
+    heat.temperature.add_output(heat.get_point_region((10e-3, 10e-3)))
+    law = fds.MaterialCouplingExponential(heat.temperature, sound, 'sound_velocity', a=0.8, b=-0.01,
+                                          stepping=4)
+    return fds.SynchronizedFields([sound, heat], [law]), steps
+
+
 COUPLED_SCENARIOS = {
+    'material_coupling_2d': material_coupling_2d,
     'thermoacoustic1d': thermoacoustic1d,
     'thermoacoustic1d_stepping': thermoacoustic1d_stepping,
     'boundary_coupling_linear': boundary_coupling_linear,

@@ -63,6 +63,20 @@ def test_device_session_equals_reference_golden_bitwise(library, name):
 
 
 @pytest.mark.gpu
+def test_two_dimensional_material_coupling_equals_reference_golden_bitwise(library):
+    """A 2-D target with a different material in every cell: the transfer function stays on the host
+    (NumPy, as in the reference), every re-assembly uploads per-cell coefficient arrays and the field
+    steps on the per-cell instantiation of the one-step kernel -- bitwise."""
+    name = 'material_coupling_2d'
+    group, steps = scenarios.COUPLED_SCENARIOS[name](fds)
+    got = _simulate_segmented(group, steps)
+    assert getattr(group, '_last_session', None) == 'per step'
+    _assert_bitwise(got, _golden(name), name)
+    engine = group.fields[0].__dict__['_engine_state'].engine
+    assert engine.last_launch_info()[2] == 'step2d_kernel<acoustic2d,lossy>'
+
+
+@pytest.mark.gpu
 def test_device_exponential_law_within_north_star_tolerance(library):
     """exp() on the device and in NumPy may differ in the last place: rel. L2 <= 1e-12
     (BASELINE.json north_star), not bitwise."""
