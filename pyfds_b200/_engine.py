@@ -685,6 +685,7 @@ def run(field, n_steps, progress_logger=None, advance=True):
         field.__dict__['_last_run_profile'] = {
             'prepare_and_tables_s': t1 - t0, 'page_lock_s': t2 - t1, 'simulate_call_s': t3 - t2,
             'signals_s': clock() - t3, 'pipeline_bands': engine.last_pipeline_bands()}
+        _log_throughput(field, engine, n_steps, t3 - t2)
         if advance:
             field.step += n_steps
         return
@@ -711,6 +712,22 @@ def run(field, n_steps, progress_logger=None, advance=True):
         'download_state_s': t4 - t3}
     if advance:
         field.step += n_steps
+
+
+def _log_throughput(field, engine, n_steps, seconds):
+    """One INFO line per call on the reference's logger (``pyfds``): steps, wall time of the engine
+    call (transfers included), cell updates per second and what that is in algorithmic bytes."""
+    import logging
+    logger = logging.getLogger('pyfds')
+    if not logger.isEnabledFor(logging.INFO) or seconds <= 0:
+        return
+    launches, per_launch, kernel = engine.last_launch_info()
+    rate = field.num_points * n_steps / seconds
+    bytes_per_update = 16 * (1 if field._device_model.startswith('thermal') else engine.ncomp)
+    logger.info('Device run: %d steps of %d cells in %.3f ms (%s, %d launches x %d steps): '
+                '%.2f Gcell-updates/s, %.0f GB/s algorithmic, host arrays in and out.',
+                n_steps, field.num_points, seconds * 1e3, kernel, launches, per_launch, rate / 1e9,
+                rate * bytes_per_update / 1e9)
 
 
 def reset(field):

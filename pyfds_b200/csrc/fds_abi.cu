@@ -1069,6 +1069,23 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     return fail(ctx, "stream2d: bad step count");
 }
 
+// Launch with programmatic stream serialisation (the kernels wait for their predecessor themselves).
+template <typename Kernel, typename... Args>
+cudaError_t launch_chained(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                           Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = getenv("FDS_NO_OVERLAP") ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // 1-D tiling: owned cells per CTA, halo and steps per launch.
 struct Plan1D {
     int tile, halo, steps, threads, per;
@@ -1149,9 +1166,11 @@ int launch_step1d(fds_ctx *ctx, const Step1DArgs &a, const StepTables &t, const 
                                                smem));
             configured = true;
         }
+        // consecutive launches of a long run are chained: the next grid is scheduled while this one
+        // runs and waits for it on the device (griddepcontrol.wait at the top of the kernel)
         const unsigned ctas = (unsigned)((p.ctas + kLineWarps - 1) / kLineWarps);
-        kernel<<<ctas, 32 * kLineWarps, smem, ctx->stream>>>(a, t, (int)p.ctas);
-        FDS_CUDA(ctx, cudaGetLastError());
+        FDS_CUDA(ctx, launch_chained(kernel, dim3(ctas), dim3(32 * kLineWarps), (size_t)smem,
+                                     ctx->stream, a, t, (int)p.ctas));
         return 0;
     }
     return p.per == 1 ? launch_step1d_as<THERMAL, LOSSY, 1>(ctx, a, t, p)
@@ -1829,23 +1848,6 @@ int group_member_step(fds_ctx *ctx, const StepTables &t, long long sig_index, lo
     ctx->last_steps_per_launch = 1;
     ctx->last_launches += 1;
     return 0;
-}
-
-// Launch with programmatic stream serialisation (the kernels wait for their predecessor themselves).
-template <typename Kernel, typename... Args>
-cudaError_t launch_chained(Kernel kernel, dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
-                           Args... args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = getenv("FDS_NO_OVERLAP") ? 0 : 1;
-    return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
 // Both members of a two-field group in one launch (line1d_pair_kernel).
