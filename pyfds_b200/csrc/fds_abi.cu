@@ -1639,6 +1639,8 @@ bool pipeline_applies(const fds_ctx *ctx, long long n_steps) {
     const long long launches = (n_steps + k - 1) / k;
     if (launches > 16) return false;                   // long runs: the transfers do not matter
     const long long reach = ctx->d.lossy ? 2 : 1;
+    // FDS_PIPELINE_FORCE (tests, sanitizer runs): also on grids too small for it to pay
+    if (getenv("FDS_PIPELINE_FORCE")) return ctx->d.rows >= 2 * (reach * n_steps + 64);
     // worth it from ~100 MB per component and as long as bands stay much taller than what a call's
     // steps eat off their upper end
     return ctx->d.rows >= 8 * (reach * n_steps + 64) && ctx->owned >= (8ll << 20);

@@ -35,10 +35,17 @@ def build(case):
         return scenarios._thermal2d(fds, 'Thermal2D', 256, 118, 14, seed=8)
     if case == 'line1d':
         return scenarios.acoustic1d_lossy(fds)
+    if case == 'pipeline':       # fds_simulate cut into row bands (FDS_PIPELINE_FORCE is set below)
+        return scenarios._acoustic2d(fds, lossy=False, nx=256, ny=420, steps=18, seed=9)
     raise SystemExit('unknown case ' + case)
 
 
 def single(case):
+    if case == 'pipeline':
+        os.environ['FDS_PIPELINE_FORCE'] = '1'
+        os.environ['FDS_PIPELINE_BANDS'] = '3'
+    if case == 'coupled':
+        return coupled()
     field, steps = build(case)
     field.simulate(steps // 2)
     field.simulate(steps - steps // 2)
@@ -48,6 +55,20 @@ def single(case):
     engine = field.__dict__['_engine_state'].engine
     print(case, 'kernel', engine.last_launch_info()[2], 'bitwise equal to the CPU restatement:', ok,
           flush=True)
+    return ok
+
+
+def coupled():
+    """A ThermoAcoustic1D group on the device (pair kernel, chained launches) against its golden."""
+    group, steps = scenarios.thermoacoustic1d_stepping(fds)
+    group.simulate(steps)
+    got = scenarios.collect_group(group)
+    golden = np.load(os.path.join(ROOT, 'tests', 'golden', 'coupled_thermoacoustic1d_stepping.npz'))
+    ok = all(np.array_equal(np.ascontiguousarray(got[k], dtype=np.float64).view(np.int64),
+                            np.ascontiguousarray(golden[k], dtype=np.float64).view(np.int64))
+             for k in golden.files if k != 'versions')
+    print('coupled session', getattr(group, '_last_session', None),
+          'bitwise equal to the reference golden:', ok, flush=True)
     return ok
 
 
