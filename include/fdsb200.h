@@ -273,6 +273,16 @@ int fds_comm_init(fds_ctx *ctx, const uint8_t id[128], int32_t rank, int32_t wor
 int fds_peer_export(fds_ctx *ctx, uint8_t *handles);
 int fds_peer_import(fds_ctx *ctx, int32_t side, const uint8_t *handles, int64_t neighbour_rows);
 
+/* The same for slabs that live in ONE process (one context per GPU, e.g. one host thread each): no NCCL
+ * communicator and no IPC -- fds_slab_init names the slab's place in the row partition, fds_peer_connect
+ * hands it the neighbour context itself (peer access is enabled between the two devices). At the start
+ * of every step call a slab copies the neighbours' edge rows into its halo rows (all slabs must have
+ * finished their uploads before any of them steps); after that the rows travel from inside the step
+ * kernels as above. The slabs' step calls must run concurrently (they wait for each other on the
+ * device). */
+int fds_slab_init(fds_ctx *ctx, int32_t rank, int32_t world);
+int fds_peer_connect(fds_ctx *ctx, int32_t side, fds_ctx *neighbour);
+
 /* --- measurement ------------------------------------------------------------------------------ */
 
 /* Device time in milliseconds of the step kernels launched by the last fds_step/fds_step_async call,

@@ -95,6 +95,8 @@ def load_library():
         'fds_comm_init': (ct.c_int, [p, p, i32, i32]),
         'fds_peer_export': (ct.c_int, [p, p]),
         'fds_peer_import': (ct.c_int, [p, i32, p, i64]),
+        'fds_slab_init': (ct.c_int, [p, i32, i32]),
+        'fds_peer_connect': (ct.c_int, [p, i32, p]),
         'fds_last_step_ms': (ct.c_int, [p, dptr]),
         'fds_last_launch_info': (ct.c_int, [p, ct.POINTER(i64), ct.POINTER(i64),
                                             ct.POINTER(ct.c_char_p)]),
@@ -307,6 +309,14 @@ class Engine:
         buf = (ct.c_uint8 * (7 * 64)).from_buffer_copy(bytes(handles))
         self._check(self.lib.fds_peer_import(self.handle, side, buf, neighbour_rows))
 
+    def slab_init(self, rank, world):
+        """This context is slab ``rank`` of ``world`` slabs that all live in this process."""
+        self._check(self.lib.fds_slab_init(self.handle, rank, world))
+
+    def peer_connect(self, side, neighbour):
+        """Wires the neighbour slab's context (same process) to side 0 (lower) / 1 (upper)."""
+        self._check(self.lib.fds_peer_connect(self.handle, side, neighbour.handle))
+
     def comm_init(self, unique_id, rank, world):
         buf = (ct.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
         self._check(self.lib.fds_comm_init(self.handle, buf, rank, world))
@@ -459,7 +469,7 @@ def halo_rows_for(field, world):
 
 
 def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None, lossy=None,
-            per_cell=False):
+            per_cell=False, state=None):
     """Creates (or reuses) the device context of ``field`` and uploads what ``assemble_matrices``
     froze: the material map and the coefficient tables. Returns the ``Engine``.
 
@@ -469,12 +479,14 @@ def prepare(field, device=0, row0=0, rows=None, halo_rows=0, kernel=None, lossy=
     steps per launch, whatever materials its own rows hold (default: decided from this window).
     ``per_cell``: give a 1-D field with per-point material vectors per-cell coefficient arrays even if
     its distinct value combinations would fit the material table (targets of a device-side material
-    law, whose coefficients are rewritten cell by cell)."""
+    law, whose coefficients are rewritten cell by cell). ``state``: where the context is kept (default:
+    the field's own slot; a run over several slabs in one process keeps one per slab)."""
     if kernel is None:
         kernel = getattr(field, 'device_kernel', 0)
-    state = field.__dict__.get('_engine_state')
     if state is None:
-        state = field.__dict__['_engine_state'] = _State()
+        state = field.__dict__.get('_engine_state')
+        if state is None:
+            state = field.__dict__['_engine_state'] = _State()
     baked = field._baked
     nx, ny = _grid(field)
     rows = ny if rows is None else rows
@@ -646,6 +658,20 @@ def run(field, n_steps, progress_logger=None, advance=True):
     import time
     clock = time.perf_counter
     t0 = clock()
+    # optional field attribute ``devices`` (or FDS_DEVICES=n): the CUDA ordinals of ONE process among
+    # which a 2-D field is cut into y-slabs -- the same simulate() call then runs on all of them
+    devices = _slab_devices(field)
+    if devices is not None:
+        from . import parallel
+        slabs = field.__dict__.get('_local_slabs')
+        if slabs is None or slabs.devices != devices:
+            if slabs is not None:
+                slabs.close()
+            slabs = field.__dict__['_local_slabs'] = parallel.LocalSlabs(field, devices)
+        slabs.simulate(n_steps, progress_logger)
+        if advance:
+            field.step += n_steps
+        return
     # optional field attribute ``device_index``: CUDA ordinal to run on (default 0)
     engine = prepare(field, device=int(getattr(field, 'device_index', 0)))
     first_step = field.step
@@ -714,6 +740,25 @@ def run(field, n_steps, progress_logger=None, advance=True):
         field.step += n_steps
 
 
+def _slab_devices(field):
+    """CUDA ordinals to spread a 2-D field over, or ``None`` for the single-GPU path: the field's
+    ``devices`` attribute (a sequence of ordinals, or a count), else the environment variable
+    ``FDS_DEVICES`` (a count). Needs slabs at least as tall as the halo the kernels consume."""
+    if not hasattr(field, 'y'):
+        return None
+    wanted = getattr(field, 'devices', None)
+    if wanted is None:
+        wanted = os.environ.get('FDS_DEVICES')
+        if wanted is None:
+            return None
+    if np.ndim(wanted) == 0:
+        wanted = list(range(int(wanted)))
+    devices = tuple(int(d) for d in wanted)
+    if len(devices) < 2 or field.y.samples // len(devices) < 16:
+        return None
+    return devices
+
+
 def _log_throughput(field, engine, n_steps, seconds):
     """One INFO line per call on the reference's logger (``pyfds``): steps, wall time of the engine
     call (transfers included), cell updates per second and what that is in algorithmic bytes."""
@@ -736,3 +781,7 @@ def reset(field):
     state = field.__dict__.get('_engine_state')
     if state is not None and state.engine is not None:
         state.engine.reset_state()
+    slabs = field.__dict__.get('_local_slabs')
+    if slabs is not None:
+        for engine in slabs.engines:
+            engine.reset_state()

@@ -191,6 +191,9 @@ struct fds_ctx {
     unsigned *peer_flags[2] = {nullptr, nullptr};
     long long peer_rows[2] = {0, 0};
     bool peer_open[2] = {false, false};
+    // slabs of ONE process (fds_peer_connect): the neighbour contexts themselves; no IPC, no NCCL
+    fds_ctx *local_neighbour[2] = {nullptr, nullptr};
+    bool local_peers = false;
     unsigned launch_seq = 0;
     // task table of the streaming launch that was enqueued last on `stream`, nothing else since
     // (nullptr otherwise): the next launch over the same table may overlap it
@@ -523,7 +526,8 @@ int launch_step2d(fds_ctx *ctx, const Step2DArgs &a, const StepTables &t) {
         const int tile_rows = g.tile_h + g.rows_below + g.rows_above;
         const int smem = tile_rows * kTilePitch * ((thermal ? 1 : 3) * 8 + (int)sizeof(map_t));
         auto kernel = tile2d_kernel<MODEL, LOSSY>;
-        static int configured = 0;
+        static int configured_by_device[64] = {};     // function attributes are per device
+        int &configured = configured_by_device[ctx->d.device & 63];
         if (configured < smem) {
             FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                smem));
@@ -959,7 +963,8 @@ template <int K, bool THERMAL, bool STATS, bool AXI>
 int launch_stream2d_as(fds_ctx *ctx, const Stream2DArgs &a) {
     auto kernel = stream2d_kernel<K, THERMAL, STATS, AXI>;
     const int smem = kStreamWarps * kS2WarpRingBytes;
-    static bool configured = false;
+    static bool configured_by_device[64] = {};     // function attributes are per device
+    bool &configured = configured_by_device[ctx->d.device & 63];
     if (!configured) {
         FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -987,7 +992,8 @@ int launch_streamv(fds_ctx *ctx, const StreamVArgs &av) {
     constexpr int CTAS = kSVCtasPerSm;
     auto kernel = streamv_kernel<K, AXI, VISC, CTAS>;
     const int smem = kStreamWarps * kS2WarpRingBytes;
-    static bool configured = false;
+    static bool configured_by_device[64] = {};     // function attributes are per device
+    bool &configured = configured_by_device[ctx->d.device & 63];
     if (!configured) {
         FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -1144,7 +1150,8 @@ Plan1D plan_1d(const fds_ctx *ctx, long long steps_left) {
 template <bool THERMAL, bool LOSSY, int PER>
 int launch_step1d_as(fds_ctx *ctx, const Step1DArgs &a, const StepTables &t, const Plan1D &p) {
     auto kernel = step1d_kernel<THERMAL, LOSSY, PER>;
-    static size_t configured = 0;
+    static size_t configured_by_device[64] = {};   // function attributes are per device
+    size_t &configured = configured_by_device[ctx->d.device & 63];
     if (configured < p.smem) {
         FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p.smem));
@@ -1160,7 +1167,8 @@ int launch_step1d(fds_ctx *ctx, const Step1DArgs &a, const StepTables &t, const 
     if (p.per == 0) {
         auto kernel = line1d_kernel<THERMAL, LOSSY>;
         const int smem = (int)(kLineWarps * sizeof(LineShared));
-        static bool configured = false;
+        static bool configured_by_device[64] = {};
+        bool &configured = configured_by_device[ctx->d.device & 63];
         if (!configured) {
             FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                smem));
@@ -1204,6 +1212,10 @@ int ensure_ring(fds_ctx *ctx, long long n_steps) {
 }
 
 // ---- peer-memory halo path ------------------------------------------------------------------------
+// A slab of a multi-GPU run: one process per GPU with an NCCL communicator (fds_comm_init), or several
+// contexts of one process wired to each other directly (fds_slab_init + fds_peer_connect).
+bool is_multi(const fds_ctx *ctx) { return ctx->world > 1 && (ctx->comm || ctx->local_peers); }
+
 bool peers_ready(const fds_ctx *ctx) {
     if (getenv("FDS_NO_PEER")) return false;
     if (ctx->rank > 0 && !ctx->peer_open[0]) return false;
@@ -1287,6 +1299,30 @@ void fill_halo_sync(fds_ctx *ctx, TaskSync &y, int which, unsigned wait_seq, boo
 
 int exchange_halos(fds_ctx *ctx, int which);
 
+// Slabs of one process, start of a call: the neighbours' edge rows of the current state (fresh uploads,
+// complete on every slab before any of them starts stepping -- the host side sees to that) are copied
+// into this slab's halo rows with peer copies on this slab's stream. From then on the rows travel from
+// inside the step kernels.
+int pull_halos_local(fds_ctx *ctx, int which) {
+    const long long nx = ctx->d.nx, h = ctx->d.halo_rows, rows = ctx->d.rows;
+    const size_t bytes = (size_t)(h * nx) * 8;
+    const int ncomp = ctx->thermal ? 1 : 3;
+    for (int side = 0; side < 2; ++side) {
+        fds_ctx *other = ctx->local_neighbour[side];
+        if (!other) continue;
+        for (int c = 0; c < ncomp; ++c) {
+            double *mine = origin(ctx, which, c);
+            const double *theirs = origin(other, which, c);
+            // lower neighbour: its top rows -> my lower halo; upper neighbour: its bottom rows -> my upper
+            double *dst = side == 0 ? mine - h * nx : mine + rows * nx;
+            const double *src = side == 0 ? theirs + (other->d.rows - h) * nx : theirs;
+            FDS_CUDA(ctx, cudaMemcpyPeerAsync(dst, ctx->d.device, src, other->d.device, bytes,
+                                              ctx->stream));
+        }
+    }
+    return 0;
+}
+
 // After a synchronisation: did a device-side wait (neighbour flag, task of the previous sweep) give up?
 int check_device_waits(fds_ctx *ctx) {
     unsigned err = 0;
@@ -1366,13 +1402,17 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
     ctx->last_steps_per_launch = 1;
     ctx->flow_shifts = 0;
 
-    if (ctx->comm && ctx->world > 1 && ctx->dims == 2) {
+    if (is_multi(ctx) && ctx->dims == 2) {
         // the neighbours' rows of the current state (fresh upload, or a previous call's last step)
-        FDS_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
-        FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
-        if (exchange_halos(ctx, ctx->cur)) return 1;
-        FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
-        FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+        if (ctx->local_peers) {
+            if (pull_halos_local(ctx, ctx->cur)) return 1;
+        } else {
+            FDS_CUDA(ctx, cudaEventRecord(ctx->ev_edge, ctx->stream));
+            FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_edge, 0));
+            if (exchange_halos(ctx, ctx->cur)) return 1;
+            FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+            FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+        }
     }
     FDS_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
     ctx->chain_tasks = nullptr;
@@ -1428,7 +1468,7 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 a.sig_index = sig0 + s;
                 a.ring_row = ring_row;
                 const long long rows = ctx->d.rows;
-                const bool multi = ctx->comm && ctx->world > 1;
+                const bool multi = is_multi(ctx);
                 int k = (int)std::min<long long>(std::min(ctx->max_k, stream_max_steps(ctx)),
                                                  chunk_steps - in_chunk);
                 // a slab can only advance as many steps as its halo rows cover
@@ -1527,7 +1567,7 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                 const long long rows = ctx->d.rows;
                 const long long last = first_step + s;
                 const bool shift = ctx->flow && flow_due(ctx, last);
-                if (ctx->comm && ctx->world > 1 && peers_ready(ctx)) {
+                if (is_multi(ctx) && peers_ready(ctx)) {
                     ++ctx->launch_seq;
                     if (peer_wait(ctx, in_chunk > 0 || chunk > 0)) return 1;
                     a.row_begin = 0; a.row_end = rows;
@@ -1535,7 +1575,7 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                     if (shift && launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
                     if (peer_push(ctx, ctx->cur ^ 1)) return 1;
                     ctx->last_launches += 1;
-                } else if (ctx->comm && ctx->world > 1 && shift) {
+                } else if (is_multi(ctx) && shift) {
                     a.row_begin = 0; a.row_end = rows;
                     if (dispatch_step2d(ctx, a, t)) return 1;
                     if (launch_flow(ctx, ctx->cur ^ 1, last)) return 1;
@@ -1545,7 +1585,7 @@ int run_steps(fds_ctx *ctx, long long first_step, long long n_steps, bool drain)
                     FDS_CUDA(ctx, cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
                     FDS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
                     ctx->last_launches += 1;
-                } else if (ctx->comm && ctx->world > 1) {
+                } else if (is_multi(ctx)) {
                     // edge bands first, so that their rows can travel while the interior computes
                     const long long band = std::min<long long>(ctx->d.halo_rows, rows);
                     a.row_begin = 0; a.row_end = band;
@@ -1634,7 +1674,7 @@ namespace {
 bool pipeline_applies(const fds_ctx *ctx, long long n_steps) {
     if (getenv("FDS_NO_PIPELINE")) return false;
     if (ctx->dims != 2 || !(ctx->use_stream2d || ctx->use_streamv)) return false;
-    if ((ctx->comm && ctx->world > 1) || ctx->flow) return false;
+    if (is_multi(ctx) || ctx->flow) return false;
     const int k = std::min(ctx->max_k, stream_max_steps(ctx));
     const long long launches = (n_steps + k - 1) / k;
     if (launches > 16) return false;                   // long runs: the transfers do not matter
@@ -1859,7 +1899,8 @@ template <int K0, int K1>
 int launch_pair(fds_group *g, const LinePairArgs &p, unsigned ctas, cudaStream_t stream) {
     auto kernel = line1d_pair_kernel<K0, K1>;
     const int smem = (int)(kLineWarps * sizeof(LineShared));
-    static bool configured = false;
+    static bool configured_by_device[64] = {};     // function attributes are per device
+    bool &configured = configured_by_device[g->members[0]->d.device & 63];
     if (!configured) {
         FDS_GCUDA(g, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
@@ -2132,7 +2173,7 @@ void fds_destroy(fds_ctx *ctx) {
     if (ctx->ctab) cudaFree(ctx->ctab);
     if (ctx->cvec) cudaFree(ctx->cvec);
     for (int side = 0; side < 2; ++side) {
-        if (!ctx->peer_open[side]) continue;
+        if (!ctx->peer_open[side] || ctx->local_peers) continue;
         for (int b = 0; b < 2; ++b)
             for (int c = 0; c < 3; ++c)
                 if (ctx->peer_base[side][b][c]) cudaIpcCloseMemHandle(ctx->peer_base[side][b][c]);
@@ -2972,6 +3013,45 @@ int fds_group_step(fds_group *g, int64_t first_step, int64_t n_steps, double *co
     g->members[0]->timed = true;
     if (rc) return 1;
     if (e != cudaSuccess) return gfail(g, std::string("fds_group_step: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+int fds_slab_init(fds_ctx *ctx, int32_t rank, int32_t world) {
+    if (!ctx) return fail(ctx, "fds_slab_init: null context");
+    if (world < 1 || rank < 0 || rank >= world) return fail(ctx, "fds_slab_init: bad rank/world");
+    if (world > 1 && ctx->d.halo_rows < 1)
+        return fail(ctx, "fds_slab_init: a multi-slab run needs halo_rows >= 1");
+    if (ctx->comm) return fail(ctx, "fds_slab_init: the context already joined an NCCL communicator");
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->local_peers = world > 1;
+    return 0;
+}
+
+int fds_peer_connect(fds_ctx *ctx, int32_t side, fds_ctx *neighbour) {
+    if (!ctx || !neighbour) return fail(ctx, "fds_peer_connect: null argument");
+    if (side < 0 || side > 1) return fail(ctx, "fds_peer_connect: side must be 0 (lower) or 1 (upper)");
+    if (!ctx->local_peers) return fail(ctx, "fds_peer_connect: call fds_slab_init first");
+    if (ctx->peer_open[side]) return fail(ctx, "fds_peer_connect: side already connected");
+    if (neighbour->d.nx != ctx->d.nx || neighbour->d.halo_rows != ctx->d.halo_rows ||
+        neighbour->d.model != ctx->d.model)
+        return fail(ctx, "fds_peer_connect: the neighbour is not a slab of the same field");
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    if (neighbour->d.device != ctx->d.device) {
+        int can = 0;
+        FDS_CUDA(ctx, cudaDeviceCanAccessPeer(&can, ctx->d.device, neighbour->d.device));
+        if (!can) return fail(ctx, "fds_peer_connect: no peer access between the two devices");
+        const cudaError_t e = cudaDeviceEnablePeerAccess(neighbour->d.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+            return fail(ctx, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+    }
+    for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 3; ++c) ctx->peer_base[side][b][c] = neighbour->buf[b][c];
+    ctx->peer_flags[side] = neighbour->flags;
+    ctx->peer_rows[side] = neighbour->d.rows;
+    ctx->local_neighbour[side] = neighbour;
+    ctx->peer_open[side] = true;
     return 0;
 }
 

@@ -151,6 +151,7 @@ class Field:
     def __getstate__(self):
         state = dict(self.__dict__)
         state.pop('_engine_state', None)
+        state.pop('_local_slabs', None)
         if '_operators' in state:       # lazy scipy views: rebuilt on demand, never shipped
             state['_operators'] = {}
         return state

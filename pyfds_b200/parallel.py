@@ -209,3 +209,123 @@ class SlabRun:
                 dist.broadcast(block, src=src)
                 values[row0 * nx:(row0 + rows) * nx] = block.cpu().numpy()
             component.values = values
+
+
+class LocalSlabs:
+    """All slabs of ``field`` in THIS process: one device context per GPU, wired to its neighbours
+    directly (``fds_slab_init`` / ``fds_peer_connect``: peer access, no IPC, no NCCL, no
+    ``torch.distributed``), and one host thread per slab for the duration of a call -- the slabs' step
+    calls wait for each other on the device, so they must be in flight together. This is what
+    ``field.simulate()`` runs on when the field has a ``devices`` attribute (or ``FDS_DEVICES`` is set):
+    the reference's call, all GPUs of the box, host ``values`` and ``signals`` complete afterwards."""
+
+    def __init__(self, field, devices, kernel=None):
+        if not hasattr(field, 'y'):
+            raise ValueError('Only 2-D fields are partitioned; 1-D problems stay on one GPU.')
+        self.field = field
+        self.devices = tuple(devices)
+        self.kernel = getattr(field, 'device_kernel', 0) if kernel is None else kernel
+        self.states = [_engine._State() for _ in self.devices]
+        self.engines = []
+
+    def close(self):
+        for state in self.states:
+            if state.engine is not None:
+                state.engine.close()
+                state.engine = None
+        self.engines = []
+
+    def _prepare(self):
+        field, world = self.field, len(self.devices)
+        if not field.matrices_assembled:
+            field.assemble_matrices()
+        parts = partition_rows(field.y.samples, world)
+        halo = halo_rows_for(field, world, self.kernel)
+        if min(rows for _, rows in parts) < halo:
+            raise ValueError('Slabs of {} rows are thinner than the {} halo rows needed.'.format(
+                min(rows for _, rows in parts), halo))
+        lossy = field._device_model.startswith('acoustic') and is_lossy(field)
+        engines = [_engine.prepare(field, device=device, row0=row0, rows=rows, halo_rows=halo,
+                                   kernel=self.kernel, lossy=lossy, state=state)
+                   for device, (row0, rows), state in zip(self.devices, parts, self.states)]
+        if len(engines) != len(self.engines) or \
+                any(a is not b for a, b in zip(engines, self.engines)):
+            # at least one context is new: wire all of them afresh
+            if self.engines and any(a is b for a, b in zip(engines, self.engines)):
+                self.close()
+                return self._prepare()
+            for rank, engine in enumerate(engines):
+                engine.slab_init(rank, world)
+            for rank, engine in enumerate(engines):
+                if rank > 0:
+                    engine.peer_connect(0, engines[rank - 1])
+                if rank < world - 1:
+                    engine.peer_connect(1, engines[rank + 1])
+            self.engines = engines
+        return parts
+
+    def simulate(self, num_steps, progress_logger=None):
+        """``num_steps`` x ``sim_step`` on all slabs (does not advance ``field.step``: the caller
+        does, as for the single-GPU path)."""
+        import threading
+        field = self.field
+        parts = self._prepare()
+        nx = field.x.samples
+        first_step = field.step
+        arrays = []
+        for name in field._device_components:
+            component = getattr(field, name)
+            values = _engine._host_values(component, field.num_points)
+            own = component.values
+            in_place = isinstance(own, np.ndarray) and own.ctypes.data == values.ctypes.data and \
+                own.nbytes == values.nbytes and values.flags.writeable
+            if not in_place:      # a list, another dtype, a read-only view: work on a copy
+                values = np.array(values, dtype=np.float64)
+                component.values = values
+            arrays.append(values)
+        layouts = [_engine.upload_run_tables(field, engine, first_step, num_steps)
+                   for engine in self.engines]
+        n_slots, layout = layouts[0]
+        uploaded = threading.Barrier(len(self.engines))
+        records, errors = [None] * len(self.engines), []
+
+        def work(rank):
+            engine, state = self.engines[rank], self.states[rank]
+            row0, rows = parts[rank]
+            cells = slice(row0 * nx, (row0 + rows) * nx)
+            try:
+                try:
+                    for c, values in enumerate(arrays):
+                        state.pin(engine.lib, c, values[cells])
+                        engine.upload_state(c, values[cells])
+                finally:
+                    uploaded.wait()          # a slab pulls its halos from the neighbours' uploads
+                records[rank] = engine.step(first_step, num_steps, n_slots)
+                for c, values in enumerate(arrays):
+                    engine.download_state(c, out=values[cells])
+            except Exception as exc:      # noqa: BLE001  (re-raised on the calling thread)
+                errors.append(exc)
+                uploaded.abort()
+
+        threads = [threading.Thread(target=work, args=(rank,)) for rank in range(len(self.engines))]
+        for thread in threads:
+            thread.start()
+        for thread in threads:
+            thread.join()
+        if errors:
+            raise errors[0]
+        if n_slots:
+            # every probe point is owned by exactly one slab: its record comes from that slab (picked,
+            # not summed -- a sum would turn a recorded -0.0 into +0.0)
+            cells = np.concatenate([np.asarray(output.region.indices, dtype=np.int64).reshape(-1)
+                                    for output, _, _ in layout])
+            first_cells = np.array([row0 * nx for row0, _ in parts], dtype=np.int64)
+            owner = np.searchsorted(first_cells, cells, side='right') - 1
+            merged = np.empty_like(records[0])
+            for rank, block in enumerate(records):
+                mine = owner == rank
+                merged[:, mine] = block[:, mine]
+            _engine._append_signals(layout, merged)
+        if progress_logger is not None:
+            for s in range(first_step, first_step + num_steps):
+                progress_logger.log(s)

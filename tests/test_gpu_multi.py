@@ -170,3 +170,30 @@ def test_other_halo_transports(library, name, env):
     _run_slabs(name, 0, 2, env)
     if _gpu_count() >= 4:
         _run_slabs(name, 0, 4, env)
+
+
+# ---- the same slabs in ONE process: field.simulate() with a `devices` attribute ------------------------
+# (contexts wired with fds_slab_init / fds_peer_connect, one host thread per slab; no torch.distributed)
+
+@pytest.mark.parametrize('world', [2, 3, 4, 8])
+@pytest.mark.parametrize('name', ['big_lossless', 'big_lossy', 'seams', 'flow_monotone',
+                                  'thermal2d_wide', 'big_axi_lossy', 'lossy_in_one_slab'])
+def test_simulate_on_several_devices_of_one_process_equals_single_domain(library, name, world):
+    if _gpu_count() < world:
+        pytest.skip('needs {} GPUs'.format(world))
+    field, steps = _build(name)
+    field.devices = list(range(world))
+    first = steps // 3
+    field.simulate(first)                       # the reference's call; all slabs behind it
+    field.simulate(steps - first)
+    slabs = field.__dict__.get('_local_slabs')
+    assert slabs is not None and len(slabs.engines) == world, 'the run did not use the devices'
+    got = scenarios.collect(field)
+    slabs.close()
+
+    fresh, _ = _build(name)
+    expected = scenarios.collect_stepper(restate.stepper_for(fresh).run(steps))
+    assert sorted(got) == sorted(expected)
+    for key in expected:
+        assert np.array_equal(bits(np.asarray(got[key])), bits(np.asarray(expected[key]))), \
+            (name, world, key)
