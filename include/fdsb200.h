@@ -280,6 +280,12 @@ int fds_peer_import(fds_ctx *ctx, int32_t side, const uint8_t *handles, int64_t 
  * finished their uploads before any of them steps); after that the rows travel from inside the step
  * kernels as above. The slabs' step calls must run concurrently (they wait for each other on the
  * device). */
+/* Everything a following fds_step over the same steps would allocate or load (flag tables, probe ring
+ * and pinned buffer, strip census, task tables, the kernels themselves), without stepping. Slabs of one
+ * process call it before the first of them starts stepping: with peer access enabled a device
+ * allocation synchronises with the peer devices, and a neighbour that is already waiting inside a step
+ * kernel for this slab would never let it return. */
+int fds_step_prepare(fds_ctx *ctx, int64_t first_step, int64_t n_steps);
 int fds_slab_init(fds_ctx *ctx, int32_t rank, int32_t world);
 int fds_peer_connect(fds_ctx *ctx, int32_t side, fds_ctx *neighbour);
 

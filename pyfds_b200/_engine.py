@@ -84,6 +84,7 @@ def load_library():
         'fds_reset_state': (ct.c_int, [p]),
         'fds_step': (ct.c_int, [p, i64, i64, p]),
         'fds_step_async': (ct.c_int, [p, i64, i64]),
+        'fds_step_prepare': (ct.c_int, [p, i64, i64]),
         'fds_simulate': (ct.c_int, [p, i64, i64, ct.POINTER(p), ct.POINTER(p), p]),
         'fds_last_pipeline_bands': (ct.c_int, [p, ct.POINTER(i64)]),
         'fds_sync': (ct.c_int, [p]),
@@ -247,6 +248,10 @@ class Engine:
         bands = ct.c_int64()
         self._check(self.lib.fds_last_pipeline_bands(self.handle, ct.byref(bands)))
         return bands.value
+
+    def step_prepare(self, first_step, n_steps):
+        """All allocations and loads of a following ``step`` over the same steps, without stepping."""
+        self._check(self.lib.fds_step_prepare(self.handle, first_step, n_steps))
 
     def step_async(self, first_step, n_steps):
         self._check(self.lib.fds_step_async(self.handle, first_step, n_steps))

@@ -194,6 +194,7 @@ struct fds_ctx {
     // slabs of ONE process (fds_peer_connect): the neighbour contexts themselves; no IPC, no NCCL
     fds_ctx *local_neighbour[2] = {nullptr, nullptr};
     bool local_peers = false;
+    bool dry_run = false;     // fds_step_prepare: everything a launch needs, but no launch
     unsigned launch_seq = 0;
     // task table of the streaming launch that was enqueued last on `stream`, nothing else since
     // (nullptr otherwise): the next launch over the same table may overlap it
@@ -534,11 +535,22 @@ int launch_step2d(fds_ctx *ctx, const Step2DArgs &a, const StepTables &t) {
             configured = smem;
         }
         const int ctas = std::min(g.n_tiles, 148 * 2);
+        if (ctx->dry_run) {
+            cudaFuncAttributes loaded;
+            FDS_CUDA(ctx, cudaFuncGetAttributes(&loaded, kernel));
+            return 0;
+        }
         kernel<<<ctas, kTileThreads, smem, ctx->stream>>>(a, t, ctx->d.n_materials + 1, g);
         FDS_CUDA(ctx, cudaGetLastError());
         return 0;
     }
     dim3 grid((unsigned)rows, (unsigned)((a.nx + 255) / 256));
+    if (ctx->dry_run) {
+        cudaFuncAttributes loaded;
+        if (ctx->cell_tab) return 0;
+        FDS_CUDA(ctx, cudaFuncGetAttributes(&loaded, step2d_kernel<MODEL, LOSSY>));
+        return 0;
+    }
     if (ctx->cell_tab) {
         constexpr bool axi = (MODEL == FDS_ACOUSTIC3DAXI || MODEL == FDS_THERMAL3DAXI);
         if (axi) return fail(ctx, "per-cell coefficients are not supported for axisymmetric models");
@@ -955,6 +967,11 @@ int launch_sweep(fds_ctx *ctx, Kernel kernel, long long ctas, int smem, const Ar
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = overlap ? 1 : 0;
+    if (ctx->dry_run) {   // make sure the kernel is loaded on this device (lazy module loading)
+        cudaFuncAttributes loaded;
+        FDS_CUDA(ctx, cudaFuncGetAttributes(&loaded, kernel));
+        return 0;
+    }
     FDS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kernel, args));
     return 0;
 }
@@ -1034,7 +1051,7 @@ int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
     a.sync.wait_deps = ctx->overlap && ctx->chain_tasks == plan->tasks;
     a.sync.n_edge_tasks[0] = plan->n_edge[0];
     a.sync.n_edge_tasks[1] = plan->n_edge[1];
-    ctx->chain_tasks = plan->tasks;
+    ctx->chain_tasks = ctx->dry_run ? nullptr : plan->tasks;
     a.map = ctx->map + ctx->pad + ctx->halo;
     a.tab = ctx->tab;
     a.tables = ctx->d_tables;
@@ -2592,6 +2609,59 @@ int fds_simulate(fds_ctx *ctx, int64_t first_step, int64_t n_steps, const double
 int fds_last_pipeline_bands(fds_ctx *ctx, int64_t *bands) {
     if (!ctx || !bands) return fail(ctx, "fds_last_pipeline_bands: null argument");
     *bands = ctx->last_bands;
+    return 0;
+}
+
+int fds_step_prepare(fds_ctx *ctx, int64_t first_step, int64_t n_steps) {
+    NvtxRange nvtx_range("fds:step prepare");
+    if (!ctx) return fail(ctx, "fds_step_prepare: null context");
+    if (n_steps <= 0) return 0;
+    if (!ctx->map_uploaded) return fail(ctx, "fds_step_prepare: material map not uploaded");
+    (void)first_step;
+    FDS_CUDA(ctx, cudaSetDevice(ctx->d.device));
+    if (refresh_flags(ctx)) return 1;
+    if (ensure_ring(ctx, n_steps)) return 1;
+    if (ctx->n_slots > 0) {
+        const size_t need = (size_t)n_steps * ctx->n_slots * 8;
+        if (ctx->pinned_bytes < need) {
+            if (ctx->pinned) cudaFreeHost(ctx->pinned);
+            ctx->pinned = nullptr;
+            ctx->pinned_bytes = 0;
+            const size_t alloc_bytes = std::max<size_t>(need, 1u << 20);
+            FDS_CUDA(ctx, cudaHostAlloc(&ctx->pinned, alloc_bytes, cudaHostAllocPortable));
+            ctx->pinned_bytes = alloc_bytes;
+        }
+    }
+    if (ctx->dims == 2) {
+        // everything the launches of the call may need: census, task tables for every step count a
+        // launch can have, the kernels themselves (lazy module loading), the helpers of the exchange
+        ctx->dry_run = true;
+        int rc = 0;
+        if (ctx->use_stream2d || ctx->use_streamv) {
+            const int kmax = std::min(ctx->max_k, stream_max_steps(ctx));
+            for (int k = 1; k <= kmax && !rc; ++k) {
+                Stream2DArgs a{};
+                a.nx = ctx->d.nx;
+                a.row_begin = 0;
+                a.row_end = ctx->d.rows;
+                rc = dispatch_stream2d(ctx, a, k);
+            }
+        } else {
+            Step2DArgs a{};
+            a.nx = ctx->d.nx;
+            a.row_begin = 0;
+            a.row_end = ctx->d.rows;
+            rc = dispatch_step2d(ctx, a, make_tables(ctx));
+        }
+        ctx->dry_run = false;
+        ctx->chain_tasks = nullptr;
+        if (rc) return 1;
+        cudaFuncAttributes loaded;
+        FDS_CUDA(ctx, cudaFuncGetAttributes(&loaded, halo_wait_kernel));
+        FDS_CUDA(ctx, cudaFuncGetAttributes(&loaded, halo_push_kernel));
+        FDS_CUDA(ctx, cudaFuncGetAttributes(&loaded, flow_shift_kernel));
+    }
+    FDS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 

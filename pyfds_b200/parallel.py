@@ -180,13 +180,15 @@ class SlabRun:
             if gather_probes and self.world > 1:
                 import torch
                 import torch.distributed as dist
-                # gloo/NCCL agnostic: go through a tensor on the backend's device
+                # gloo/NCCL agnostic: go through a tensor on the backend's device. The records are
+                # summed as BIT PATTERNS (int64): every slot is zero bits on all ranks but its owner,
+                # so the sum is the owner's sample bit for bit -- a float sum would turn -0.0 into +0.0
                 backend = dist.get_backend()
-                tensor = torch.from_numpy(records)
+                tensor = torch.from_numpy(np.ascontiguousarray(records).view(np.int64).copy())
                 if backend == 'nccl':
                     tensor = tensor.cuda()
                 dist.all_reduce(tensor)
-                records = tensor.cpu().numpy()
+                records = tensor.cpu().numpy().view(np.float64)
             _engine._append_signals(layout, records)
         field.__dict__['_last_run_profile']['probe_gather_s'] = clock() - t4
         field.step += num_steps
@@ -298,6 +300,10 @@ class LocalSlabs:
                     for c, values in enumerate(arrays):
                         state.pin(engine.lib, c, values[cells])
                         engine.upload_state(c, values[cells])
+                    # nothing may be allocated once a neighbour is stepping (it may already be waiting
+                    # for this slab on the device, and with peer access an allocation synchronises
+                    # with the peers): do it all now
+                    engine.step_prepare(first_step, num_steps)
                 finally:
                     uploaded.wait()          # a slab pulls its halos from the neighbours' uploads
                 records[rank] = engine.step(first_step, num_steps, n_slots)
