@@ -26,6 +26,9 @@ TAB = {'GX': 0, 'GY': 1, 'FX': 2, 'FY': 3, 'VM1': 4, 'VP1': 5, 'VMN': 6, 'VPN': 
 CTAB = {'FX': 0, 'VM1': 1, 'VP1': 2}
 CVEC = {'R': 0, 'RR': 1}
 
+#: a field is only cut into slabs of at least this many rows (twice the 4 halo rows a sweep consumes)
+MIN_SLAB_ROWS = 8
+
 #: upper bound for one probe drain buffer (steps per fds_step call are chunked to stay below it)
 MAX_PROBE_BYTES = 256 << 20
 
@@ -759,8 +762,8 @@ def _slab_devices(field):
     if np.ndim(wanted) == 0:
         wanted = list(range(int(wanted)))
     devices = tuple(int(d) for d in wanted)
-    if len(devices) < 2 or field.y.samples // len(devices) < 16:
-        return None
+    if len(devices) < 2 or field.y.samples // len(devices) < MIN_SLAB_ROWS:
+        return None      # slabs thinner than the edge bands of the kernels: one GPU does it
     return devices
 
 

@@ -187,9 +187,14 @@ def test_simulate_on_several_devices_of_one_process_equals_single_domain(library
     field.simulate(first)                       # the reference's call; all slabs behind it
     field.simulate(steps - first)
     slabs = field.__dict__.get('_local_slabs')
-    assert slabs is not None and len(slabs.engines) == world, 'the run did not use the devices'
+    from pyfds_b200 import _engine
+    if field.y.samples // world >= _engine.MIN_SLAB_ROWS:
+        assert slabs is not None and len(slabs.engines) == world, 'the run did not use the devices'
+    else:       # slabs would be thinner than the kernels' edge bands: one GPU does the whole field
+        assert slabs is None
     got = scenarios.collect(field)
-    slabs.close()
+    if slabs is not None:
+        slabs.close()
 
     fresh, _ = _build(name)
     expected = scenarios.collect_stepper(restate.stepper_for(fresh).run(steps))
