@@ -567,8 +567,8 @@ def upload_run_tables(field, engine, first_step, n_steps):
         table.cells = table.cells - engine.halo_rows * nx
         # Unchanged since the last call (an animator calling simulate(20) again and again): nothing to
         # send -- an upload marks the cell flags dirty and with them the task tables of the kernels.
-        mark = _fingerprint(table.cells, table.offsets, table.alpha, table.value, table.signal)
-        if sent.get(('bounds', c)) != mark:
+        mark = (table.cells, table.offsets, table.alpha, table.value, table.signal)
+        if not _same_arrays(sent.get(('bounds', c)), mark):
             engine.upload_boundaries(c, table)
             sent[('bounds', c)] = mark
     engine.upload_signals(np.array(signals, dtype=np.float64).reshape(len(signals), n_steps)
@@ -587,11 +587,27 @@ def upload_run_tables(field, engine, first_step, n_steps):
         cells, slots, _ = _bake.probe_table(component.outputs, base, own_lo, own_hi)
         tables.append((c, cells, slots))
     for c, cells, slots in tables:
-        mark = _fingerprint(cells, slots, np.asarray([slot]))
-        if sent.get(('probes', c)) != mark:
+        mark = (cells, slots, np.asarray([slot]))
+        if not _same_arrays(sent.get(('probes', c)), mark):
             engine.upload_probes(c, cells, slots, slot)
             sent[('probes', c)] = mark
     return slot, layout
+
+
+def _same_arrays(kept, fresh):
+    """True if ``kept`` (the arrays of the last upload, or None) equal ``fresh`` element for element,
+    dtype and shape included; floats are compared as bit patterns (a -0.0 is not a 0.0 here)."""
+    if kept is None or len(kept) != len(fresh):
+        return False
+    for a, b in zip(kept, fresh):
+        a, b = np.asarray(a), np.asarray(b)
+        if a.dtype != b.dtype or a.shape != b.shape:
+            return False
+        if a.dtype == np.float64:
+            a, b = np.ascontiguousarray(a).view(np.int64), np.ascontiguousarray(b).view(np.int64)
+        if not np.array_equal(a, b):
+            return False
+    return True
 
 
 def _fingerprint(*arrays):

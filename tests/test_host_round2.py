@@ -55,14 +55,19 @@ def test_linear_transfer_function_is_the_lambda_it_replaces():
     assert np.array_equal(target.values, -0.5 * values)
 
 
-def test_table_fingerprints_follow_content_not_identity():
+def test_tables_are_resent_on_content_not_identity():
     a = np.arange(10, dtype=np.int64)
     b = np.linspace(0, 1, 10)
+    assert _engine._same_arrays((a, b), (a.copy(), b.copy()))
+    assert not _engine._same_arrays(None, (a, b))
+    assert not _engine._same_arrays((a, b), (a, b + 1e-16 * (np.arange(10) == 3)))
+    assert not _engine._same_arrays((a, b), (a.astype(np.int32), b))
+    assert not _engine._same_arrays((a, b), (a[:9], b))
+    assert not _engine._same_arrays((np.zeros(2),), (-np.zeros(2),))      # -0.0 is not 0.0 here
+    assert _engine._same_arrays((np.zeros(0),), (np.zeros(0),))
     mark = _engine._fingerprint(a, b)
     assert mark == _engine._fingerprint(a.copy(), b.copy())
-    assert mark != _engine._fingerprint(a, b + 1e-16 * (np.arange(10) == 3))
     assert mark != _engine._fingerprint(a.astype(np.int32), b)
-    assert _engine._fingerprint(np.zeros(0)) != _engine._fingerprint(np.zeros(0, dtype=np.int32))
 
 
 def test_slab_devices_selection(monkeypatch):
