@@ -208,6 +208,8 @@ struct fds_ctx {
     bool use_streamv = false;  // streaming kernel of the viscous / axisymmetric acoustic models
     StepTables *d_tables = nullptr;   // device copy of the tables for the streaming kernel's slow path
     unsigned long long *stream_stats = nullptr;   // FDS_STREAM_STATS: counters of the streaming kernel
+    int sv_ctas = 0;   // resident CTAs per SM of the viscous kernel: 0 = by model (launch_streamv),
+                       // FDS_SV_CTAS = 2 or 3 overrides
     int *task_counters = nullptr;     // pool of zeroed work counters, one per streaming launch
     int next_counter = 0;
     int chunk_rows = 0;       // rows per streaming task (0 = heuristic)
@@ -699,6 +701,12 @@ void invalidate_plans(fds_ctx *ctx) {
     ctx->census_valid = false;
 }
 
+// Resident CTAs per SM of the viscous streaming kernel (see launch_streamv for the measurements).
+static int streamv_ctas_per_sm(const fds_ctx *ctx) {
+    if (ctx->sv_ctas) return ctx->sv_ctas;
+    return ctx->d.model == FDS_ACOUSTIC3DAXI ? 2 : kSVCtasPerSm;
+}
+
 // Task table of one streaming launch: every strip is cut into chunks of rows so that all tasks cost
 // about the same and fill a whole number of rounds over the 148 SMs x CTAs x warps.
 //   cost of a task = its rows + overhead, a row that takes the general row iteration counting
@@ -712,7 +720,7 @@ void invalidate_plans(fds_ctx *ctx) {
 int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int k, int lag_rows) {
     NvtxRange nvtx_range("fds:plan tasks");
     const long long rows = plan.row_end - plan.row_begin;
-    const double slots = 148.0 * (ctx->use_streamv ? kSVCtasPerSm : kS2CtasPerSm) * kStreamWarps;
+    const double slots = 148.0 * (ctx->use_streamv ? streamv_ctas_per_sm(ctx) : kS2CtasPerSm) * kStreamWarps;
     const double overhead = 2.0 * lag_rows + 4.0;
     // measured on B200 (4096^2, bench.py, 3 CTAs/SM): 1.5 and 2.5 -> 346, 4 -> 341 Gcell-updates/s.
     double general_weight = 2.5;
@@ -1001,23 +1009,37 @@ int launch_stream2d(fds_ctx *ctx, const Stream2DArgs &a) {
                    : launch_stream2d_as<K, THERMAL, false, false>(ctx, a);
 }
 
-// Resident CTAs per SM (measured on B200, Gcell-updates/s at K = 2, lossy Acoustic2D 4096^2 /
-// Acoustic3DAxi 8192x4096): 2 CTAs (no spills) 164 / 109, 3 CTAs (168 registers, a few spills in the
-// general row iteration) 172 / 110, 4 CTAs (128 registers, spills in the loop) 122 / 69.
-template <int K, bool AXI, bool VISC>
-int launch_streamv(fds_ctx *ctx, const StreamVArgs &av) {
-    constexpr int CTAS = kSVCtasPerSm;
+// Resident CTAs per SM, measured on B200 at K = 2 in Gcell-updates/s (lossy Acoustic2D 4096^2 /
+// lossy Acoustic3DAxi 8192 x 4096; profiles/r2_c18_ab.jsonl): 3 CTAs (12 warps, 168 registers, spills
+// in and around the steady loop) 161 / 106, 2 CTAs (8 warps, 188 / 204 registers, no spills)
+// 160 / 121; 4 CTAs (128 registers) 122 / 69 (round 1). The axisymmetric body holds 14 more
+// per-column coefficients and the quotient's operands: it runs with 2 CTAs, the plain one with 3.
+template <int K, bool AXI, bool VISC, int CTAS>
+int launch_streamv_ctas(fds_ctx *ctx, const StreamVArgs &av) {
     auto kernel = streamv_kernel<K, AXI, VISC, CTAS>;
     const int smem = kStreamWarps * kS2WarpRingBytes;
     static bool configured_by_device[64] = {};     // function attributes are per device
     bool &configured = configured_by_device[ctx->d.device & 63];
     if (!configured) {
         FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        // the ring plus the per-column coefficient slots of three CTAs: ~190 KB of the SM's 228
+        FDS_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     const long long want = (av.base.n_tasks + kStreamWarps - 1) / kStreamWarps;
     const long long ctas = std::min<long long>(want, 148 * CTAS);
     return launch_sweep(ctx, kernel, ctas, smem, av, av.base.sync.wait_deps != 0);
+}
+
+template <int K, bool AXI, bool VISC>
+int launch_streamv(fds_ctx *ctx, const StreamVArgs &av) {
+    if constexpr (K == 1) {   // the odd last step of a run
+        return launch_streamv_ctas<K, AXI, VISC, kSVCtasPerSm>(ctx, av);
+    } else {
+        return streamv_ctas_per_sm(ctx) == 2 ? launch_streamv_ctas<K, AXI, VISC, 2>(ctx, av)
+                                : launch_streamv_ctas<K, AXI, VISC, 3>(ctx, av);
+    }
 }
 
 int dispatch_stream2d(fds_ctx *ctx, Stream2DArgs a, int k) {
@@ -2116,6 +2138,7 @@ int fds_create(const fds_desc *desc, fds_ctx **out) {
     if (const char *env = getenv("FDS_CHUNK_ROWS")) ctx->chunk_rows = atoi(env);
     if (const char *env = getenv("FDS_HALO_1D")) ctx->halo_1d = std::max(2, atoi(env) / 2 * 2);
     if (getenv("FDS_NO_OVERLAP")) ctx->overlap = false;
+    if (const char *env = getenv("FDS_SV_CTAS")) ctx->sv_ctas = atoi(env) == 2 ? 2 : 3;
     if (getenv("FDS_HALO_KERNELS")) ctx->halo_in_kernel = false;
     if (const char *env = getenv("FDS_MAX_K"))
         ctx->max_k = std::max(1, std::min(kMaxStreamSteps, atoi(env)));

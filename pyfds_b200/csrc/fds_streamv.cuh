@@ -41,7 +41,10 @@ struct StreamVArgs {
     int n_mat1;
 };
 
-constexpr int kSVCtasPerSm = 12 / kStreamWarps;             // resident CTAs per SM (register budget: 168)
+#ifndef FDS_SV_CTAS
+#define FDS_SV_CTAS (12 / FDS_STREAM_WARPS)
+#endif
+constexpr int kSVCtasPerSm = FDS_SV_CTAS;                   // resident CTAs per SM (register budget: 168)
 constexpr int kMaxStreamVSteps = 2;         // K: bounded by the strip halo (see above)
 
 // Coefficients of this lane's cells on steady rows (the same for rows q, q-1, q-2: steady rows repeat
@@ -57,20 +60,75 @@ struct SVCoef {
     double vm1[C], vp1[C];       // a_v_v x diagonals: entry of cell c-1 / of cell c+1
     double eb[C];                // axisymmetric extra term dt*mu/rho of cell c
     double r[C + 1], rr[C];      // axisymmetric: r of columns x0 .. x0+C, r^2 of x0 .. x0+C-1
+    double ry[C];                // axisymmetric: 1 / r^2 rounded to nearest (sv_quotient)
 };
+
+// The axisymmetric model divides by r^2 in every cell and stage (pyfds/acoustics.py:210-212). nvcc
+// expands an IEEE division into a reciprocal seed, four Newton steps, the quotient, a residual
+// correction and a guarded call of a slow path: ~22 instructions in one serial chain, and the guard's
+// branch cuts the stage into basic blocks the scheduler cannot move work across. The divisor only
+// depends on the column, so its correctly rounded reciprocal y = RN(1 / b) is computed once per steady
+// run (with the IEEE division) and a cell needs three operations:
+//     q0 = RN(a y);   t = b q0 - a  (exact, one fma);   q = RN(q0 - t y)
+// q is the correctly rounded a / b (Markstein 1990: y correctly rounded, q0 within one ulp, the
+// residual exact) as long as nothing under- or overflows on the way and the significand of b is not
+// all ones: 2^-256 <= b <= 2^256 and 2^-693 <= |a| <= 2^677 guarantee that (the residual is a
+// multiple of 2^(e_a - 106) or larger, q0 and q stay normal). Written as q0 - t y, signed zeros come
+// out right as well: a = +-0 gives q0 = +-0, t = +0, q = +-0. The numerator is a = eb * vx with eb a
+// material constant, so "vx is zero or 2^-493 <= |vx| <= 2^477" (sv_covered) together with
+// 2^-200 <= eb <= 2^200 is sufficient; the steady loop checks the four rows of vx an iteration
+// divides BEFORE it starts the iteration and runs the iteration with the IEEE division otherwise
+// (denormals and the leading edge of a pulse that decays towards them, infinities, NaN).
+// tests/test_fast_division.py runs the same sequence against the division on the CPU.
+constexpr unsigned kDivHiLo = (1023u - 493u) << 20;    // high word of 2^-493
+constexpr unsigned kDivHiSpan = (493u + 477u) << 20;   // ... up to 2^477
+__device__ __forceinline__ double sv_quotient(double a, double b, double y) {
+    const double q0 = mul(a, y);
+    const double t = __fma_rn(b, q0, -a);
+    return __fma_rn(-t, y, q0);
+}
+__device__ __forceinline__ bool sv_covered(double vx) {
+    const unsigned h = (unsigned)__double2hiint(vx) & 0x7fffffffu;
+    return h - kDivHiLo < kDivHiSpan || (h | (unsigned)__double2loint(vx)) == 0u;
+}
+// positive, exponent within +-`range`, significand not all ones
+__device__ __forceinline__ bool sv_moderate(double b, unsigned range) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(b);
+    const unsigned e = (unsigned)(u >> 52);
+    return e >= 1023u - range && e <= 1023u + range &&
+           (u & 0xfffffffffffffull) != 0xfffffffffffffull;
+}
+#ifndef FDS_SV_FASTDIV
+#define FDS_SV_FASTDIV 1
+#endif
+#ifndef FDS_SV_COLSMEM
+#define FDS_SV_COLSMEM 1
+#endif
+
 
 // One stage on a steady row: `cur` = row q at level s on entry, row q-2 at level s+1 on exit.
 // pA/uA/vA = p (after boundaries), old vx, old vy of row q-1; pB/uB/vB = the same of row q-2 on entry
 // and of row q on exit (the next row's "A": the caller swaps the roles). U/V = new vx, vy of row q-2
 // (read), Un/Vn = new vx, vy of row q-1 (written). CC, ca, cv: as in steady_stage (fds_stream2d.cuh).
-template <bool AXI, bool VISC, int CC>
+template <bool AXI, bool VISC, int CC, bool EXACT = true>
 __device__ __forceinline__ void sv_steady_stage(
     double (&cur)[3][kS2LaneCells], const double (&pA)[kS2LaneCells],
     const double (&uA)[kS2LaneCells], const double (&vA)[kS2LaneCells], double (&pB)[kS2LaneCells],
     double (&uB)[kS2LaneCells], double (&vB)[kS2LaneCells], const double (&U)[kS2LaneCells],
     const double (&V)[kS2LaneCells], double (&Un)[kS2LaneCells], double (&Vn)[kS2LaneCells],
-    const SVCoef &k, const double (&ca)[kS2LaneCells], const double (&cv)[kS2LaneCells]) {
+    const SVCoef &ku, const double (&ca)[kS2LaneCells], const double (&cv)[kS2LaneCells],
+    const double2 *col = nullptr) {
     constexpr int C = kS2LaneCells;
+    static_assert(C == 2, "the per-column slots are pairs");
+    SVCoef k = ku;
+    if (AXI && FDS_SV_COLSMEM) {
+        // per-column coefficients of this lane: re-read for every stage instead of held in registers
+        const double2 a0 = col[0 * 32], a1 = col[1 * 32], a2 = col[2 * 32], a3 = col[3 * 32];
+        const double2 a4 = col[4 * 32], a5 = col[5 * 32], a6 = col[6 * 32];
+        k.fx[0] = a0.x; k.fx[1] = a0.y; k.fx[2] = a1.x; k.r[0] = a1.y; k.r[1] = a2.x; k.r[2] = a2.y;
+        k.vm1[0] = a3.x; k.vm1[1] = a3.y; k.vp1[0] = a4.x; k.vp1[1] = a4.y;
+        k.rr[0] = a5.x; k.rr[1] = a5.y; k.ry[0] = a6.x; k.ry[1] = a6.y;
+    }
     if (CC == 0) {
 #pragma unroll
         for (int c = 0; c < C; ++c) cur[0][c] = add(mul(ca[c], cur[0][c]), cv[c]);
@@ -101,7 +159,9 @@ __device__ __forceinline__ void sv_steady_stage(
             vis = add(vis, mul(k.vp1[c], ur));
             vis = add(vis, mul(k.vpn[c], cur[1][c]));
             double rhs = sub(du, vis);
-            if (AXI) rhs = add(rhs, mul(k.eb[c], uold) / k.rr[c]);
+            if (AXI)
+                rhs = add(rhs, EXACT ? mul(k.eb[c], uold) / k.rr[c]
+                                     : sv_quotient(mul(k.eb[c], uold), k.rr[c], k.ry[c]));
             Un[c] = sub(uold, rhs);
             double visv = acc0(mul(k.vmn[c], vB[c]));
             visv = add(visv, mul(k.vm1[c], vl));
@@ -149,6 +209,7 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double tabs[FDS_TAB_COUNT][kMaxMaterials];
     __shared__ double cls_alpha[3][kMaxClasses], cls_value[K][3][kMaxClasses];
+    __shared__ double2 colco[AXI && FDS_SV_COLSMEM ? kStreamWarps * 7 * 32 : 1];
 
     for (int k = threadIdx.x; k < FDS_TAB_COUNT * kMaxMaterials; k += blockDim.x)
         (&tabs[0][0])[k] = a.tab[k];
@@ -304,6 +365,8 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
             if (a.stats && lane == 0) atomicAdd(a.stats + (UNI ? CC + 1 : 4), 1ull);
             const unsigned my_ids = info[0].ids;
             SVCoef k;
+            constexpr bool kFast = AXI && VISC && FDS_SV_FASTDIV;   // sv_quotient
+            bool fast_run = true;   // this lane's r^2 and eb are in the range sv_quotient covers
             {
                 const unsigned material = info[0].bits & kIdMask;
                 const unsigned left = __shfl_up_sync(0xffffffffu, my_ids, 1) >> (16 * (C - 1));
@@ -336,6 +399,11 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
                     k.gy[c] = UNI ? u_gy : tab(FDS_TAB_GY, c);
                     k.fy[c] = UNI ? u_fy : tab(FDS_TAB_FY, c);
                     if (AXI) k.rr[c] = __ldg(av.cvec + FDS_CVEC_RR * nx + col_of(c));
+                    k.ry[c] = 0.0;
+                    if (kFast) {
+                        fast_run = fast_run && sv_moderate(k.rr[c], 256u);
+                        k.ry[c] = 1.0 / k.rr[c];
+                    }
                     if (VISC) {
                         k.v0[c] = UNI ? u_v0 : tab(FDS_TAB_V0, c);
                         k.vmn[c] = UNI ? u_vmn : tab(FDS_TAB_VMN, c);
@@ -345,8 +413,21 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
                                        : UNI ? u_vm1 : tab(FDS_TAB_VM1, c - 1);
                         k.vp1[c] = AXI ? ctab(FDS_CTAB_VP1, mat(c + 1), col_of(c + 1))
                                        : UNI ? u_vp1 : tab(FDS_TAB_VP1, c + 1);
+                        if (kFast) fast_run = fast_run && (k.eb[c] == 0.0 || sv_moderate(k.eb[c], 200u));
                     }
                 }
+            }
+            double2 *col = colco + (AXI && FDS_SV_COLSMEM ? warp * 7 * 32 + lane : 0);
+            if (AXI && FDS_SV_COLSMEM) {
+                __syncwarp();
+                col[0 * 32] = make_double2(k.fx[0], k.fx[1]);
+                col[1 * 32] = make_double2(k.fx[2], k.r[0]);
+                col[2 * 32] = make_double2(k.r[1], k.r[2]);
+                col[3 * 32] = make_double2(k.vm1[0], k.vm1[1]);
+                col[4 * 32] = make_double2(k.vp1[0], k.vp1[1]);
+                col[5 * 32] = make_double2(k.rr[0], k.rr[1]);
+                col[6 * 32] = make_double2(k.ry[0], k.ry[1]);
+                __syncwarp();
             }
             double ca[C], cv[K][C];
 #pragma unroll
@@ -357,13 +438,15 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
 #pragma unroll
                 for (int s = 0; s < K; ++s) cv[s][c] = kc ? cls_value[s][CC < 0 ? 0 : CC][kc] : -0.0;
             }
-            for (;;) {
-                double cur[3][C], un1[K][C], vn1[K][C];
-                load_row(cur, ring + slot * kS2SlotBytes);
+            // rows r and r+1 through the K stages (`exact_tag`: with the IEEE division)
+            auto two_rows = [&](double (&cur)[3][C], auto exact_tag) {
+                constexpr bool EXACT = decltype(exact_tag)::value;
+                double un1[K][C], vn1[K][C];
 #pragma unroll
                 for (int s = 0; s < K; ++s)
-                    sv_steady_stage<AXI, VISC, CC>(cur, pA[s], uA[s], vA[s], pB[s], uB[s], vB[s],
-                                                   un[s], vn[s], un1[s], vn1[s], k, ca, cv[s]);
+                    sv_steady_stage<AXI, VISC, CC, EXACT>(cur, pA[s], uA[s], vA[s], pB[s], uB[s],
+                                                          vB[s], un[s], vn[s], un1[s], vn1[s], k, ca,
+                                                          cv[s], col);
                 store_row(cur, r - kLag, cell_r - kLag * nx);
 
                 load_row(cur, ring + (slot + 1) * kS2SlotBytes);
@@ -371,9 +454,38 @@ __global__ void __launch_bounds__(kStreamWarps * 32, CTAS) streamv_kernel(Stream
                 if (lane == 0 && r + kS2RingDepth < r1) issue_pair(r + kS2RingDepth, slot);
 #pragma unroll
                 for (int s = 0; s < K; ++s)
-                    sv_steady_stage<AXI, VISC, CC>(cur, pB[s], uB[s], vB[s], pA[s], uA[s], vA[s],
-                                                   un1[s], vn1[s], un[s], vn[s], k, ca, cv[s]);
+                    sv_steady_stage<AXI, VISC, CC, EXACT>(cur, pB[s], uB[s], vB[s], pA[s], uA[s],
+                                                          vA[s], un1[s], vn1[s], un[s], vn[s], k, ca,
+                                                          cv[s], col);
                 store_row(cur, r + 1 - kLag, cell_r + nx - kLag * nx);
+            };
+            for (;;) {
+                double cur[3][C];
+                load_row(cur, ring + slot * kS2SlotBytes);
+                if (kFast) {
+                    // the vx rows this iteration divides: stage s of row r takes the old vx of its
+                    // row q-1 (uA[s]), stage s of row r+1 what stage s of row r receives as row q
+                    // (the row just loaded; the new vx the stage before has in hand)
+                    bool covered = true;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        covered &= sv_covered(cur[1][c]);
+#pragma unroll
+                        for (int s = 0; s < K; ++s) {
+                            covered &= sv_covered(uA[s][c]);
+                            if (s + 1 < K) covered &= sv_covered(un[s][c]);
+                        }
+                    }
+                    if (__builtin_expect(
+                            __all_sync(0xffffffffu, !lane_relevant || (covered && fast_run)), 1)) {
+                        two_rows(cur, std::false_type{});
+                    } else {
+                        if (a.stats && lane == 0) atomicAdd(a.stats + 7, 1ull);
+                        two_rows(cur, std::true_type{});
+                    }
+                } else {
+                    two_rows(cur, std::true_type{});
+                }
                 cell_r += 2 * nx;
                 r += 2;
                 slot = slot + 2 == kS2RingDepth ? 0 : slot + 2;

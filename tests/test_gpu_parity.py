@@ -545,3 +545,73 @@ def test_viscous_streaming_kernel_steady_variants(library, klass, lossy, pattern
 def test_viscous_streaming_kernel_steady_variants_vs_oracle(library, klass, lossy, pattern):
     f = _steady_case(pattern, 192, 97, 11, seed=75, kernel=2, klass=klass, lossy=lossy)
     _vs_oracle(f, 11, 'streamv steady {} {} vs oracle'.format(klass, pattern))
+
+
+# ---- the axisymmetric kernel's division by r^2 (sv_quotient in fds_streamv.cuh) -------------------------
+
+def _division_ranges_case(kernel, pattern='plain', steps=9, nx=256, ny=118):
+    """Lossy Acoustic3DAxi whose velocity_x holds everything the quotient sequence must tell apart:
+    zeros of both signs, denormals, values either side of the 2^-493 and 2^477 limits of the fast
+    sequence, tiny and ordinary normals -- in row blocks and scattered."""
+    f = _steady_case(pattern, nx, ny, steps, seed=91, kernel=kernel, klass='Acoustic3DAxi',
+                     lossy=True)
+    rng = np.random.default_rng(92)
+    vx = np.array(f.velocity_x.values, dtype=np.float64).reshape(ny, nx)
+    sign = np.where(rng.random((ny, nx)) < 0.5, -1.0, 1.0)
+    mant = 1.0 + rng.random((ny, nx))
+    vx[50:57] = 0.0 * sign[50:57]                                   # +0.0 and -0.0
+    vx[57:63] = sign[57:63] * rng.integers(1, 2 ** 40, (6, nx)) * 5e-324    # denormals
+    expo = rng.integers(-497, -489, (8, nx))
+    vx[63:71] = sign[63:71] * np.ldexp(mant[63:71], expo)           # around 2^-493
+    vx[71:76] = sign[71:76] * mant[71:76] * 1e-300
+    expo = rng.integers(474, 480, (7, nx))
+    vx[76:83] = sign[76:83] * np.ldexp(mant[76:83], expo)           # around 2^477
+    scatter = rng.random((7, nx))
+    tail = vx[83:90]
+    tail[scatter < 0.2] = 0.0
+    tail[(scatter >= 0.2) & (scatter < 0.3)] = -0.0
+    tail[(scatter >= 0.3) & (scatter < 0.4)] = 3e-320
+    tail[(scatter >= 0.4) & (scatter < 0.45)] = -2.0 ** -493
+    tail[(scatter >= 0.45) & (scatter < 0.5)] = np.nextafter(2.0 ** -493, 0.0)
+    f.velocity_x.values = vx.reshape(-1)
+    return f
+
+
+@pytest.mark.parametrize('pattern', ['plain', 'vx_walls', 'signal_vx'])
+def test_axisymmetric_division_fast_and_exact_iterations(library, pattern, monkeypatch):
+    """Bitwise against the one-step kernel (IEEE division in every cell) and against the CPU
+    restatement; the counters prove that both kinds of iteration ran."""
+    monkeypatch.setenv('FDS_STREAM_STATS', '1')
+    results = []
+    for kernel in (1, 2):
+        f = _division_ranges_case(kernel, pattern)
+        f.simulate(5)
+        f.simulate(4)
+        results.append(scenarios.collect(f))
+        if kernel == 2:
+            engine = f.__dict__['_engine_state'].engine
+            assert 'streamv' in engine.last_launch_info()[2]
+            stats = engine.stream_stats()
+    assert_same(results[1], results[0], 'division ranges, streamv vs one-step kernel')
+    assert sum(stats[:4]) > 0 and stats[6] > 0, stats
+    exact_iterations = stats[7]
+    assert 0 < exact_iterations < stats[6] // 2, stats     # some, not all row pairs
+    g = _division_ranges_case(2, pattern)
+    _vs_oracle(g, 9, 'division ranges vs oracle')
+
+
+def test_axisymmetric_division_quiet_field_stays_on_fast_iterations(library, monkeypatch):
+    """A field at rest (all zeros) with a source: zeros are covered by the fast sequence, so only the
+    rows the leading edge of the pulse reaches (values decaying towards the denormals) may take the
+    exact iterations."""
+    monkeypatch.setenv('FDS_STREAM_STATS', '1')
+    f = _steady_case('plain', 256, 118, 12, seed=93, kernel=2, klass='Acoustic3DAxi', lossy=True)
+    for name in ('pressure', 'velocity_x', 'velocity_y'):
+        getattr(f, name).values = np.zeros(f.num_points)
+    stepper = restate.stepper_for(f)
+    stepper.run(12)
+    f.simulate(12)
+    assert_same(scenarios.collect(f), scenarios.collect_stepper(stepper), 'quiet axisymmetric field')
+    stats = f.__dict__['_engine_state'].engine.stream_stats()
+    assert stats[7] < stats[6] // 4, stats
+
