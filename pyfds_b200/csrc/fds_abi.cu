@@ -720,7 +720,9 @@ static int streamv_ctas_per_sm(const fds_ctx *ctx) {
 int build_stream_plan(fds_ctx *ctx, fds_ctx::StreamPlan &plan, int n_strips, int k, int lag_rows) {
     NvtxRange nvtx_range("fds:plan tasks");
     const long long rows = plan.row_end - plan.row_begin;
-    const double slots = 148.0 * (ctx->use_streamv ? streamv_ctas_per_sm(ctx) : kS2CtasPerSm) * kStreamWarps;
+    // (the viscous kernel: 12 warps per SM also where it runs with 2 resident CTAs -- config 3 with
+    // 2 CTAs: tasks cut for 8 warps per SM 117.8, for 12 warps per SM 121.4 Gcell-updates/s)
+    const double slots = 148.0 * (ctx->use_streamv ? kSVCtasPerSm : kS2CtasPerSm) * kStreamWarps;
     const double overhead = 2.0 * lag_rows + 4.0;
     // measured on B200 (4096^2, bench.py, 3 CTAs/SM): 1.5 and 2.5 -> 346, 4 -> 341 Gcell-updates/s.
     double general_weight = 2.5;
