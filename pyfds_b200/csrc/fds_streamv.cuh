@@ -20,13 +20,16 @@
 // with class operations on at most one component, or several materials -- interfaces along y --
 // without operations) run through a branch-free body that takes two rows per
 // iteration; the two window rows swap roles between the halves of the iteration, so no register is
-// moved. Material coefficients -- and, for the axisymmetric model, the per-column values of this
-// lane's cells and of its two neighbours (a_p_vx / r, the viscous x diagonals with the 1/r term, r,
-// r^2) -- are loaded into registers when such a run starts. Every other row takes the general row
-// iteration: one rolled copy of the stage code with per-cell coefficient lookups, inline classes and
-// the table slow path.
+// moved. Material coefficients are loaded into registers when such a run starts; for the
+// axisymmetric model the per-column values of this lane's cells and of its two neighbours (a_p_vx / r,
+// the viscous x diagonals with the 1/r term, r, r^2, 1 / r^2) go to per-lane shared-memory slots and
+// are re-read for every row (FDS_SV_COLSMEM). Every other row takes the general row iteration: one
+// rolled copy of the stage code with per-cell coefficient lookups, inline classes and the table slow
+// path.
 //
-// Every value is produced by the same __dmul_rn/__dadd_rn sequence as cell_body in fds_step2d.cuh.
+// Every value is produced by the same __dmul_rn/__dadd_rn sequence as cell_body in fds_step2d.cuh;
+// the one exception, the axisymmetric model's division by r^2 in steady rows, is a sequence that
+// returns the IEEE quotient bit for bit (sv_quotient below).
 #pragma once
 
 #include "fds_common.cuh"
