@@ -30,6 +30,34 @@ def build(force=False):
     return LIBRARY
 
 
+QUOTIENT_SOURCE = os.path.join(_HERE, 'quotient_check.c')
+QUOTIENT_BINARY = os.path.join(OUT_DIR, 'quotient_check')
+
+
+def build_quotient_check(force=False):
+    """Compiles ``oracle/quotient_check.c`` (the CPU check of the axisymmetric kernel's quotient
+    sequence against the IEEE division; run by tests/test_fast_division.py) into ``oracle/_ref/``."""
+    if not force and os.path.exists(QUOTIENT_BINARY) and \
+            os.path.getmtime(QUOTIENT_BINARY) >= os.path.getmtime(QUOTIENT_SOURCE):
+        return QUOTIENT_BINARY
+    gcc = shutil.which('gcc') or shutil.which('cc')
+    if gcc is None:
+        raise RuntimeError('gcc not found: oracle/quotient_check.c cannot be built')
+    os.makedirs(OUT_DIR, exist_ok=True)
+    flags = ['-O2', '-std=c99', '-ffp-contract=off']
+    try:
+        with open('/proc/cpuinfo') as handle:
+            if ' fma ' in handle.read():
+                flags.append('-mfma')   # hardware fma; libm's fma() computes the same, slowly
+    except OSError:
+        pass
+    result = subprocess.run([gcc] + flags + ['-o', QUOTIENT_BINARY, QUOTIENT_SOURCE, '-lm'],
+                            capture_output=True, text=True)
+    if result.returncode != 0:
+        raise RuntimeError('gcc failed:\n' + result.stdout + result.stderr)
+    return QUOTIENT_BINARY
+
+
 _lib = None
 
 
@@ -45,3 +73,4 @@ def library():
 
 if __name__ == '__main__':
     print(build(force=True))
+    print(build_quotient_check(force=True))

@@ -4,31 +4,30 @@ pyfds_b200/csrc/fds_streamv.cuh) against the IEEE division the reference uses
 same operations (one rounded multiply, two fused multiply-adds) over the ranges the kernel admits."""
 
 import os
-import shutil
 import subprocess
+import sys
 
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 SOURCE = os.path.join(ROOT, 'oracle', 'quotient_check.c')
-BINARY = os.path.join(ROOT, 'oracle', '_ref', 'quotient_check')
 
 
 def _build():
-    gcc = shutil.which('gcc') or shutil.which('cc')
-    if gcc is None:
-        pytest.skip('gcc not found')
-    os.makedirs(os.path.dirname(BINARY), exist_ok=True)
-    flags = ['-O2', '-std=c99', '-ffp-contract=off']
-    with open('/proc/cpuinfo') as handle:
-        if ' fma ' in handle.read():
-            flags.append('-mfma')       # hardware fma; libm's fma() computes the same, slowly
-    subprocess.run([gcc] + flags + ['-o', BINARY, SOURCE, '-lm'], check=True)
+    from oracle import cbuild
+    try:
+        return cbuild.build_quotient_check()
+    except RuntimeError as error:
+        if 'gcc not found' in str(error):
+            pytest.skip('gcc not found')
+        raise
 
 
 def test_quotient_sequence_equals_ieee_division():
-    _build()
-    result = subprocess.run([BINARY, '2000000'], capture_output=True, text=True, timeout=600)
+    binary = _build()
+    result = subprocess.run([binary, '2000000'], capture_output=True, text=True, timeout=600)
     assert result.returncode == 0, result.stdout
     cases, mismatches = [int(result.stdout.split()[k]) for k in (-3, -1)]
     assert cases > 30_000_000 and mismatches == 0, result.stdout
