@@ -15,6 +15,10 @@
   same run, with its own roofline record.
 * ``config5`` -- BASELINE.json configs[4]: ``weak`` = 32768 x 4096 cells per GPU (a 32768 x 4096 N
   grid), ``strong`` = ONE 32768 x 32768 grid cut into N slabs (on one GPU as well: 51.5 GB).
+* ``other_models`` (N = 1) -- the remaining single-GPU entries of BASELINE.json ``configs``, device
+  resident, through ``benchmarks/configs.py``: configs[2] (Acoustic3DAxi 8192 x 4096 with lossy
+  regions), configs[3] (Thermal2D 8192 x 8192), and the lossy twin of configs[1]. Parity-test
+  cases, not bench lines: they are reported so that their kernels' rates are driver-run numbers.
 * ``parity`` (N > 1) -- a 4096 x (512 N) grid stepped as N slabs and, on every rank, as one grid on
   that rank's GPU; true if every rank's rows and all probe records are bitwise equal.
 * ``e2e`` -- the same K steps through the public API (``field.simulate(K)``): host arrays in, host
@@ -457,6 +461,22 @@ def measure_e2e(job, nx, rows, ny):
                         args.warmup, args.steps)}
 
 
+OTHER_MODELS = {'config3': 3, 'config4': 4, 'config6_lossy_twin_of_config2': 6}
+OTHER_MODEL_KEYS = ('model', 'grid', 'steps', 'ms_per_step', 'gcell_updates_per_s', 'kernel',
+                    'steps_per_launch', 'bytes_per_cell_update', 'algorithmic_gbs')
+
+
+def measure_other_model(number, steps=200, warmup=20):
+    """One of the other BASELINE.json configurations, device resident (CUDA-event time of `steps`
+    steps after `warmup`, random initial state): benchmarks/configs.py::run."""
+    bench_dir = os.path.join(ROOT, 'benchmarks')
+    if bench_dir not in sys.path:
+        sys.path.insert(0, bench_dir)
+    import configs
+    line = configs.run(number, steps, warmup)
+    return {key: line[key] for key in OTHER_MODEL_KEYS}
+
+
 def check_parity(job, nx=4096, rows=512, steps=26):
     """Multi-GPU against single-GPU, bit for bit: a 4096 x (512 N) grid with sources, walls and probes
     on slab seams is stepped as N slabs; every rank also steps the whole grid on its own GPU and
@@ -523,7 +543,10 @@ def main():
     parser.add_argument('--no-target', action='store_true', help='skip the 16384^2 record')
     parser.add_argument('--no-config5', action='store_true', help='skip the 32768-wide records')
     parser.add_argument('--no-parity', action='store_true', help='skip the multi-GPU parity check')
-    parser.add_argument('--only', default='', help='comma list: main,target,weak,strong,parity,e2e')
+    parser.add_argument('--no-other-models', action='store_true',
+                        help='skip configs 3, 4 and 6 (benchmarks/configs.py)')
+    parser.add_argument('--only', default='',
+                        help='comma list: main,target,weak,strong,parity,e2e,other')
     parser.add_argument('--no-wall', action='store_true', help='experiment: drop the x=0 rigid line')
     parser.add_argument('--strong', action='store_true',
                         help='make the headline value the strong-scaling one: ONE size x size grid '
@@ -581,6 +604,10 @@ def main():
     parity = None
     if world > 1 and wanted('parity', not args.no_parity):
         parity = sub_record(check_parity, job)
+    other_models = None
+    if world == 1 and rank == 0 and wanted('other', not args.no_other_models):
+        other_models = {name: sub_record(measure_other_model, number)
+                        for name, number in OTHER_MODELS.items()}
 
     cpu = None
     if not args.no_cpu_baseline and rank == 0 and world == 1:
@@ -607,7 +634,7 @@ def main():
             'roofline': main_record['roofline'],
             'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': main_record['gpu_launches'],
             'clocks': main_record.get('clocks'),
-            'target': target, 'config5': config5, 'parity': parity,
+            'target': target, 'config5': config5, 'other_models': other_models, 'parity': parity,
             'wall_seconds': time.perf_counter() - t_wall,
         }
         if parity is not None:

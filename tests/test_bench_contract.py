@@ -77,3 +77,28 @@ def test_product_arm_fails_loudly_without_a_gpu():
     assert result.returncode != 0
     assert not any(ln.lstrip().startswith('{') for ln in result.stdout.splitlines()), result.stdout
     assert fds is not None
+
+
+def test_other_models_record_keeps_the_documented_keys(monkeypatch):
+    """`other_models` of the product arm's line: what benchmarks/configs.py::run returns, reduced to
+    the documented keys (checked here with a stand-in for the GPU run)."""
+    import types
+    sys.path.insert(0, ROOT)
+    import bench
+    seen = []
+
+    def run(number, steps, warmup):
+        seen.append((number, steps, warmup))
+        return {'config': number, 'model': 'Acoustic3DAxi', 'grid': [8192, 4096], 'steps': steps,
+                'device_ms': 55.3, 'ms_per_step': 0.2765, 'wall_s': 0.06,
+                'gcell_updates_per_s': 121.4, 'kernel': 'streamv_kernel<acoustic3daxi,lossy>',
+                'launches': 100, 'steps_per_launch': 2, 'algorithmic_gbs': 5826.7,
+                'bytes_per_cell_update': 48, 'setup_s': 1.2, 'device_gb': 1.7}
+
+    monkeypatch.setitem(sys.modules, 'configs', types.SimpleNamespace(run=run))
+    record = bench.measure_other_model(3)
+    assert seen == [(3, 200, 20)]
+    assert set(record) == set(bench.OTHER_MODEL_KEYS)
+    assert record['gcell_updates_per_s'] == 121.4 and record['steps_per_launch'] == 2
+    assert sorted(bench.OTHER_MODELS.values()) == [3, 4, 6]
+    json.dumps(record)
