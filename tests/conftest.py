@@ -11,6 +11,9 @@ for path in (ROOT, os.path.join(ROOT, 'tests')):
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run with -m gpu on the B200 box)')
+    # the staged reference converts one-element arrays with int() (pyfds/fields.py:571)
+    config.addinivalue_line('filterwarnings',
+                            'ignore:Conversion of an array with ndim:DeprecationWarning')
 
 
 def _cuda_devices():
