@@ -302,8 +302,10 @@ int64_t fds_device_bytes(const fds_ctx *ctx);
 /* Diagnostics of the streaming kernel, accumulated since fds_create when the environment variable
  * FDS_STREAM_STATS is set (all zero otherwise): out[0..4] entries into the branch-free row-pair body
  * by variant (no boundary operation, constant operations on component 0 / 1 / 2, several materials),
- * out[5] rows that took the general row iteration, out[6] rows streamed in total. Test support: no
- * reference counterpart. */
+ * out[5] rows that took the general row iteration, out[6] rows streamed in total, out[7] row pairs of
+ * the lossy axisymmetric model that were stepped with the IEEE division because a numerator was
+ * outside the range of the quotient sequence (fds_streamv.cuh). Test support: no reference
+ * counterpart. */
 int fds_stream_stats(fds_ctx *ctx, int64_t out[8]);
 
 #ifdef __cplusplus

@@ -303,7 +303,8 @@ class Engine:
 
     def stream_stats(self):
         """Counters of the streaming kernel (all zero unless FDS_STREAM_STATS was set at creation):
-        entries into the branch-free body by variant [0..4], general rows [5], rows streamed [6]."""
+        entries into the branch-free body by variant [0..4], general rows [5], rows streamed [6], row
+        pairs of the lossy axisymmetric model stepped with the IEEE division [7]."""
         out = (ct.c_int64 * 8)()
         self._check(self.lib.fds_stream_stats(self.handle, out))
         return list(out)
