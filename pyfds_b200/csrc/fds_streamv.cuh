@@ -101,13 +101,14 @@ __device__ __forceinline__ bool sv_moderate(double b, unsigned range) {
     return e >= 1023u - range && e <= 1023u + range &&
            (u & 0xfffffffffffffull) != 0xfffffffffffffull;
 }
+// Build switches for A/B measurements (python -m pyfds_b200._build --variant NAME -DFDS_SV_...=0):
+// 0 = the IEEE division in every cell / the per-column coefficients in registers, as before round 2.
 #ifndef FDS_SV_FASTDIV
 #define FDS_SV_FASTDIV 1
 #endif
 #ifndef FDS_SV_COLSMEM
 #define FDS_SV_COLSMEM 1
 #endif
-
 
 // One stage on a steady row: `cur` = row q at level s on entry, row q-2 at level s+1 on exit.
 // pA/uA/vA = p (after boundaries), old vx, old vy of row q-1; pB/uB/vB = the same of row q-2 on entry
