@@ -165,3 +165,57 @@ def test_restatement_equals_the_reference_with_flow(pyfds, seed):
         field.simulate(steps)
     stepper.run(steps)
     assert_same(scenarios.collect_stepper(stepper), scenarios.collect(field), 'flow seed {}'.format(seed))
+
+
+# ---- the reference's documented usage (doc/ex_acoustics.rst, doc/usage.rst), scaled down --------------
+
+def documented_waveguide(package, steps=90):
+    """doc/ex_acoustics.rst:52-93 in the style the documentation uses -- ``boundaries.append(
+    Boundary(...))``, ``outputs.append(Output(...))``, ``max(fld.y.vector)``, a Gauss pulse built
+    from ``fld.t.vector`` -- on a grid a tenth of the documented size."""
+    fld = package.Acoustic3DAxi(t_delta=1e-6, t_samples=steps, x_delta=1e-3, x_samples=31,
+                                y_delta=1e-3, y_samples=91,
+                                material=package.AcousticMaterial(sound_velocity=700, density=1000,
+                                                                  shear_viscosity=1e-2))
+    t = fld.t.vector - 1.2e-5
+    ex_signal = np.exp(-(t / 4e-6) ** 2) * np.cos(2 * np.pi * 5e4 * t)
+    fld.velocity_x.add_boundary(fld.get_line_region((0, 0, 0, max(fld.y.vector))))
+    fld.velocity_x.boundaries.append(package.Boundary(
+        fld.get_line_region((20e-3, 0, 20e-3, max(fld.y.vector)))))
+    fld.pressure.boundaries.append(package.Boundary(
+        fld.get_line_region((0, 20e-3, 19e-3, 20e-3)), value=ex_signal, additive=True))
+    fld.pressure.outputs.append(package.Output(fld.get_line_region((0, 70e-3, 20e-3, 70e-3))))
+    return fld, steps
+
+
+def documented_line(package, steps=400):
+    """doc/ex_acoustics.rst:9-45: the 1-D pulse between a rigid and a pressure-release end."""
+    fld = package.Acoustic1D(t_delta=1e-7, t_samples=steps, x_delta=1e-3, x_samples=301,
+                             material=package.AcousticMaterial(sound_velocity=700, density=0.01,
+                                                               shear_viscosity=1e-3))
+    t = fld.t.vector - 0.1e-4
+    ex_signal = np.exp(-(t / 3e-6) ** 2) * np.cos(2 * np.pi * 1e5 * t)
+    fld.velocity.boundaries.append(package.Boundary(fld.get_point_region(0)))
+    fld.pressure.boundaries.append(package.Boundary(fld.get_point_region(max(fld.x.vector))))
+    fld.pressure.boundaries.append(package.Boundary(fld.get_point_region(0.1), value=ex_signal,
+                                                    additive=True))
+    fld.pressure.outputs.append(package.Output(fld.get_point_region(0.2)))
+    return fld, steps
+
+
+@pytest.mark.parametrize('builder', [documented_waveguide, documented_line])
+def test_documented_usage_builds_the_same_scenario_under_this_package(pyfds, builder):
+    """The script of the documentation, written once and run with either package: the reference
+    steps its own field; this package's field (same calls, same attribute names) is stepped by the
+    restatement. Equal bits mean the two packages built the same scenario out of the script."""
+    import pyfds_b200 as fds
+    theirs, steps = builder(pyfds)
+    ours, _ = builder(fds)
+    assert bool(ours.is_stable()) == bool(theirs.is_stable())
+    stepper = restate.stepper_for(ours).run(steps)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        theirs.simulate()                       # no argument: all t_samples steps (fields.py:74-75)
+    assert_same(scenarios.collect_stepper(stepper), scenarios.collect(theirs), builder.__name__)
+    mean = np.mean(stepper.signals('pressure')[0], axis=0)
+    assert np.array_equal(bits(mean), bits(theirs.pressure.outputs[0].mean_signal))
